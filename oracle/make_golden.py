@@ -1,0 +1,101 @@
+"""TEST INFRASTRUCTURE ONLY -- generate tests/golden/*.npz by running the REFERENCE's own code.
+
+Run in the build container (needs /root/reference):  python -m oracle.make_golden
+Each case = seeded synthetic inputs (tests/helpers.py) + seeded fresh-initialised weights pushed through the
+reference's unmodified ``TensorProductScoreModel.forward`` (models/score_model.py:259) or ``sampling()``
+(utils/sampling.py:49) behind the leaf-op shims, with ``torch.normal`` replaced by pre-drawn noise.  The
+files hold the reference outputs plus fingerprints of the inputs / weights so a replay on another box can
+tell "inputs drifted" from "math differs".
+"""
+from __future__ import annotations
+
+import copy
+import os
+import sys
+from functools import partial
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from disco_diffdock_b200 import data as ddata  # noqa: E402
+from disco_diffdock_b200.synthetic import as_loader_item  # noqa: E402
+from oracle import ref_loader, restate  # noqa: E402
+from tests import helpers  # noqa: E402
+
+CASES = {
+    # name: (model seed, gain, complex seed, n_lig, n_rec, B, steps, temps, latent_dim)
+    'forward_small': dict(mseed=0, gain=1.0, cseed=3, n_lig=20, n_rec=50, B=3, t=0.6, latent=0),
+    'forward_latent': dict(mseed=0, gain=1.0, cseed=3, n_lig=20, n_rec=50, B=3, t=0.35, latent=2),
+    'forward_cfg1': dict(mseed=2, gain=1.0, cseed=11, n_lig=60, n_rec=300, B=1, t=0.9, latent=0),
+    'sample_small': dict(mseed=1, gain=5.0, cseed=4, n_lig=14, n_rec=40, B=2, steps=8, temps=True, latent=0),
+    'sample_mid': dict(mseed=1, gain=5.0, cseed=6, n_lig=30, n_rec=80, B=3, steps=20, temps=True, latent=0),
+    'sample_cfg1': dict(mseed=2, gain=5.0, cseed=11, n_lig=60, n_rec=300, B=1, steps=20, temps=True, latent=0),
+}
+
+
+def fingerprint(sd):
+    return float(sum(v.double().abs().sum() for v in sd.values()))
+
+
+def forward_inputs(c):
+    m, sd, cfg = helpers.make_model(c['mseed'], latent_dim=c['latent'], latent_droprate=0.1 if c['latent'] else 0.0,
+                                    gain=c['gain'])
+    _, lst = helpers.make_pose_batch(c['cseed'], c['n_lig'], c['n_rec'], c['B'])
+    batch = ddata.Batch.from_data_list(lst)
+    restate.set_time(batch, c['t'], c['t'], c['t'], c['B'])
+    if c['latent']:
+        gen = torch.Generator().manual_seed(5)
+        for nt in ('ligand', 'receptor'):
+            batch[nt].latent_h = (torch.rand(batch[nt].num_nodes, c['latent'], generator=gen) > 0.9).float()
+            batch[nt].unconditional = (torch.rand(batch[nt].num_nodes, 1, generator=gen) > 0.5).float()
+    return m, sd, cfg, batch
+
+
+def sample_inputs(c):
+    m, sd, cfg = helpers.make_model(c['mseed'], gain=c['gain'])
+    g, lst = helpers.make_pose_batch(c['cseed'], c['n_lig'], c['n_rec'], c['B'])
+    R = g['ligand'].mask_rotate.shape[0]
+    noise = helpers.draw_noise(7, c['steps'], c['B'], R)
+    sched = np.linspace(1, 0, c['steps'] + 1)[:-1]
+    temps = helpers.README_TEMPS if c['temps'] else {}
+    return m, sd, cfg, lst, noise, sched, temps
+
+
+def main():
+    out_dir = os.path.join(ROOT, 'tests', 'golden')
+    os.makedirs(out_dir, exist_ok=True)
+    mods = ref_loader.modules()
+    for name, c in CASES.items():
+        if name.startswith('forward'):
+            m, sd, cfg, batch = forward_inputs(c)
+            ref_model, _ = ref_loader.build_reference_model(cfg, sd)
+            with torch.no_grad():
+                tr, rot, tor = ref_model(copy.deepcopy(batch))
+                lig_h, rec_h = ref_model.embed(copy.deepcopy(batch))[:2]
+            np.savez_compressed(os.path.join(out_dir, name + '.npz'), tr=tr.numpy(), rot=rot.numpy(), tor=tor.numpy(),
+                                lig_h=lig_h.numpy(), rec_h=rec_h.numpy(), weights_fp=fingerprint(sd),
+                                pos_fp=float(batch['ligand'].pos.double().abs().sum()),
+                                rec_fp=float(batch['receptor'].x.double().abs().sum()))
+        else:
+            m, sd, cfg, lst, noise, sched, temps = sample_inputs(c)
+            ref_model, args = ref_loader.build_reference_model(cfg, sd)
+            t2s = partial(mods.diffusion_utils.t_to_sigma, args=args)
+            ref_list = [as_loader_item(x) for x in copy.deepcopy(lst)]
+            with ref_loader.InjectedNormal(noise, c['steps']), torch.no_grad():
+                out_list, _ = mods.sampling.sampling(ref_list, SimpleNamespace(score_model=ref_model), c['steps'],
+                                                     sched, sched, sched, torch.device('cpu'), t2s, args,
+                                                     batch_size=c['B'], no_final_step_noise=False, **temps)
+            pos = torch.cat([x['ligand'].pos for x in out_list])
+            start = torch.cat([x['ligand'].pos for x in lst])
+            np.savez_compressed(os.path.join(out_dir, name + '.npz'), pos=pos.numpy(), weights_fp=fingerprint(sd),
+                                pos_fp=float(start.double().abs().sum()),
+                                rec_fp=float(lst[0]['receptor'].x.double().abs().sum()))
+        print('wrote', name)
+
+
+if __name__ == '__main__':
+    main()

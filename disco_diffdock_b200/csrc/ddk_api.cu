@@ -1,0 +1,487 @@
+// C ABI of libddk (include/ddk.h): context / batch management and the step drivers.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+
+#include "ddk_internal.h"
+
+using namespace ddk;
+
+namespace {
+
+std::string g_create_error;
+
+#define DDK_CUDA_TRY(ctx, expr)                                                                     \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess) {                                                                        \
+      (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(_e);                              \
+      return DDK_ERR_CUDA;                                                                          \
+    }                                                                                               \
+  } while (0)
+
+int fail(DdkCtx* c, int code, const std::string& msg) {
+  if (c) c->err = msg; else g_create_error = msg;
+  return code;
+}
+
+int ensure(DdkCtx* c, Buf& b, size_t bytes) {
+  if (bytes == 0) bytes = 16;
+  if (b.bytes >= bytes) return DDK_OK;
+  if (b.p) DDK_CUDA_TRY(c, cudaFree(b.p));
+  b.p = nullptr; b.bytes = 0;
+  size_t want = bytes + bytes / 8;   // a little head-room so slowly growing batches do not reallocate every time
+  cudaError_t e = cudaMalloc(&b.p, want);
+  if (e != cudaSuccess) { c->err = std::string("cudaMalloc: ") + cudaGetErrorString(e); return DDK_ERR_NOMEM; }
+  b.bytes = want;
+  return DDK_OK;
+}
+
+template <typename T>
+int upload(DdkCtx* c, Buf& b, const std::vector<T>& v, cudaStream_t st) {
+  int rc = ensure(c, b, v.size() * sizeof(T));
+  if (rc) return rc;
+  if (!v.empty()) DDK_CUDA_TRY(c, cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+  return DDK_OK;
+}
+
+void build_layers(DdkCtx* c) {
+  c->layers.clear();
+  for (int l = 0; l < c->cfg.num_conv_layers; ++l) {
+    int lin = std::min(l, 3), lout = std::min(l + 1, 3);
+    int mi0e = NS, mi1o = lin >= 1 ? NV : 0, mi1e = lin >= 2 ? NV : 0, mi0o = lin >= 3 ? NS : 0;
+    int mo[4] = {NS, lout >= 1 ? NV : 0, lout >= 2 ? NV : 0, lout >= 3 ? NS : 0};
+    int F[4] = {mi0e + mi1o, mi0e + mi1o + mi1e, mi1o + mi1e + mi0o, mi1e + mi0o};
+    int ncomp[4] = {1, 3, 3, 1}, col0[4] = {0, 24, 42, 60};
+    LayerInfo li{};
+    li.lv = lin;
+    li.dout = NS + 3 * mo[1] + 3 * mo[2] + mo[3];
+    int uoff = 0; int64_t woff = 0, boff = 0; li.ncls = 0;
+    for (int k = 0; k < 4; ++k) {
+      if (F[k] == 0 || mo[k] == 0) continue;
+      ClassInfo ci{};
+      ci.F = F[k]; ci.O = mo[k]; ci.ncomp = ncomp[k]; ci.uoff = uoff; ci.col0 = col0[k]; ci.woff = woff; ci.boff = boff;
+      li.cls[li.ncls++] = ci;
+      uoff += ncomp[k] * F[k];
+      woff += (int64_t)F[k] * HID * mo[k];
+      boff += (int64_t)F[k] * mo[k];
+    }
+    li.U = uoff;
+    li.NA = (uoff + 31) / 32;
+    c->layers.push_back(li);
+  }
+}
+
+void free_buf(Buf& b) {
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr; b.bytes = 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ddk_abi_version(void) { return DDK_ABI_VERSION; }
+
+const char* ddk_last_error(const DdkCtx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int ddk_create(const DdkConfig* cfg, const float* weights_h, size_t n_floats, const int64_t* offsets_h, int32_t n_offsets,
+               int32_t device, DdkCtx** out) {
+  if (!cfg || !weights_h || !offsets_h || !out) return fail(nullptr, DDK_ERR_INVALID, "null argument");
+  if (cfg->abi_version != DDK_ABI_VERSION) return fail(nullptr, DDK_ERR_INVALID, "ABI version mismatch");
+  if (cfg->ns != NS || cfg->nv != NV) return fail(nullptr, DDK_ERR_INVALID, "kernels are compiled for ns=24, nv=6");
+  if (cfg->num_conv_layers < 1 || cfg->num_conv_layers > 8) return fail(nullptr, DDK_ERR_INVALID, "num_conv_layers out of range");
+  if (cfg->latent_dim < 0 || cfg->latent_dim > 2) return fail(nullptr, DDK_ERR_INVALID, "latent_dim must be 0..2");
+  if (n_offsets != DDK_W_CONV_BASE + cfg->num_conv_layers * DDK_W_CONV_STRIDE)
+    return fail(nullptr, DDK_ERR_INVALID, "offset table has the wrong length");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, DDK_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(nullptr, DDK_ERR_INVALID, "device index out of range");
+  DdkCtx* c = new DdkCtx();
+  c->cfg = *cfg;
+  if (c->cfg.scratch_bytes <= 0) c->cfg.scratch_bytes = (int64_t)4 << 30;
+  c->device = device;
+  c->off.assign(offsets_h, offsets_h + n_offsets);
+  for (int64_t o : c->off)
+    if (o >= (int64_t)n_floats) { delete c; return fail(nullptr, DDK_ERR_INVALID, "offset beyond the weight blob"); }
+  double rl = cfg->lig_max_radius, rc = cfg->cross_max_distance;
+  c->r2_lig = (float)(rl * rl);
+  c->r2_cross = (float)(rc * rc);
+  build_layers(c);
+  auto bail = [&](const char* what, cudaError_t err) {
+    g_create_error = std::string(what) + ": " + cudaGetErrorString(err);
+    if (c->w) cudaFree(c->w);
+    delete c;
+    return DDK_ERR_CUDA;
+  };
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+  if ((e = cudaMalloc(&c->w, n_floats * sizeof(float))) != cudaSuccess) return bail("cudaMalloc(weights)", e);
+  if ((e = cudaMemcpy(c->w, weights_h, n_floats * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess)
+    return bail("cudaMemcpy(weights)", e);
+  if ((e = conv_configure()) != cudaSuccess) return bail("cudaFuncSetAttribute(conv)", e);
+  if ((e = heads_configure()) != cudaSuccess) return bail("cudaFuncSetAttribute(heads)", e);
+  *out = c;
+  return DDK_OK;
+}
+
+int ddk_destroy(DdkCtx* c) {
+  if (!c) return DDK_OK;
+  cudaSetDevice(c->device);
+  Buf* all[] = {&c->b_lig_ptr, &c->b_rec_ptr, &c->b_lig_graph, &c->b_rec_graph, &c->b_bond_src, &c->b_bond_dst, &c->b_rr_src,
+                &c->b_rr_dst, &c->b_rot_u, &c->b_rot_v, &c->b_rot_ptr, &c->b_rot_graph, &c->b_mr_off, &c->b_ll_off,
+                &c->b_lr_off, &c->b_seg_base, &c->b_seg_static, &c->b_seg_cnt, &c->b_seg_list, &c->b_seg_order,
+                &c->b_seg_sidx, &c->b_lig_static, &c->b_rec_static, &c->b_rr_pre, &c->b_ea_pool, &c->b_sh_pool, &c->b_tb,
+                &c->b_xa, &c->b_xb, &c->b_proj, &c->b_A, &c->b_Bsum, &c->b_tr, &c->b_rot, &c->b_tor, &c->b_pos, &c->b_step};
+  for (Buf* b : all) free_buf(*b);
+  if (c->w) cudaFree(c->w);
+  delete c;
+  return DDK_OK;
+}
+
+int ddk_set_batch(DdkCtx* c, const DdkBatch* b, void* stream) {
+  if (!c || !b) return DDK_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  DDK_CUDA_TRY(c, cudaSetDevice(c->device));
+  c->has_batch = false;
+  if (b->B <= 0 || b->NL <= 0 || b->NR <= 0) return fail(c, DDK_ERR_INVALID, "empty batch");
+  if (!b->lig_ptr_h || !b->rec_ptr_h || !b->bond_ptr_h || !b->rec_edge_ptr_h || !b->lig_x || !b->rec_x || !b->rec_pos)
+    return fail(c, DDK_ERR_INVALID, "missing batch arrays");
+  if (b->EB > 0 && (!b->bond_index_h || !b->edge_mask_h || !b->bond_attr)) return fail(c, DDK_ERR_INVALID, "missing bond arrays");
+  if (b->ER > 0 && !b->rec_index_h) return fail(c, DDK_ERR_INVALID, "missing receptor edges");
+  if (c->cfg.latent_dim > 0 && (!b->lig_latent || !b->rec_latent)) return fail(c, DDK_ERR_INVALID, "latents required");
+  if (b->lig_ptr_h[b->B] != b->NL || b->rec_ptr_h[b->B] != b->NR || b->bond_ptr_h[b->B] != b->EB ||
+      b->rec_edge_ptr_h[b->B] != b->ER)
+    return fail(c, DDK_ERR_INVALID, "ptr arrays do not match the totals");
+  const int B = b->B, NL = b->NL, NR = b->NR, EB = b->EB, ER = b->ER;
+  c->B = B; c->NL = NL; c->NR = NR; c->EB = EB; c->ER = ER; c->N = NL + NR;
+  c->rec_pos = b->rec_pos; c->mask_rotate = b->mask_rotate; c->bond_attr = b->bond_attr;
+  c->lig_latent = b->lig_latent; c->rec_latent = b->rec_latent;
+  c->lig_uncond = b->lig_uncond; c->rec_uncond = b->rec_uncond;
+
+  std::vector<int> lig_ptr(b->lig_ptr_h, b->lig_ptr_h + B + 1), rec_ptr(b->rec_ptr_h, b->rec_ptr_h + B + 1);
+  std::vector<int> lig_graph(NL), rec_graph(NR);
+  std::vector<int64_t> ll_off(B), lr_off(B);
+  int64_t LL = 0, LR = 0;
+  c->maxNl = 0; c->maxNr = 0;
+  for (int g = 0; g < B; ++g) {
+    int nl = lig_ptr[g + 1] - lig_ptr[g], nr = rec_ptr[g + 1] - rec_ptr[g];
+    if (nl <= 0 || nr <= 0) return fail(c, DDK_ERR_INVALID, "graph without ligand atoms or residues");
+    for (int n = lig_ptr[g]; n < lig_ptr[g + 1]; ++n) lig_graph[n] = g;
+    for (int n = rec_ptr[g]; n < rec_ptr[g + 1]; ++n) rec_graph[n] = g;
+    ll_off[g] = LL; lr_off[g] = LR;
+    LL += (int64_t)nl * nl; LR += (int64_t)nl * nr;
+    c->maxNl = std::max(c->maxNl, nl); c->maxNr = std::max(c->maxNr, nr);
+  }
+  c->LLtot = LL; c->LRtot = LR;
+  c->slot_ll = EB; c->slot_lr = EB + LL; c->slot_rr = EB + LL + LR; c->P = c->slot_rr + ER;
+  if (c->P >= ((int64_t)1 << 31)) return fail(c, DDK_ERR_INVALID, "batch too large for 32-bit edge slots");
+
+  // bonds, rotatable bonds
+  std::vector<int> bond_src(b->bond_index_h, b->bond_index_h + EB), bond_dst(b->bond_index_h + EB, b->bond_index_h + 2 * EB);
+  std::vector<int> rr_src(b->rec_index_h, b->rec_index_h + ER), rr_dst(b->rec_index_h + ER, b->rec_index_h + 2 * ER);
+  std::vector<int> rot_u, rot_v, rot_ptr(B + 1, 0);
+  for (int g = 0; g < B; ++g) {
+    for (int e = b->bond_ptr_h[g]; e < b->bond_ptr_h[g + 1]; ++e) {
+      if (bond_src[e] < lig_ptr[g] || bond_src[e] >= lig_ptr[g + 1] || bond_dst[e] < lig_ptr[g] || bond_dst[e] >= lig_ptr[g + 1])
+        return fail(c, DDK_ERR_INVALID, "bond crosses a graph boundary");
+      if (b->edge_mask_h[e]) { rot_u.push_back(bond_src[e]); rot_v.push_back(bond_dst[e]); }
+    }
+    rot_ptr[g + 1] = (int)rot_u.size();
+  }
+  c->RB = (int)rot_u.size();
+  if (b->RB != c->RB) return fail(c, DDK_ERR_INVALID, "RB does not match edge_mask");
+  if (c->RB > 0 && !c->cfg.no_torsion && (!b->mask_rotate || !b->mask_rotate_off_h))
+    return fail(c, DDK_ERR_INVALID, "mask_rotate required");
+  std::vector<int64_t> mr_off(B, 0);
+  if (b->mask_rotate_off_h) mr_off.assign(b->mask_rotate_off_h, b->mask_rotate_off_h + B);
+  for (int e = 0; e < ER; ++e) {
+    int g = rec_graph[std::min(std::max(rr_src[e], 0), NR - 1)];
+    if (rr_src[e] < 0 || rr_src[e] >= NR || rr_dst[e] < rec_ptr[g] || rr_dst[e] >= rec_ptr[g + 1])
+      return fail(c, DDK_ERR_INVALID, "receptor edge crosses a graph boundary");
+  }
+
+  // segments: (node, group) -> list of (edge slot, destination node)
+  const int nsegs = 2 * (NL + NR);
+  std::vector<int> seg_static(nsegs, 0), seg_cap(nsegs, 0), seg_base(nsegs + 1, 0);
+  for (int e = 0; e < EB; ++e) seg_static[2 * bond_src[e]]++;
+  for (int e = 0; e < ER; ++e) seg_static[2 * (NL + rr_src[e])]++;
+  for (int n = 0; n < NL; ++n) {
+    int g = lig_graph[n], nl = lig_ptr[g + 1] - lig_ptr[g], nr = rec_ptr[g + 1] - rec_ptr[g];
+    seg_cap[2 * n] = seg_static[2 * n] + nl - 1;
+    seg_cap[2 * n + 1] = nr;
+  }
+  for (int r = 0; r < NR; ++r) {
+    int g = rec_graph[r], nl = lig_ptr[g + 1] - lig_ptr[g];
+    seg_cap[2 * (NL + r)] = seg_static[2 * (NL + r)];
+    seg_cap[2 * (NL + r) + 1] = nl;
+  }
+  int64_t total = 0;
+  for (int s = 0; s < nsegs; ++s) { seg_base[s] = (int)total; total += seg_cap[s]; }
+  if (total >= ((int64_t)1 << 31)) return fail(c, DDK_ERR_INVALID, "batch too large for 32-bit list offsets");
+  c->list_total = total;
+  std::vector<int2> seg_list((size_t)std::max<int64_t>(total, 1), make_int2(0, 0));
+  {
+    std::vector<int> fill(nsegs, 0);
+    for (int e = 0; e < EB; ++e) { int s = 2 * bond_src[e]; seg_list[seg_base[s] + fill[s]++] = make_int2(e, bond_dst[e]); }
+    for (int e = 0; e < ER; ++e) {
+      int s = 2 * (NL + rr_src[e]);
+      seg_list[seg_base[s] + fill[s]++] = make_int2((int)(c->slot_rr + e), NL + rr_dst[e]);
+    }
+  }
+  // chunks of graphs bounded by the outer-product scratch; LPT-ish order inside a chunk (largest groups first)
+  int Umax = 0;
+  for (const LayerInfo& li : c->layers) Umax = std::max(Umax, li.U);
+  const int64_t seg_bytes = (int64_t)Umax * HID * sizeof(float);
+  const int64_t max_segs = std::max<int64_t>(c->cfg.scratch_bytes / seg_bytes, 2 * (c->maxNl + c->maxNr));
+  c->chunks.clear();
+  std::vector<int> seg_order, seg_sidx(nsegs, 0);
+  int64_t max_chunk_segs = 0;
+  for (int g = 0; g < B;) {
+    Chunk ch{};
+    ch.g0 = g;
+    int64_t segs = 0;
+    while (g < B) {
+      int64_t add = 2 * ((lig_ptr[g + 1] - lig_ptr[g]) + (rec_ptr[g + 1] - rec_ptr[g]));
+      if (segs > 0 && segs + add > max_segs) break;
+      segs += add;
+      ++g;
+    }
+    ch.g1 = g;
+    ch.lig0 = lig_ptr[ch.g0]; ch.lig1 = lig_ptr[ch.g1]; ch.rec0 = rec_ptr[ch.g0]; ch.rec1 = rec_ptr[ch.g1];
+    ch.nseg = (int)segs;
+    ch.order_off = (int)seg_order.size();
+    const int nlc = ch.lig1 - ch.lig0;
+    for (int n = ch.lig0; n < ch.lig1; ++n) seg_order.push_back(2 * n + 1);                  // group 1 (largest)
+    for (int r = ch.rec0; r < ch.rec1; ++r) seg_order.push_back(2 * (NL + r) + 1);           // group 3
+    for (int r = ch.rec0; r < ch.rec1; ++r) seg_order.push_back(2 * (NL + r));               // group 2
+    for (int n = ch.lig0; n < ch.lig1; ++n) seg_order.push_back(2 * n);                      // group 0
+    for (int n = ch.lig0; n < ch.lig1; ++n) { seg_sidx[2 * n] = 2 * (n - ch.lig0); seg_sidx[2 * n + 1] = 2 * (n - ch.lig0) + 1; }
+    for (int r = ch.rec0; r < ch.rec1; ++r) {
+      seg_sidx[2 * (NL + r)] = 2 * nlc + 2 * (r - ch.rec0);
+      seg_sidx[2 * (NL + r) + 1] = 2 * nlc + 2 * (r - ch.rec0) + 1;
+    }
+    max_chunk_segs = std::max<int64_t>(max_chunk_segs, segs);
+    c->chunks.push_back(ch);
+  }
+
+  int rc;
+#define UP(buf, vec) if ((rc = upload(c, buf, vec, st)) != DDK_OK) return rc
+  UP(c->b_lig_ptr, lig_ptr); UP(c->b_rec_ptr, rec_ptr); UP(c->b_lig_graph, lig_graph); UP(c->b_rec_graph, rec_graph);
+  UP(c->b_bond_src, bond_src); UP(c->b_bond_dst, bond_dst); UP(c->b_rr_src, rr_src); UP(c->b_rr_dst, rr_dst);
+  UP(c->b_rot_u, rot_u); UP(c->b_rot_v, rot_v); UP(c->b_rot_ptr, rot_ptr); UP(c->b_mr_off, mr_off);
+  UP(c->b_ll_off, ll_off); UP(c->b_lr_off, lr_off);
+  seg_base.resize(nsegs);
+  UP(c->b_seg_base, seg_base); UP(c->b_seg_static, seg_static); UP(c->b_seg_cnt, seg_static); UP(c->b_seg_list, seg_list);
+  UP(c->b_seg_order, seg_order); UP(c->b_seg_sidx, seg_sidx);
+#undef UP
+#define EN(buf, bytes) if ((rc = ensure(c, buf, (size_t)(bytes))) != DDK_OK) return rc
+  EN(c->b_lig_static, (size_t)NL * NS * 4); EN(c->b_rec_static, (size_t)NR * NS * 4); EN(c->b_rr_pre, (size_t)ER * EA * 4);
+  EN(c->b_ea_pool, (size_t)c->P * EA * 4); EN(c->b_sh_pool, (size_t)c->P * 16);
+  EN(c->b_tb, (size_t)B * TB_COUNT * NS * 4);
+  EN(c->b_xa, (size_t)c->N * D * 4); EN(c->b_xb, (size_t)c->N * D * 4); EN(c->b_proj, (size_t)c->N * 4 * HID * 4);
+  EN(c->b_A, (size_t)max_chunk_segs * seg_bytes); EN(c->b_Bsum, (size_t)max_chunk_segs * Umax * 4);
+  EN(c->b_tr, (size_t)B * 3 * 4); EN(c->b_rot, (size_t)B * 3 * 4); EN(c->b_tor, (size_t)std::max(c->RB, 1) * 4);
+#undef EN
+  launch_setup(c, b, b->lig_x, b->rec_x, st);
+  DDK_CUDA_TRY(c, cudaGetLastError());
+  DDK_CUDA_TRY(c, cudaStreamSynchronize(st));   // host vectors above go out of scope
+  c->has_batch = true;
+  c->x_final = nullptr;
+  return DDK_OK;
+}
+
+static int run_embed(DdkCtx* c, const float* lig_pos, const DdkStepInputs* in, cudaStream_t st) {
+  launch_step_consts(c, in->sigma_emb, st);
+  launch_build_lists(c, lig_pos, in->cross_cutoff, st);
+  launch_edge_features(c, lig_pos, st);
+  float* xa = ptr<float>(c->b_xa);
+  float* xb = ptr<float>(c->b_xb);
+  launch_node_proj(c, 0, nullptr, xa, st);
+  float* xin = xa; float* xout = xb;
+  for (int l = 0; l < c->cfg.num_conv_layers; ++l) {
+    launch_conv_layer(c, l, xin, xout, st);
+    if (l + 1 < c->cfg.num_conv_layers) launch_node_proj(c, l + 1, xout, nullptr, st);
+    std::swap(xin, xout);
+  }
+  c->x_final = xin;
+  return DDK_OK;
+}
+
+static int check_step(DdkCtx* c, const float* lig_pos, const DdkStepInputs* in) {
+  if (!c || !lig_pos || !in) return DDK_ERR_INVALID;
+  if (!c->has_batch) return fail(c, DDK_ERR_STATE, "ddk_set_batch has not been called");
+  if (!in->sigma_emb || !in->tr_sigma || !in->rot_scale || (c->cfg.dynamic_max_cross && !in->cross_cutoff))
+    return fail(c, DDK_ERR_INVALID, "missing step inputs");
+  if (c->RB > 0 && !c->cfg.no_torsion && !in->tor_scale) return fail(c, DDK_ERR_INVALID, "missing tor_scale");
+  return DDK_OK;
+}
+
+int ddk_embed(DdkCtx* c, const float* lig_pos, const DdkStepInputs* in, void* stream) {
+  int rc = check_step(c, lig_pos, in);
+  if (rc) return rc;
+  DDK_CUDA_TRY(c, cudaSetDevice(c->device));
+  run_embed(c, lig_pos, in, (cudaStream_t)stream);
+  DDK_CUDA_TRY(c, cudaGetLastError());
+  return DDK_OK;
+}
+
+int ddk_score(DdkCtx* c, const float* lig_pos, const DdkStepInputs* in, float* tr, float* rot, float* tor, void* stream) {
+  int rc = check_step(c, lig_pos, in);
+  if (rc) return rc;
+  if (!tr || !rot) return fail(c, DDK_ERR_INVALID, "null output");
+  cudaStream_t st = (cudaStream_t)stream;
+  DDK_CUDA_TRY(c, cudaSetDevice(c->device));
+  run_embed(c, lig_pos, in, st);
+  launch_head_trrot(c, lig_pos, c->x_final, in, tr, rot, st);
+  if (tor) launch_head_tor(c, lig_pos, c->x_final, in, tor, st);
+  DDK_CUDA_TRY(c, cudaGetLastError());
+  return DDK_OK;
+}
+
+int ddk_get_node_features(DdkCtx* c, float* lig_out, float* rec_out, void* stream) {
+  if (!c || !c->has_batch || !c->x_final) return fail(c, DDK_ERR_STATE, "no embedding available");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (lig_out) DDK_CUDA_TRY(c, cudaMemcpyAsync(lig_out, c->x_final, (size_t)c->NL * D * 4, cudaMemcpyDeviceToDevice, st));
+  if (rec_out)
+    DDK_CUDA_TRY(c, cudaMemcpyAsync(rec_out, c->x_final + (size_t)c->NL * D, (size_t)c->NR * D * 4, cudaMemcpyDeviceToDevice, st));
+  return DDK_OK;
+}
+
+int ddk_update(DdkCtx* c, float* lig_pos, const float* tr, const float* rot, const float* tor, const float* z_tr,
+               const float* z_rot, const float* z_tor, const DdkStepCoef* coef_h, void* stream) {
+  if (!c || !lig_pos || !tr || !rot || !coef_h) return DDK_ERR_INVALID;
+  if (!c->has_batch) return fail(c, DDK_ERR_STATE, "ddk_set_batch has not been called");
+  DDK_CUDA_TRY(c, cudaSetDevice(c->device));
+  launch_update(c, lig_pos, tr, rot, tor, z_tr, z_rot, z_tor, *coef_h, (cudaStream_t)stream);
+  DDK_CUDA_TRY(c, cudaGetLastError());
+  return DDK_OK;
+}
+
+int ddk_sample(DdkCtx* c, float* lig_pos, int32_t n_steps, const DdkStepInputs* si, const float* z_tr, const float* z_rot,
+               const float* z_tor, const DdkStepCoef* coef_h, void* stream) {
+  int rc = check_step(c, lig_pos, si);
+  if (rc) return rc;
+  if (n_steps <= 0 || !coef_h) return fail(c, DDK_ERR_INVALID, "bad step count / coefficients");
+  cudaStream_t st = (cudaStream_t)stream;
+  DDK_CUDA_TRY(c, cudaSetDevice(c->device));
+  float* tr = ptr<float>(c->b_tr);
+  float* rot = ptr<float>(c->b_rot);
+  float* tor = (c->RB > 0 && !c->cfg.no_torsion) ? ptr<float>(c->b_tor) : nullptr;
+  for (int s = 0; s < n_steps; ++s) {
+    DdkStepInputs in;
+    in.sigma_emb = si->sigma_emb + (size_t)s * c->B * SE;
+    in.cross_cutoff = si->cross_cutoff ? si->cross_cutoff + (size_t)s * c->B : nullptr;
+    in.tr_sigma = si->tr_sigma + (size_t)s * c->B;
+    in.rot_scale = si->rot_scale + (size_t)s * c->B;
+    in.tor_scale = si->tor_scale ? si->tor_scale + (size_t)s * c->B : nullptr;
+    run_embed(c, lig_pos, &in, st);
+    launch_head_trrot(c, lig_pos, c->x_final, &in, tr, rot, st);
+    if (tor) launch_head_tor(c, lig_pos, c->x_final, &in, tor, st);
+    launch_update(c, lig_pos, tr, rot, tor, z_tr ? z_tr + (size_t)s * c->B * 3 : nullptr,
+                  z_rot ? z_rot + (size_t)s * c->B * 3 : nullptr, (z_tor && tor) ? z_tor + (size_t)s * c->RB : nullptr,
+                  coef_h[s], st);
+  }
+  DDK_CUDA_TRY(c, cudaGetLastError());
+  return DDK_OK;
+}
+
+int ddk_sample_host(DdkCtx* c, float* lig_pos_h, int32_t n_steps, const DdkStepInputs* si_h, const float* z_tr_h,
+                    const float* z_rot_h, const float* z_tor_h, const DdkStepCoef* coef_h) {
+  if (!c || !lig_pos_h || !si_h) return DDK_ERR_INVALID;
+  if (!c->has_batch) return fail(c, DDK_ERR_STATE, "ddk_set_batch has not been called");
+  if (n_steps <= 0) return fail(c, DDK_ERR_INVALID, "bad step count");
+  DDK_CUDA_TRY(c, cudaSetDevice(c->device));
+  cudaStream_t st = 0;
+  const size_t B = c->B, S = n_steps;
+  const size_t n_emb = S * B * SE, n_b = S * B, n_z3 = S * B * 3, n_zt = S * (size_t)c->RB, n_pos = (size_t)c->NL * 3;
+  size_t total = n_emb + 4 * n_b + 2 * n_z3 + n_zt + n_pos;
+  int rc = ensure(c, c->b_step, total * sizeof(float));
+  if (rc) return rc;
+  float* base = ptr<float>(c->b_step);
+  float* d_emb = base; float* d_cut = d_emb + n_emb; float* d_trs = d_cut + n_b; float* d_rot = d_trs + n_b;
+  float* d_tor = d_rot + n_b; float* d_ztr = d_tor + n_b; float* d_zrot = d_ztr + n_z3; float* d_ztor = d_zrot + n_z3;
+  float* d_pos = d_ztor + n_zt;
+  auto h2d = [&](float* dst, const float* src, size_t n) -> cudaError_t {
+    if (!src || n == 0) return cudaSuccess;
+    return cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyHostToDevice, st);
+  };
+  DDK_CUDA_TRY(c, h2d(d_emb, si_h->sigma_emb, n_emb));
+  DDK_CUDA_TRY(c, h2d(d_cut, si_h->cross_cutoff, n_b));
+  DDK_CUDA_TRY(c, h2d(d_trs, si_h->tr_sigma, n_b));
+  DDK_CUDA_TRY(c, h2d(d_rot, si_h->rot_scale, n_b));
+  DDK_CUDA_TRY(c, h2d(d_tor, si_h->tor_scale, n_b));
+  DDK_CUDA_TRY(c, h2d(d_ztr, z_tr_h, n_z3));
+  DDK_CUDA_TRY(c, h2d(d_zrot, z_rot_h, n_z3));
+  DDK_CUDA_TRY(c, h2d(d_ztor, z_tor_h, n_zt));
+  DDK_CUDA_TRY(c, h2d(d_pos, lig_pos_h, n_pos));
+  DdkStepInputs si;
+  si.sigma_emb = d_emb; si.cross_cutoff = si_h->cross_cutoff ? d_cut : nullptr; si.tr_sigma = d_trs; si.rot_scale = d_rot;
+  si.tor_scale = si_h->tor_scale ? d_tor : nullptr;
+  rc = ddk_sample(c, d_pos, n_steps, &si, z_tr_h ? d_ztr : nullptr, z_rot_h ? d_zrot : nullptr, z_tor_h ? d_ztor : nullptr,
+                  coef_h, st);
+  if (rc) return rc;
+  DDK_CUDA_TRY(c, cudaMemcpyAsync(lig_pos_h, d_pos, n_pos * sizeof(float), cudaMemcpyDeviceToHost, st));
+  DDK_CUDA_TRY(c, cudaStreamSynchronize(st));
+  return DDK_OK;
+}
+
+int64_t ddk_kernel_launches(const DdkCtx* c) { return c ? c->launches : 0; }
+
+int64_t ddk_last_edge_count(DdkCtx* c) {
+  if (!c || !c->has_batch) return -1;
+  cudaSetDevice(c->device);
+  int nsegs = 2 * (c->NL + c->NR);
+  std::vector<int> cnt(nsegs);
+  if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+  if (cudaMemcpy(cnt.data(), c->b_seg_cnt.p, nsegs * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  int64_t t = 0;
+  for (int v : cnt) t += v;
+  return t;
+}
+
+int ddk_debug_read(DdkCtx* c, const char* name, void* dst_h, size_t max_bytes, size_t* n_bytes) {
+  if (!c || !name || !c->has_batch) return DDK_ERR_INVALID;
+  cudaSetDevice(c->device);
+  const void* src = nullptr;
+  size_t n = 0;
+  std::string s(name);
+  const int nsegs = 2 * (c->NL + c->NR);
+  if (s == "x_final") { src = c->x_final; n = (size_t)c->N * D * 4; }
+  else if (s == "xa") { src = c->b_xa.p; n = (size_t)c->N * D * 4; }
+  else if (s == "xb") { src = c->b_xb.p; n = (size_t)c->N * D * 4; }
+  else if (s == "proj") { src = c->b_proj.p; n = (size_t)c->N * 4 * HID * 4; }
+  else if (s == "tb") { src = c->b_tb.p; n = (size_t)c->B * TB_COUNT * NS * 4; }
+  else if (s == "seg_cnt") { src = c->b_seg_cnt.p; n = (size_t)nsegs * 4; }
+  else if (s == "seg_base") { src = c->b_seg_base.p; n = (size_t)nsegs * 4; }
+  else if (s == "seg_list") { src = c->b_seg_list.p; n = (size_t)c->list_total * 8; }
+  else if (s == "ea_pool") { src = c->b_ea_pool.p; n = (size_t)c->P * EA * 4; }
+  else if (s == "sh_pool") { src = c->b_sh_pool.p; n = (size_t)c->P * 16; }
+  else if (s == "lig_static") { src = c->b_lig_static.p; n = (size_t)c->NL * NS * 4; }
+  else if (s == "rec_static") { src = c->b_rec_static.p; n = (size_t)c->NR * NS * 4; }
+  else if (s == "tr") { src = c->b_tr.p; n = (size_t)c->B * 12; }
+  else if (s == "rot") { src = c->b_rot.p; n = (size_t)c->B * 12; }
+  else if (s == "tor") { src = c->b_tor.p; n = (size_t)c->RB * 4; }
+  else return fail(c, DDK_ERR_INVALID, "unknown debug buffer " + s);
+  if (n_bytes) *n_bytes = n;
+  if (!dst_h) return DDK_OK;
+  if (!src) return fail(c, DDK_ERR_STATE, "buffer not available yet");
+  DDK_CUDA_TRY(c, cudaDeviceSynchronize());
+  DDK_CUDA_TRY(c, cudaMemcpy(dst_h, src, std::min(n, max_bytes), cudaMemcpyDeviceToHost));
+  return DDK_OK;
+}
+
+int ddk_host_kabsch(const float* a_h, const float* b_h, int32_t n, float* R9_h, float* t3_h) {
+  if (!a_h || !b_h || n <= 0 || !R9_h || !t3_h) return DDK_ERR_INVALID;
+  host_kabsch(a_h, b_h, n, R9_h, t3_h);
+  return DDK_OK;
+}
+
+int ddk_host_axis_angle_to_matrix(const float* aa, float* R9_h) {
+  if (!aa || !R9_h) return DDK_ERR_INVALID;
+  host_axis_angle(aa, R9_h);
+  return DDK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,116 @@
+// Internal declarations shared by the libddk translation units (not part of the C ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/ddk.h"
+
+namespace ddk {
+
+constexpr int NS = 24;          // scalar multiplicity (ns)
+constexpr int NV = 6;           // vector multiplicity (nv)
+constexpr int D = 84;           // node feature width: [0e 24 | 1o 6x3 | 1e 6x3 | 0o 24]
+constexpr int HID = 72;         // radial MLP width (3 ns)
+constexpr int SE = 32;          // sigma embedding width
+constexpr int DE = 32;          // distance embedding width
+constexpr int ESM = 1280;
+constexpr int REC_X = 1 + ESM;  // receptor row: amino-acid index + ESM embedding
+constexpr int LIG_CAT = 16;
+constexpr int EA = 24;          // edge embedding width (ns)
+
+// per-graph per-step bias vectors derived from the sigma embedding (k_step_consts)
+enum { TB_LIG_NODE = 0, TB_REC_NODE, TB_LIG_EDGE, TB_REC_EDGE, TB_CROSS_EDGE, TB_CENTER, TB_TR_FINAL, TB_ROT_FINAL, TB_COUNT };
+
+struct ClassInfo {   // one irrep class of a conv layer's output (0e, 1o, 1e, 0o)
+  int F, O, ncomp, uoff, col0;
+  int64_t woff, boff;  // offsets inside the packed W2p / b2p of a group
+};
+
+struct LayerInfo {
+  int lv;            // basis level = min(layer, 3)
+  int U;             // basis size
+  int NA;            // ceil(U / 32)
+  int dout;          // valid output width (24, 42, 60, 84)
+  ClassInfo cls[4];
+  int ncls;
+};
+
+struct Chunk {       // a contiguous range of graphs processed through one accumulate / contract pass
+  int g0, g1;
+  int lig0, lig1, rec0, rec1;
+  int nseg;
+  int order_off;     // offset into seg_order
+};
+
+struct Buf {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
+}  // namespace ddk
+
+struct DdkCtx {
+  DdkConfig cfg;
+  int device = 0;
+  std::string err;
+  float* w = nullptr;                 // device weight blob
+  std::vector<int64_t> off;           // offsets (floats)
+  int64_t launches = 0;
+  std::vector<ddk::LayerInfo> layers;
+  float r2_lig = 25.f, r2_cross = 6400.f;
+
+  // ---- batch (static) ----
+  bool has_batch = false;
+  int B = 0, NL = 0, NR = 0, EB = 0, ER = 0, RB = 0, N = 0;
+  int maxNl = 0, maxNr = 0, maxRot = 0;
+  int64_t LLtot = 0, LRtot = 0, P = 0, list_total = 0;
+  int64_t slot_ll = 0, slot_lr = 0, slot_rr = 0;
+  std::vector<ddk::Chunk> chunks;
+  const float* rec_pos = nullptr;     // caller memory (must stay alive while the batch is current)
+  const uint8_t* mask_rotate = nullptr;
+  const float* lig_latent = nullptr; const float* rec_latent = nullptr;
+  const float* lig_uncond = nullptr; const float* rec_uncond = nullptr;
+  const float* bond_attr = nullptr;
+
+  // device arrays owned by the context (grow-only)
+  ddk::Buf b_lig_ptr, b_rec_ptr, b_lig_graph, b_rec_graph, b_bond_src, b_bond_dst, b_rr_src, b_rr_dst;
+  ddk::Buf b_rot_u, b_rot_v, b_rot_ptr, b_rot_graph, b_mr_off, b_ll_off, b_lr_off;
+  ddk::Buf b_seg_base, b_seg_static, b_seg_cnt, b_seg_list, b_seg_order, b_seg_sidx;
+  ddk::Buf b_lig_static, b_rec_static, b_rr_pre, b_ea_pool, b_sh_pool, b_tb;
+  ddk::Buf b_xa, b_xb, b_proj, b_A, b_Bsum;
+  ddk::Buf b_tr, b_rot, b_tor, b_pos;
+  ddk::Buf b_step;                    // staging for ddk_sample_host
+  float* x_final = nullptr;           // points into xa or xb after the last conv layer
+};
+
+namespace ddk {
+
+inline const float* W(const DdkCtx* c, int id) { return c->w + c->off[id]; }
+inline int conv_id(int layer, int k) { return DDK_W_CONV_BASE + layer * DDK_W_CONV_STRIDE + k; }
+
+template <typename T>
+inline T* ptr(const Buf& b) { return reinterpret_cast<T*>(b.p); }
+
+cudaError_t conv_configure();
+cudaError_t heads_configure();
+void host_kabsch(const float* A, const float* Bp, int N, float* R9, float* t3);   // host build of the device routine (tests)
+void host_axis_angle(const float* aa, float* R9);   // opt-in dynamic shared memory sizes (once per process / device)
+
+// launchers (each enqueues on `st` and bumps ctx->launches)
+void launch_setup(DdkCtx* c, const DdkBatch* b, const int32_t* lig_x, const float* rec_x, cudaStream_t st);
+void launch_step_consts(DdkCtx* c, const float* sigma_emb, cudaStream_t st);
+void launch_build_lists(DdkCtx* c, const float* lig_pos, const float* cutoff, cudaStream_t st);
+void launch_edge_features(DdkCtx* c, const float* lig_pos, cudaStream_t st);
+void launch_node_proj(DdkCtx* c, int layer, const float* x_in, float* x0_out, cudaStream_t st);
+void launch_conv_layer(DdkCtx* c, int layer, const float* x_in, float* x_out, cudaStream_t st);
+void launch_head_trrot(DdkCtx* c, const float* lig_pos, const float* x, const DdkStepInputs* in, float* tr, float* rot,
+                       cudaStream_t st);
+void launch_head_tor(DdkCtx* c, const float* lig_pos, const float* x, const DdkStepInputs* in, float* tor, cudaStream_t st);
+void launch_update(DdkCtx* c, float* lig_pos, const float* tr, const float* rot, const float* tor, const float* z_tr,
+                   const float* z_rot, const float* z_tor, DdkStepCoef coef, cudaStream_t st);
+
+}  // namespace ddk

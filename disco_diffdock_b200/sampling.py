@@ -1,0 +1,214 @@
+"""Drop-in for ``utils/sampling.py`` of the reference: ``randomize_position`` and ``sampling`` with the same
+signatures (``/root/reference/utils/sampling.py:12, 49-54``; called from ``evaluate.py:233, 268-291``).
+
+``sampling()`` keeps the reference's contract -- it mutates ``data_list[i]['ligand'].pos`` and returns
+``(data_list, confidence)`` -- but the whole reverse-diffusion loop of a batch (``sampling.py:105-198``: set_time,
+score model, perturbation, modify_conformer_batch) runs inside ``libddk`` as one stream-ordered sequence of kernels
+with no host synchronisation (``ddk_sample``).  Everything that depends only on the schedule (sigma(t), the sinusoidal
+embedding, the cross cut-off, SO(3)/torus score-norm look-ups and the a*score + b*z coefficients) is computed once on
+the host for all steps.
+
+Two keyword-only extensions: ``noise`` (pre-drawn z, used by the parity tests so the CPU oracle and the GPU consume
+identical noise) and ``generator`` (seeded device RNG; the reference never seeds).
+"""
+from __future__ import annotations
+
+import copy
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from .data import DataLoader
+from .engine import StepTables, so3_score_norm, torus_score_norm
+
+
+def is_iterable(arr):
+    try:
+        iter(arr)
+        return True
+    except TypeError:
+        return False
+
+
+def _three(x):
+    return list(x) if is_iterable(x) else [x] * 3
+
+
+def _score_model_of(model):
+    m = model.module if hasattr(model, 'module') else model
+    return m.score_model if hasattr(m, 'score_model') else m
+
+
+def randomize_position(data_list, no_torsion, no_random, tr_sigma_max, unbatched=False, ar_args=None):
+    """sampling.py:12-46: uniform torsions, uniform random rotation about the centroid, N(0, tr_sigma_max) shift.
+    Host code (numpy / scipy RNG), once per complex -- it defines the start poses."""
+    from scipy.spatial.transform import Rotation as R
+    if not no_torsion:
+        for g in data_list:
+            lig = g['ligand']
+            mask = lig.edge_mask.cpu().numpy().astype(bool)
+            upd = np.random.uniform(low=-np.pi, high=np.pi, size=int(mask.sum()))
+            mr = lig.mask_rotate if unbatched else lig.mask_rotate[0]
+            edges = g['ligand', 'ligand'].edge_index.T[torch.from_numpy(mask)]
+            lig.pos = torsion_update_host(lig.pos, edges, np.asarray(mr), upd)
+    for g in data_list:
+        lig = g['ligand']
+        center = torch.mean(lig.pos, dim=0, keepdim=True)
+        rot = torch.from_numpy(R.random().as_matrix()).float()
+        lig.pos = (lig.pos - center) @ rot.T
+        if not no_random:
+            lig.pos = lig.pos + torch.normal(mean=0, std=tr_sigma_max, size=(1, 3))
+    if ar_args is not None:
+        for g in data_list:
+            if getattr(ar_args, 'no_randomness', False):
+                ar = torch.from_numpy(np.asarray(g['ligand'].orig_rdkit_pos[0])).float()
+                ar = (ar - ar.mean(0, keepdim=True)) @ torch.from_numpy(R.random().as_matrix()).float().T
+                g['ligand'].ar_pos = ar
+            else:
+                g['ligand'].ar_pos = copy.deepcopy(g['ligand'].pos)
+
+
+def torsion_update_host(pos, edge_index, mask_rotate, torsion_updates):
+    """utils/torsion.py:48-68 (numpy, sequential over rotatable bonds); used only by randomize_position."""
+    from scipy.spatial.transform import Rotation as R
+    p = pos.cpu().numpy().astype(np.float64).copy() if torch.is_tensor(pos) else np.array(pos, dtype=np.float64)
+    for k, e in enumerate(edge_index.cpu().numpy()):
+        if torsion_updates[k] == 0:
+            continue
+        u, v = int(e[0]), int(e[1])
+        assert not mask_rotate[k, u] and mask_rotate[k, v]
+        rv = p[u] - p[v]
+        rv = rv * torsion_updates[k] / np.linalg.norm(rv)
+        rm = R.from_rotvec(rv).as_matrix()
+        p[mask_rotate[k]] = (p[mask_rotate[k]] - p[v]) @ rm.T + p[v]
+    return torch.from_numpy(p.astype(np.float32))
+
+
+def build_step_tables(score_model, model_args, t_to_sigma, tr_schedule, rot_schedule, tor_schedule, inference_steps, B,
+                      temp_sampling, temp_psi, temp_sigma_data, ode=False) -> StepTables:
+    """Host arithmetic of sampling.py:106-113, 137-192 and of the sigma-dependent parts of
+    TensorProductScoreModel.forward (score_model.py:187, 203, 276, 284-286, 303-307) for every step."""
+    ts, tp, td = _three(temp_sampling), _three(temp_psi), _three(temp_sigma_data)
+    emb_fn = score_model.timestep_emb_func
+    rng = [(model_args.tr_sigma_min, model_args.tr_sigma_max), (model_args.rot_sigma_min, model_args.rot_sigma_max),
+           (model_args.tor_sigma_min, model_args.tor_sigma_max)]
+    semb, cutoff, trs, rots, tors, coef = [], [], [], [], [], []
+    for s in range(inference_steps):
+        t = [tr_schedule[s], rot_schedule[s], tor_schedule[s]]
+        last = s == inference_steps - 1
+        dt = [t[0] if last else tr_schedule[s] - tr_schedule[s + 1], t[1] if last else rot_schedule[s] - rot_schedule[s + 1],
+              t[2] if last else tor_schedule[s] - tor_schedule[s + 1]]
+        sig = t_to_sigma(t[0], t[1], t[2])                                   # float64 scalars (sampling.py:111)
+        # what the model derives from complex_t (float32 tensors, set_time at sampling.py:113)
+        ct = [float(x) * torch.ones(B) for x in t]
+        m_sig = [torch.as_tensor(x).float() for x in score_model.t_to_sigma(*ct)]
+        semb.append(emb_fn(ct[0]))
+        cutoff.append(m_sig[0] * 3 + 20 if score_model.dynamic_max_cross else torch.full((B,), score_model.cross_max_distance))
+        if score_model.scale_by_sigma:
+            trs.append(m_sig[0]); rots.append(so3_score_norm(m_sig[1])); tors.append(torch.sqrt(torus_score_norm(m_sig[2])))
+        else:
+            trs.append(torch.ones(B)); rots.append(torch.ones(B)); tors.append(torch.ones(B))
+        row = []
+        for i in range(3):
+            g = sig[i] * np.sqrt(2 * np.log(rng[i][1] / rng[i][0]))        # sampling.py:137-140, 167-169
+            if ode:
+                a, b = 0.5 * g ** 2 * dt[i], 0.0                            # :142-144, 171
+            elif ts[i] != 1.0:                                              # low-temperature sampling, :179-192
+                sd = np.exp(td[i] * np.log(rng[i][1]) + (1 - td[i]) * np.log(rng[i][0]))
+                lam = (sd + sig[i]) / (sd + sig[i] / ts[i])
+                a = g ** 2 * dt[i] * (lam + ts[i] * tp[i] / 2)
+                b = g * np.sqrt(dt[i] * (1 + tp[i]))
+            else:
+                a, b = g ** 2 * dt[i], g * np.sqrt(dt[i])                   # :149, 154, 175
+            row += [np.float32(a), np.float32(b)]
+        coef.append(row)
+    return StepTables(inference_steps, torch.stack(semb), torch.stack(cutoff), torch.stack(trs), torch.stack(rots),
+                      torch.stack(tors), coef)
+
+
+def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_schedule, device, t_to_sigma, model_args,
+             no_random=False, ode=False, visualization_list=None, confidence_model=None, confidence_data_list=None,
+             confidence_model_args=None, batch_size=32, no_final_step_noise=False, use_latent=True,
+             gumbel_latent_temperature=0.01, ar_model=None, ar_args=None, temp_sampling=1.0, temp_psi=0.0, temp_sigma_data=0.5,
+             classifier_free_guidance_weight=0.0, softmax_latent_temperature=1.0, cfg_start=1.0, cfg_end=0.0,
+             compute_ar_accuracy=False, *, noise: Optional[Dict[str, torch.Tensor]] = None, generator=None,
+             host_buffers=False):
+    N = len(data_list)
+    device = torch.device(device)
+    sm = _score_model_of(model)
+    loader = DataLoader(data_list, batch_size=batch_size)
+    confidence = [] if confidence_model is not None else None
+    conf_loader = iter(DataLoader(confidence_data_list, batch_size=batch_size)) if confidence_data_list is not None else None
+    latent = use_latent and getattr(model_args, 'latent_dim', 0) > 0
+    if classifier_free_guidance_weight != 0.0:
+        raise NotImplementedError('classifier-free guidance (two score evaluations per step) is not wired up yet')
+    pose0 = 0
+    with torch.no_grad():
+        for batch_id, batch in enumerate(loader):
+            b = batch.num_graphs
+            if latent:
+                if ar_model is None:
+                    raise NotImplementedError('oracle latent encoder (TPEncoder) is out of scope; pass ar_model')
+                from .latent import encode_ar_batch
+                pos_keep = batch['ligand'].pos
+                if 'ar_pos' in batch['ligand']:
+                    batch['ligand'].pos = batch['ligand'].ar_pos
+                lat_l, lat_r = encode_ar_batch(ar_model, batch, softmax_latent_temperature, device, generator=generator)
+                batch['ligand'].pos = pos_keep
+                batch['ligand'].latent_h, batch['receptor'].latent_h = lat_l, lat_r
+            if getattr(sm, 'latent_droprate', 0) > 0:
+                batch['ligand'].unconditional = torch.zeros(batch['ligand'].num_nodes, 1)
+                batch['receptor'].unconditional = torch.zeros(batch['receptor'].num_nodes, 1)
+            eng = sm.engine(device)
+            info = eng.set_batch(batch)
+            eng._batch_key = None
+            steps = build_step_tables(sm, model_args, t_to_sigma, tr_schedule, rot_schedule, tor_schedule, inference_steps, b,
+                                      temp_sampling, temp_psi, temp_sigma_data, ode)
+            R = info.RB
+            if no_random or ode:
+                z = None
+            elif noise is not None:
+                per = R // b if b else 0
+                z = {'tr': noise['tr'][:, pose0:pose0 + b], 'rot': noise['rot'][:, pose0:pose0 + b],
+                     'tor': noise['tor'][:, pose0 * per:(pose0 + b) * per] if R else None}
+            else:
+                zdev = torch.device('cpu') if host_buffers else device
+                z = {'tr': torch.randn(inference_steps, b, 3, device=zdev, generator=generator),
+                     'rot': torch.randn(inference_steps, b, 3, device=zdev, generator=generator),
+                     'tor': torch.randn(inference_steps, R, device=zdev, generator=generator) if R else None}
+                if no_final_step_noise:
+                    for v in z.values():
+                        if v is not None:
+                            v[-1] = 0
+            if host_buffers:
+                pos = batch['ligand'].pos.detach().to('cpu', torch.float32).contiguous()
+                eng.sample_host(pos, steps, z)
+            else:
+                pos = batch['ligand'].pos.to(device, torch.float32).contiguous().clone()
+                eng.sample(pos, steps, z)
+            batch['ligand'].pos = pos
+            len_lig = pos.shape[0] // b
+            for i in range(b):
+                data_list[batch_id * batch_size + i]['ligand'].pos = pos[i * len_lig:(i + 1) * len_lig]
+                if latent:
+                    data_list[batch_id * batch_size + i]['ligand'].latent_h = batch['ligand'].latent_h[i * len_lig:(i + 1) * len_lig]
+            pose0 += b
+            if visualization_list is not None:
+                for idx, vis in enumerate(visualization_list):
+                    vis.add((data_list[idx]['ligand'].pos.detach().cpu() + data_list[idx].original_center.detach().cpu()),
+                            part=1, order=2)
+            if confidence_model is not None:
+                from .diffusion_utils import set_time
+                if conf_loader is not None:
+                    cb = next(conf_loader)
+                    cb['ligand'].pos = pos.cpu()
+                    cb = cb.to(device)
+                    set_time(cb, 0, 0, 0, b, confidence_model_args.all_atoms, device)
+                    out = confidence_model(cb)
+                else:
+                    out = confidence_model(batch.to(device))
+                confidence.append(out[0] if type(out) is tuple else out)
+    if confidence_model is not None:
+        confidence = torch.nan_to_num(torch.cat(confidence, dim=0), nan=-1000)
+    return data_list, confidence

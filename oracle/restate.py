@@ -455,16 +455,17 @@ def forward(p, cfg, data, tables, trace: Optional[dict] = None):
 
 # ------------------------------------------------------------------------------------------------ LUTs
 def so3_score_norm(tables, eps):
-    """so3.score_norm (so3.py:91-95)."""
-    e = np.asarray(eps.double().numpy() if torch.is_tensor(eps) else eps, dtype=np.float64)
+    """so3.score_norm (so3.py:91-95).  ``eps.numpy()`` is float32, so log10 is evaluated in float32 and the
+    rest in float64 (the np.float64 constants promote), exactly as the reference module does under this numpy."""
+    e = eps.float().numpy() if torch.is_tensor(eps) else np.asarray(eps, dtype=np.float32)
     idx = (np.log10(e) - np.log10(0.01)) / (np.log10(2) - np.log10(0.01)) * 1000
-    idx = np.clip(np.around(idx).astype(int), 0, 999)
+    idx = np.clip(np.around(idx).astype(int), a_min=0, a_max=999)
     return torch.from_numpy(tables['so3_exp_score_norms'][idx]).float()
 
 
 def torus_score_norm(tables, sigma):
-    """torus.score_norm (torus.py:79-83)."""
-    s = np.asarray(sigma.double().numpy() if torch.is_tensor(sigma) else sigma, dtype=np.float64)
+    """torus.score_norm (torus.py:79-83) on the float32 array score_model.py:306 passes in."""
+    s = sigma.float().numpy() if torch.is_tensor(sigma) else np.asarray(sigma, dtype=np.float32)
     s = np.log(s / np.pi)
     s = (s - np.log(3e-3)) / (np.log(2) - np.log(3e-3)) * 5000
     idx = np.round(np.clip(s, 0, 5000)).astype(int)

@@ -10,6 +10,8 @@ from disco_diffdock_b200 import data as ddata
 from disco_diffdock_b200 import synthetic
 from disco_diffdock_b200.score_model import TensorProductScoreModel
 from oracle import restate
+from functools import partial
+from disco_diffdock_b200 import diffusion_utils as du
 
 README_TEMPS = dict(  # /root/reference/README.md:15 (DiffDock-S inference command)
     temp_sampling=(1.886430780895051, 5.659562317960644, 2.8888668488630156),
@@ -17,10 +19,12 @@ README_TEMPS = dict(  # /root/reference/README.md:15 (DiffDock-S inference comma
     temp_sigma_data=(0.3617563913086843, 0.7437588205919711, 0.08897393057297842))
 
 
-def make_model(seed=0, latent_dim=0, latent_droprate=0.0, device='cpu', randomize_bn=True, gain=1.0):
+def make_model(seed=0, latent_dim=0, latent_droprate=0.0, device='cpu', randomize_bn=True, gain=1.0, num_conv_layers=5):
     """Fresh default-initialised DiffDock-S architecture (model_parameters.yml of the shipped checkpoint)."""
     torch.manual_seed(seed)
-    m = TensorProductScoreModel(None, device, None, sh_lmax=1, ns=24, nv=6, num_conv_layers=5, lig_max_radius=5.0,
+    cfg = restate.default_config(latent_dim=latent_dim, latent_droprate=latent_droprate, num_conv_layers=num_conv_layers)
+    m = TensorProductScoreModel(partial(du.t_to_sigma, args=cfg), device,
+                                du.get_timestep_embedding('sinusoidal', 32, 1000), sh_lmax=1, ns=24, nv=6, num_conv_layers=num_conv_layers, lig_max_radius=5.0,
                                 cross_max_distance=80.0, dynamic_max_cross=True, dropout=0.1, lm_embedding_type='esm',
                                 latent_dim=latent_dim, latent_vocab=1, latent_droprate=latent_droprate)
     sd = {k: v.clone() for k, v in m.state_dict().items()}
@@ -41,7 +45,6 @@ def make_model(seed=0, latent_dim=0, latent_droprate=0.0, device='cpu', randomiz
         for k in ('tr_final_layer.3.weight', 'rot_final_layer.3.weight', 'tor_final_layer.3.weight'):
             sd[k] = sd[k] * gain
     m.load_state_dict(sd)
-    cfg = restate.default_config(latent_dim=latent_dim, latent_droprate=latent_droprate)
     return m, sd, cfg
 
 

@@ -1,0 +1,251 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle and the reference-generated golden vectors.
+
+Run on the B200 box:  python -m pytest tests -m gpu -q
+Tolerances (fp32 path, different summation order than the reference): scores 2e-5 relative to the largest score
+component, node features 2e-5 absolute, final poses <= 1e-3 A RMSD after a full reverse-diffusion run (the tolerance
+BASELINE.json's north_star states).  Edge sets (radius / cross graph construction) must match bit-exactly.
+"""
+import copy
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from disco_diffdock_b200 import data as ddata
+from disco_diffdock_b200 import diffusion_utils as du
+from disco_diffdock_b200 import sampling as dsampling
+from disco_diffdock_b200 import synthetic
+from oracle import make_golden, restate
+from tests import helpers
+from tests.test_oracle_golden import GOLD, load_tables
+
+pytestmark = pytest.mark.gpu
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out')
+
+
+def dump(name, obj):
+    os.makedirs(OUT, exist_ok=True)
+    with open(os.path.join(OUT, f'diag_{name}.json'), 'w') as f:
+        json.dump(obj, f, indent=1, default=float)
+
+
+@pytest.fixture(scope='module', autouse=True)
+def _need_cuda():
+    assert torch.cuda.is_available(), 'these tests need the B200'
+    from disco_diffdock_b200 import build
+    build.build()
+
+
+def rel_err(a, b):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    return float((a - b).abs().max() / max(1.0, float(b.abs().max())))
+
+
+def oracle_forward(sd, cfg, batch):
+    tr = {}
+    with torch.no_grad():
+        out = restate.forward(sd, cfg, copy.deepcopy(batch), load_tables(), tr)
+    return out, tr
+
+
+def edge_sets_from_engine(eng, info):
+    """(src, dst, slot) triples of the four groups as the kernels listed them."""
+    cnt = eng.debug_read('seg_cnt', np.int32)
+    base = eng.debug_read('seg_base', np.int32)
+    lst = eng.debug_read('seg_list', np.int32).reshape(-1, 2)
+    NL, NR = info.NL, info.NR
+    groups = {0: [], 1: [], 2: [], 3: []}
+    for node in range(NL + NR):
+        for which in range(2):
+            seg = 2 * node + which
+            g = which if node < NL else 2 + which
+            for e in range(cnt[seg]):
+                slot, dst = lst[base[seg] + e]
+                groups[g].append((node, int(dst), int(slot)))
+    return groups
+
+
+@pytest.mark.parametrize('layers', [1, 2, 3, 4, 5])
+def test_forward_stages(layers):
+    """Every stage of one score evaluation against the oracle, for models truncated after 1..5 conv layers
+    (isolates the four basis levels of the conv kernels)."""
+    m, sd, cfg = helpers.make_model(10 + layers, num_conv_layers=layers)
+    m = m.to('cuda')
+    _, lst = helpers.make_pose_batch(3, 20, 50, 3)
+    batch = ddata.Batch.from_data_list(lst)
+    restate.set_time(batch, 0.6, 0.6, 0.6, 3)
+    (tr_o, rot_o, tor_o), trc = oracle_forward(sd, cfg, batch)
+    tr, rot, tor = m(batch)
+    eng = m.engine()
+    info = eng.batch_info
+    diag = {}
+    # --- graph construction: identical edge sets
+    groups = edge_sets_from_engine(eng, info)
+    NL = info.NL
+    rr = batch['receptor', 'receptor'].edge_index
+    want = {0: set(zip(trc['ll_src'].tolist(), trc['ll_dst'].tolist())),
+            1: set(zip(trc['lr_src'].tolist(), (trc['lr_dst'] + NL).tolist())),
+            2: set(zip((rr[0] + NL).tolist(), (rr[1] + NL).tolist())),
+            3: set(zip((trc['lr_dst'] + NL).tolist(), trc['lr_src'].tolist()))}
+    # group 0 holds bonded pairs twice (bond edge + radius edge): compare as multisets
+    from collections import Counter
+    got0 = Counter((s, d) for s, d, _ in groups[0])
+    want0 = Counter(zip(trc['ll_src'].tolist(), trc['ll_dst'].tolist()))
+    diag['edges'] = {g: len(groups[g]) for g in groups}
+    assert got0 == want0, 'ligand-ligand edge multiset differs'
+    for g in (1, 2, 3):
+        assert set((s, d) for s, d, _ in groups[g]) == want[g], f'group {g} edge set differs'
+        assert len(groups[g]) == len(want[g])
+    assert eng.last_edge_count() == trc['n_edges']
+    # --- edge embeddings / harmonics at the listed slots
+    ea = eng.debug_read('ea_pool').reshape(-1, 24)
+    sh = eng.debug_read('sh_pool').reshape(-1, 4)
+    o_lr = {(s, d): i for i, (s, d) in enumerate(zip(trc['lr_src'].tolist(), (trc['lr_dst'] + NL).tolist()))}
+    idx_k = np.array([sl for s, d, sl in groups[1]])
+    idx_o = np.array([o_lr[(s, d)] for s, d, _ in groups[1]])
+    diag['lr_ea'] = float(np.abs(ea[idx_k] - trc['lr_ea'].numpy()[idx_o]).max())
+    diag['lr_sh'] = float(np.abs(sh[idx_k] - trc['lr_sh'].numpy()[idx_o]).max())
+    o_rr = {(s, d): i for i, (s, d) in enumerate(zip((rr[0] + NL).tolist(), (rr[1] + NL).tolist()))}
+    idx_k = np.array([sl for s, d, sl in groups[2]])
+    idx_o = np.array([o_rr[(s, d)] for s, d, _ in groups[2]])
+    diag['rr_ea'] = float(np.abs(ea[idx_k] - trc['rr_ea'].numpy()[idx_o]).max())
+    diag['rr_sh'] = float(np.abs(sh[idx_k] - trc['rr_sh'].numpy()[idx_o]).max())
+    # ligand-ligand: radius edges (zero bond attr) and bond edges; match by (src, dst, is_bond)
+    nb = batch['ligand', 'ligand'].edge_index.shape[1]
+    o_ll = {}
+    for i, (s, d) in enumerate(zip(trc['ll_src'].tolist(), trc['ll_dst'].tolist())):
+        o_ll[(s, d, i < nb)] = i
+    idx_k = np.array([sl for s, d, sl in groups[0]])
+    idx_o = np.array([o_ll[(s, d, sl < nb)] for s, d, sl in groups[0]])
+    diag['ll_ea'] = float(np.abs(ea[idx_k] - trc['ll_ea'].numpy()[idx_o]).max())
+    diag['ll_sh'] = float(np.abs(sh[idx_k] - trc['ll_sh'].numpy()[idx_o]).max())
+    # --- node features after the last layer
+    x = eng.debug_read('x_final').reshape(-1, 84)
+    ref_x = torch.cat([trc['lig_h'], trc['rec_h']]).numpy()
+    w = ref_x.shape[1]
+    diag['x_final'] = float(np.abs(x[:, :w] - ref_x).max())
+    diag['x_pad'] = float(np.abs(x[:, w:]).max()) if w < 84 else 0.0
+    diag['x_per_node_max'] = [float(v) for v in np.abs(x[:, :w] - ref_x).max(1)[:8]]
+    diag['tr'], diag['rot'], diag['tor'] = rel_err(tr, tr_o), rel_err(rot, rot_o), rel_err(tor, tor_o)
+    diag['tr_vals'] = [tr.cpu().tolist(), tr_o.tolist()]
+    diag['tor_vals'] = [tor.cpu().tolist()[:6], tor_o.tolist()[:6]]
+    dump(f'stages_L{layers}', diag)
+    for k in ('lr_ea', 'lr_sh', 'rr_ea', 'rr_sh', 'll_ea', 'll_sh'):
+        assert diag[k] < 5e-6, (k, diag[k])
+    assert diag['x_final'] < 2e-5 and diag['x_pad'] == 0.0, diag
+    assert diag['tr'] < 2e-5 and diag['rot'] < 2e-5 and diag['tor'] < 2e-5, diag
+
+
+@pytest.mark.parametrize('name', ['forward_small', 'forward_latent', 'forward_cfg1'])
+def test_forward_matches_reference_golden(name):
+    """GPU forward vs the vectors generated by the reference's own forward (oracle/make_golden.py)."""
+    z = np.load(os.path.join(GOLD, name + '.npz'))
+    m, sd, cfg, batch = make_golden.forward_inputs(make_golden.CASES[name])
+    m = m.to('cuda')
+    tr, rot, tor = m(batch)
+    lig_h, rec_h = m.embed(batch)[:2]
+    d = {'tr': rel_err(tr, torch.from_numpy(z['tr'])), 'rot': rel_err(rot, torch.from_numpy(z['rot'])),
+         'tor': rel_err(tor, torch.from_numpy(z['tor'])),
+         'lig_h': float((lig_h.cpu() - torch.from_numpy(z['lig_h'])).abs().max()),
+         'rec_h': float((rec_h.cpu() - torch.from_numpy(z['rec_h'])).abs().max())}
+    dump(name, d)
+    assert max(d['tr'], d['rot'], d['tor']) < 2e-5 and max(d['lig_h'], d['rec_h']) < 3e-5, d
+
+
+def test_forward_mixed_batch_and_no_rotatable_bonds():
+    """forward() on a batch of *different* complexes (the reference's forward supports it, only sampling() assumes
+    copies) including a ligand without rotatable bonds."""
+    m, sd, cfg = helpers.make_model(5)
+    m = m.to('cuda')
+    gs = [synthetic.make_complex(21, 12, 30), synthetic.make_complex(22, 25, 64), synthetic.make_complex(23, 9, 17)]
+    gs[2]['ligand'].edge_mask = torch.zeros_like(gs[2]['ligand'].edge_mask)
+    gs[2]['ligand'].mask_rotate = np.zeros((0, 9), dtype=bool)
+    batch = ddata.Batch.from_data_list(gs)
+    restate.set_time(batch, 0.3, 0.3, 0.3, 3)
+    (tr_o, rot_o, tor_o), _ = oracle_forward(sd, cfg, batch)
+    tr, rot, tor = m(batch)
+    d = {'tr': rel_err(tr, tr_o), 'rot': rel_err(rot, rot_o), 'tor': rel_err(tor, tor_o), 'n_tor': int(tor.numel())}
+    dump('mixed', d)
+    assert tor.shape == tor_o.shape
+    assert max(d['tr'], d['rot'], d['tor']) < 2e-5, d
+
+
+def test_update_matches_oracle():
+    """ddk_update (perturbation + rigid move + sequential torsions + Kabsch) vs modify_conformer_batch."""
+    m, sd, cfg = helpers.make_model(6)
+    m = m.to('cuda')
+    B = 4
+    g, lst = helpers.make_pose_batch(8, 24, 40, B)
+    batch = ddata.Batch.from_data_list(lst)
+    eng = m.engine()
+    info = eng.set_batch(batch)
+    R = g['ligand'].mask_rotate.shape[0]
+    gen = torch.Generator().manual_seed(3)
+    tr, rot, tor = torch.randn(B, 3, generator=gen), torch.randn(B, 3, generator=gen) * 0.5, torch.randn(B * R, generator=gen)
+    z = helpers.draw_noise(4, 1, B, R, no_final_step_noise=False)
+    coef = [0.7, 0.3, 0.4, 0.2, 0.9, 0.5]
+    pos = batch['ligand'].pos.clone()
+    M = batch['ligand', 'ligand'].edge_index.shape[1] // B
+    rot_bonds = batch['ligand', 'ligand'].edge_index[:, :M].T[batch['ligand'].edge_mask[:M]]
+    mask_rotate = torch.from_numpy(g['ligand'].mask_rotate)
+    want = restate.modify_conformer_batch(pos, B, rot_bonds, mask_rotate,
+                                          coef[0] * tr + coef[1] * z['tr'][0], coef[2] * rot + coef[3] * z['rot'][0],
+                                          coef[4] * tor + coef[5] * z['tor'][0])
+    dev = eng.device
+    got = eng.update(pos.to(dev).contiguous(), tr.to(dev), rot.to(dev), tor.to(dev), z['tr'][0].to(dev).contiguous(),
+                     z['rot'][0].to(dev).contiguous(), z['tor'][0].to(dev).contiguous(), coef)
+    rmsd = helpers.rmsd_per_pose(want, got.cpu(), B)
+    dump('update', {'rmsd': rmsd.tolist()})
+    assert float(rmsd.max()) < 2e-5, rmsd
+
+
+def run_gpu_sampling(m, cfg, lst, sched, noise, steps, temps, B, host_buffers=False):
+    from functools import partial
+    data_list = [synthetic.as_loader_item(x) for x in copy.deepcopy(lst)]
+    t2s = partial(du.t_to_sigma, args=cfg)
+    out, _ = dsampling.sampling(data_list, m, steps, sched, sched, sched, torch.device('cuda'), t2s, cfg, batch_size=B,
+                                no_final_step_noise=False, noise=noise, host_buffers=host_buffers, **temps)
+    return torch.cat([x['ligand'].pos.cpu() for x in out])
+
+
+@pytest.mark.parametrize('name', ['sample_small', 'sample_mid', 'sample_cfg1'])
+def test_sampling_matches_reference_golden(name):
+    """Full reverse-diffusion runs through the drop-in sampling() vs poses produced by the reference's sampling()."""
+    c = make_golden.CASES[name]
+    z = np.load(os.path.join(GOLD, name + '.npz'))
+    m, sd, cfg, lst, noise, sched, temps = make_golden.sample_inputs(c)
+    m = m.to('cuda')
+    pos = run_gpu_sampling(m, cfg, lst, sched, noise, c['steps'], temps, c['B'])
+    rmsd = helpers.rmsd_per_pose(torch.from_numpy(z['pos']), pos, c['B'])
+    pos_h = run_gpu_sampling(m, cfg, lst, sched, noise, c['steps'], temps, c['B'], host_buffers=True)
+    dump(name, {'rmsd_vs_reference': rmsd.tolist(), 'host_vs_device': float((pos_h - pos).abs().max())})
+    assert float(rmsd.max()) < 1e-3, rmsd
+    assert float((pos_h - pos).abs().max()) == 0.0
+
+
+def test_sampling_matches_oracle_multi_batch():
+    """10 poses in batches of 4 (ragged last batch), 20 steps, README temperatures: GPU vs oracle trajectory."""
+    m, sd, cfg = helpers.make_model(1, gain=5.0)
+    m = m.to('cuda')
+    N, bs, steps = 10, 4, 20
+    g, lst = helpers.make_pose_batch(9, 22, 60, N)
+    R = g['ligand'].mask_rotate.shape[0]
+    noise = helpers.draw_noise(11, steps, N, R)
+    sched = du.get_t_schedule(steps)
+    from functools import partial
+    data_list = [synthetic.as_loader_item(x) for x in copy.deepcopy(lst)]
+    out, _ = dsampling.sampling(data_list, m, steps, sched, sched, sched, torch.device('cuda'), partial(du.t_to_sigma, args=cfg),
+                                cfg, batch_size=bs, noise=noise, **helpers.README_TEMPS)
+    got = torch.cat([x['ligand'].pos.cpu() for x in out])
+    want = []
+    for b0 in range(0, N, bs):
+        b1 = min(N, b0 + bs)
+        batch = ddata.Batch.from_data_list(copy.deepcopy(lst[b0:b1]))
+        nz = {'tr': noise['tr'][:, b0:b1], 'rot': noise['rot'][:, b0:b1], 'tor': noise['tor'][:, b0 * R:b1 * R]}
+        with torch.no_grad():
+            want.append(restate.sample(sd, cfg, batch, load_tables(), sched, nz, inference_steps=steps, **helpers.README_TEMPS).clone())
+    rmsd = helpers.rmsd_per_pose(torch.cat(want), got, N)
+    dump('multi_batch', {'rmsd': rmsd.tolist()})
+    assert float(rmsd.max()) < 1e-3, rmsd

@@ -90,7 +90,7 @@ int ddk_create(const DdkConfig* cfg, const float* weights_h, size_t n_floats, co
   if (!cfg || !weights_h || !offsets_h || !out) return fail(nullptr, DDK_ERR_INVALID, "null argument");
   if (cfg->abi_version != DDK_ABI_VERSION) return fail(nullptr, DDK_ERR_INVALID, "ABI version mismatch");
   if (cfg->ns != NS || cfg->nv != NV) return fail(nullptr, DDK_ERR_INVALID, "kernels are compiled for ns=24, nv=6");
-  if (cfg->num_conv_layers < 1 || cfg->num_conv_layers > 8) return fail(nullptr, DDK_ERR_INVALID, "num_conv_layers out of range");
+  if (cfg->num_conv_layers < 3 || cfg->num_conv_layers > 8) return fail(nullptr, DDK_ERR_INVALID, "num_conv_layers must be 3..8");
   if (cfg->latent_dim < 0 || cfg->latent_dim > 2) return fail(nullptr, DDK_ERR_INVALID, "latent_dim must be 0..2");
   if (n_offsets != DDK_W_CONV_BASE + cfg->num_conv_layers * DDK_W_CONV_STRIDE)
     return fail(nullptr, DDK_ERR_INVALID, "offset table has the wrong length");

@@ -113,8 +113,9 @@ __device__ __forceinline__ void basis_desc(int u, int& type, int& i0, int& m) {
     return;
   }
   u -= 3 * F1o;
+  constexpr int F1eD = F1e > 0 ? F1e : 1;
   if (u < 3 * F1e) {
-    int c = u / F1e, k = u % F1e;
+    int c = u / F1eD, k = u % F1eD;
     if (k < 6) { type = 2; i0 = X1O + 3 * k; m = 1 + c; }
     else if (k < 12) { type = 0; i0 = X1E + 3 * (k - 6) + c; m = 0; }
     else { type = 0; i0 = X0O + (k - 12); m = 1 + c; }

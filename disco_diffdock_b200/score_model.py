@@ -47,6 +47,8 @@ class TensorProductScoreModel(nn.Module):
             unsupported.append("lm_embedding_type must be 'esm'")
         if latent_dim > 0 and latent_vocab != 1:
             unsupported.append('only equivariant latents (latent_vocab == 1)')
+        if num_conv_layers < 3:
+            unsupported.append('num_conv_layers >= 3 (the score heads consume the full 0e+1o+1e+0o representation)')
         if in_lig_edge_features != 4:
             unsupported.append('in_lig_edge_features must be 4')
         if unsupported:

@@ -113,6 +113,7 @@ def bn_affine_84(sd, key, layer, eps=1e-5):
 
 def pack_weights(sd: Dict[str, torch.Tensor], hyper):
     """Returns (blob float32 [n], offsets int64 [n_offsets])."""
+    sd = {k: v.detach().cpu() for k, v in sd.items()}
     L = hyper.num_conv_layers
     n_off = ENUMS['DDK_W_CONV_BASE'] + L * ENUMS['DDK_W_CONV_STRIDE']
     offsets = np.full(n_off, -1, dtype=np.int64)

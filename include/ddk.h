@@ -54,7 +54,7 @@ typedef enum DdkStatus {
 typedef struct DdkConfig {
   int32_t abi_version;        /* DDK_ABI_VERSION */
   int32_t ns, nv;             /* must be 24, 6 */
-  int32_t num_conv_layers;    /* 1..8 */
+  int32_t num_conv_layers;    /* 3..8 (the heads consume the full 0e+1o+1e+0o representation) */
   int32_t latent_dim;         /* 0, or the number of equivariant latents (DisCo: 2) */
   int32_t has_unconditional;  /* latent_droprate > 0: *_unconditional_embedding present */
   int32_t dynamic_max_cross;  /* cross cutoff = 3*sigma_tr + 20 per graph (score_model.py:202-205) */

@@ -120,6 +120,9 @@ int ddk_create(const DdkConfig* cfg, const float* weights_h, size_t n_floats, co
   if ((e = cudaMalloc(&c->w, n_floats * sizeof(float))) != cudaSuccess) return bail("cudaMalloc(weights)", e);
   if ((e = cudaMemcpy(c->w, weights_h, n_floats * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess)
     return bail("cudaMemcpy(weights)", e);
+  if ((e = cudaMalloc(&c->b_edge_total.p, 8)) != cudaSuccess) return bail("cudaMalloc(counter)", e);
+  c->b_edge_total.bytes = 8;
+  if ((e = cudaMemset(c->b_edge_total.p, 0, 8)) != cudaSuccess) return bail("cudaMemset(counter)", e);
   if ((e = conv_configure()) != cudaSuccess) return bail("cudaFuncSetAttribute(conv)", e);
   if ((e = heads_configure()) != cudaSuccess) return bail("cudaFuncSetAttribute(heads)", e);
   *out = c;
@@ -133,8 +136,9 @@ int ddk_destroy(DdkCtx* c) {
                 &c->b_rr_dst, &c->b_rot_u, &c->b_rot_v, &c->b_rot_ptr, &c->b_rot_graph, &c->b_mr_off, &c->b_ll_off,
                 &c->b_lr_off, &c->b_seg_base, &c->b_seg_static, &c->b_seg_cnt, &c->b_seg_list, &c->b_seg_order,
                 &c->b_seg_sidx, &c->b_lig_static, &c->b_rec_static, &c->b_rr_pre, &c->b_ea_pool, &c->b_sh_pool, &c->b_tb,
-                &c->b_xa, &c->b_xb, &c->b_proj, &c->b_A, &c->b_Bsum, &c->b_tr, &c->b_rot, &c->b_tor, &c->b_pos, &c->b_step};
+                &c->b_xa, &c->b_xb, &c->b_proj, &c->b_A, &c->b_Bsum, &c->b_tr, &c->b_rot, &c->b_tor, &c->b_pos, &c->b_step, &c->b_edge_total};
   for (Buf* b : all) free_buf(*b);
+  for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   if (c->w) cudaFree(c->w);
   delete c;
   return DDK_OK;
@@ -441,6 +445,15 @@ int64_t ddk_last_edge_count(DdkCtx* c) {
   return t;
 }
 
+int64_t ddk_edge_total(DdkCtx* c) {
+  if (!c) return -1;
+  cudaSetDevice(c->device);
+  unsigned long long v = 0;
+  if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+  if (cudaMemcpy(&v, c->b_edge_total.p, 8, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return (int64_t)v;
+}
+
 int ddk_debug_read(DdkCtx* c, const char* name, void* dst_h, size_t max_bytes, size_t* n_bytes) {
   if (!c || !name || !c->has_batch) return DDK_ERR_INVALID;
   cudaSetDevice(c->device);
@@ -469,6 +482,27 @@ int ddk_debug_read(DdkCtx* c, const char* name, void* dst_h, size_t max_bytes, s
   if (!src) return fail(c, DDK_ERR_STATE, "buffer not available yet");
   DDK_CUDA_TRY(c, cudaDeviceSynchronize());
   DDK_CUDA_TRY(c, cudaMemcpy(dst_h, src, std::min(n, max_bytes), cudaMemcpyDeviceToHost));
+  return DDK_OK;
+}
+
+int ddk_profile_enable(DdkCtx* c, int32_t on) {
+  if (!c) return DDK_ERR_INVALID;
+  c->prof = on != 0;
+  return DDK_OK;
+}
+
+int ddk_profile_read(DdkCtx* c, double* ms, int64_t* launches) {
+  if (!c || !ms || !launches) return DDK_ERR_INVALID;
+  static_assert(PC_COUNT == DDK_PROFILE_CLASSES, "profile class count");
+  cudaSetDevice(c->device);
+  DDK_CUDA_TRY(c, cudaDeviceSynchronize());
+  for (int i = 0; i < PC_COUNT; ++i) { ms[i] = 0.0; launches[i] = 0; }
+  for (const ProfRec& r : c->prof_recs) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) { ms[r.cls] += t; launches[r.cls]++; }
+  }
+  c->prof_recs.clear();
+  c->ev_used = 0;
   return DDK_OK;
 }
 

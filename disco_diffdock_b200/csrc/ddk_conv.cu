@@ -448,9 +448,9 @@ void launch_node_proj(DdkCtx* c, int layer, const float* x_in, float* x0_out, cu
   }
   p.proj = ptr<float>(c->b_proj);
   int blocks = (c->NL + PROJ_NODES - 1) / PROJ_NODES + (c->NR + PROJ_NODES - 1) / PROJ_NODES;
+  LaunchScope ls(c, PC_PROJ, st);
   if (x0_out != nullptr) k_node_proj<true><<<blocks, 288, 0, st>>>(p);
   else k_node_proj<false><<<blocks, 288, 0, st>>>(p);
-  DDK_LAUNCH_CHECK(c);
 }
 
 void launch_conv_layer(DdkCtx* c, int layer, const float* x_in, float* x_out, cudaStream_t st) {
@@ -465,13 +465,15 @@ void launch_conv_layer(DdkCtx* c, int layer, const float* x_in, float* x_out, cu
     a.ea_pool = ptr<float>(c->b_ea_pool); a.sh_pool = ptr<float4>(c->b_sh_pool);
     for (int g = 0; g < 4; ++g) a.W1[g] = W(c, conv_id(layer, DDK_WL_W1 + g));
     a.A = ptr<float>(c->b_A); a.Bsum = ptr<float>(c->b_Bsum);
+    {
+    LaunchScope ls(c, PC_ACC0 + li.lv, st);
     switch (li.lv) {
       case 0: k_conv_accum<0><<<ch.nseg, ACC_THREADS, sizeof(AccSmem<0>), st>>>(a); break;
       case 1: k_conv_accum<1><<<ch.nseg, ACC_THREADS, sizeof(AccSmem<1>), st>>>(a); break;
       case 2: k_conv_accum<2><<<ch.nseg, ACC_THREADS, sizeof(AccSmem<2>), st>>>(a); break;
       default: k_conv_accum<3><<<ch.nseg, ACC_THREADS, sizeof(AccSmem<3>), st>>>(a); break;
     }
-    DDK_LAUNCH_CHECK(c);
+    }
     ConArgs q;
     q.NL = c->NL;
     q.lig0 = ch.lig0; q.lig1 = ch.lig1; q.rec0 = ch.rec0; q.rec1 = ch.rec1;
@@ -486,8 +488,7 @@ void launch_conv_layer(DdkCtx* c, int layer, const float* x_in, float* x_out, cu
     q.x_in = x_in; q.x_out = x_out;
     q.li = li;
     int blocks = (ch.lig1 - ch.lig0 + CON_TM - 1) / CON_TM + (ch.rec1 - ch.rec0 + CON_TM - 1) / CON_TM;
-    k_conv_contract<<<blocks, 256, 0, st>>>(q);
-    DDK_LAUNCH_CHECK(c);
+    { LaunchScope ls(c, PC_CONTRACT, st); k_conv_contract<<<blocks, 256, 0, st>>>(q); }
   }
 }
 

@@ -35,5 +35,3 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 }  // namespace ddk
-
-#define DDK_LAUNCH_CHECK(ctx) (ctx)->launches++

@@ -124,6 +124,7 @@ struct ListArgs {
   int64_t slot_ll, slot_lr;
   float r2_lig, r2_cross;
   int dynamic;
+  unsigned long long* edge_total;
 };
 
 // One warp per dynamic segment; ordered (ascending index) compaction so the lists -- and therefore every
@@ -159,7 +160,7 @@ __global__ void k_build_lists(ListArgs p) {
       }
       cnt += __popc(m);
     }
-    if (lane == 0) p.seg_cnt[seg] = cnt;
+    if (lane == 0) { p.seg_cnt[seg] = cnt; atomicAdd(p.edge_total, (unsigned long long)cnt); }
     return;
   }
   bool from_lig = task < 2 * p.NL;
@@ -192,7 +193,7 @@ __global__ void k_build_lists(ListArgs p) {
     }
     cnt += __popc(m);
   }
-  if (lane == 0) p.seg_cnt[seg] = cnt;
+  if (lane == 0) { p.seg_cnt[seg] = cnt; atomicAdd(p.edge_total, (unsigned long long)cnt); }
 }
 
 struct EdgeArgs {
@@ -298,24 +299,24 @@ void launch_setup(DdkCtx* c, const DdkBatch* b, const int32_t* lig_x, const floa
   int L = c->cfg.latent_dim;
   {
     dim3 blk(NS, 8);
+    LaunchScope ls(c, PC_SETUP, st);
     k_setup_lig_nodes<<<(c->NL + 7) / 8, blk, 0, st>>>(c->NL, lig_x, W(c, DDK_W_LIG_EMB_TABLES), W(c, DDK_W_LIG_NODE_W),
                                                      W(c, DDK_W_LIG_NODE_B), NS + SE + L, L, c->lig_latent,
                                                      ptr<float>(c->b_lig_static));
-    DDK_LAUNCH_CHECK(c);
   }
   {
     int threads = 256, warps_per_block = threads / 32;
+    LaunchScope ls(c, PC_SETUP, st);
     k_setup_rec_nodes<<<(c->NR + warps_per_block - 1) / warps_per_block, threads, 0, st>>>(
         c->NR, rec_x, W(c, DDK_W_REC_EMB_TABLE), W(c, DDK_W_REC_NODE_W), W(c, DDK_W_REC_NODE_B), NS + ESM + SE + L, L,
         c->rec_latent, ptr<float>(c->b_rec_static));
-    DDK_LAUNCH_CHECK(c);
   }
   if (c->ER > 0) {
+    LaunchScope ls(c, PC_SETUP, st);
     k_setup_rr_edges<<<(c->ER + 127) / 128, 128, 0, st>>>(c->ER, ptr<int>(c->b_rr_src), ptr<int>(c->b_rr_dst), c->rec_pos,
                                                         W(c, DDK_W_REC_EDGE_W1), SE + DE + 2 * L, L, c->rec_latent,
                                                         W(c, DDK_W_SMEAR) + 33 * 1, ptr<float>(c->b_rr_pre),
                                                         ptr<float4>(c->b_sh_pool) + c->slot_rr);
-    DDK_LAUNCH_CHECK(c);
   }
 }
 
@@ -336,8 +337,8 @@ void launch_step_consts(DdkCtx* c, const float* sigma_emb, cudaStream_t st) {
   set(TB_CENTER, DDK_W_CENTER_EDGE_W1, DDK_W_CENTER_EDGE_B1, DE + SE, DE);
   set(TB_TR_FINAL, DDK_W_TR_FINAL_W1, DDK_W_TR_FINAL_B1, 1 + SE, 1);
   set(TB_ROT_FINAL, DDK_W_ROT_FINAL_W1, DDK_W_ROT_FINAL_B1, 1 + SE, 1);
+  LaunchScope ls(c, PC_GRAPH, st);
   k_step_consts<<<c->B, TB_COUNT * NS, 0, st>>>(c->B, sigma_emb, a, ptr<float>(c->b_tb));
-  DDK_LAUNCH_CHECK(c);
 }
 
 void launch_build_lists(DdkCtx* c, const float* lig_pos, const float* cutoff, cudaStream_t st) {
@@ -351,9 +352,10 @@ void launch_build_lists(DdkCtx* c, const float* lig_pos, const float* cutoff, cu
   p.lig_pos = lig_pos; p.rec_pos = c->rec_pos; p.cutoff = cutoff;
   p.slot_ll = c->slot_ll; p.slot_lr = c->slot_lr;
   p.r2_lig = c->r2_lig; p.r2_cross = c->r2_cross; p.dynamic = c->cfg.dynamic_max_cross;
+  p.edge_total = ptr<unsigned long long>(c->b_edge_total);
   int tasks = 2 * c->NL + c->NR, threads = 256;
+  LaunchScope ls(c, PC_GRAPH, st);
   k_build_lists<<<(tasks * 32 + threads - 1) / threads, threads, 0, st>>>(p);
-  DDK_LAUNCH_CHECK(c);
 }
 
 void launch_edge_features(DdkCtx* c, const float* lig_pos, cudaStream_t st) {
@@ -374,20 +376,17 @@ void launch_edge_features(DdkCtx* c, const float* lig_pos, cudaStream_t st) {
   p.W1 = W(c, DDK_W_LIG_EDGE_W1); p.W2 = W(c, DDK_W_LIG_EDGE_W2); p.b2 = W(c, DDK_W_LIG_EDGE_B2);
   p.wcols = 4 + SE + DE + 2 * L; p.sm = W(c, DDK_W_SMEAR) + 33 * 0;
   p.uncond = c->cfg.has_unconditional ? c->lig_uncond : nullptr; p.uncond_emb = unc + 2 * NS;
-  k_edge_features<0><<<(c->NL + wpb - 1) / wpb, threads, 0, st>>>(p);
-  DDK_LAUNCH_CHECK(c);
+  { LaunchScope ls(c, PC_GRAPH, st); k_edge_features<0><<<(c->NL + wpb - 1) / wpb, threads, 0, st>>>(p); }
   // cross
   p.W1 = W(c, DDK_W_CROSS_EDGE_W1); p.W2 = W(c, DDK_W_CROSS_EDGE_W2); p.b2 = W(c, DDK_W_CROSS_EDGE_B2);
   p.wcols = SE + DE + 2 * L; p.sm = W(c, DDK_W_SMEAR) + 33 * 2;
   p.uncond_emb = unc + 4 * NS;
-  k_edge_features<1><<<(c->NL + wpb - 1) / wpb, threads, 0, st>>>(p);
-  DDK_LAUNCH_CHECK(c);
+  { LaunchScope ls(c, PC_GRAPH, st); k_edge_features<1><<<(c->NL + wpb - 1) / wpb, threads, 0, st>>>(p); }
   // receptor contacts
   p.W1 = W(c, DDK_W_REC_EDGE_W1); p.W2 = W(c, DDK_W_REC_EDGE_W2); p.b2 = W(c, DDK_W_REC_EDGE_B2);
   p.wcols = SE + DE + 2 * L; p.sm = W(c, DDK_W_SMEAR) + 33 * 1;
   p.uncond = c->cfg.has_unconditional ? c->rec_uncond : nullptr; p.uncond_emb = unc + 3 * NS;
-  k_edge_features<2><<<(c->NR + wpb - 1) / wpb, threads, 0, st>>>(p);
-  DDK_LAUNCH_CHECK(c);
+  { LaunchScope ls(c, PC_GRAPH, st); k_edge_features<2><<<(c->NR + wpb - 1) / wpb, threads, 0, st>>>(p); }
 }
 
 }  // namespace ddk

@@ -314,8 +314,8 @@ void launch_head_trrot(DdkCtx* c, const float* lig_pos, const float* x, const Dd
   p.Wr1 = W(c, DDK_W_ROT_FINAL_W1); p.Wr2 = W(c, DDK_W_ROT_FINAL_W2); p.br2 = W(c, DDK_W_ROT_FINAL_B2);
   p.tr_sigma = in->tr_sigma; p.rot_scale = in->rot_scale;
   p.tr = tr; p.rot = rot;
+  LaunchScope ls(c, PC_HEADS, st);
   k_head_trrot<<<c->B, HEAD_THREADS, 0, st>>>(p);
-  DDK_LAUNCH_CHECK(c);
 }
 
 void launch_head_tor(DdkCtx* c, const float* lig_pos, const float* x, const DdkStepInputs* in, float* tor, cudaStream_t st) {
@@ -334,8 +334,8 @@ void launch_head_tor(DdkCtx* c, const float* lig_pos, const float* x, const DdkS
   p.tor_scale = in->tor_scale;
   p.r2_lig = c->r2_lig;
   p.tor = tor;
+  LaunchScope ls(c, PC_HEADS, st);
   k_head_tor<<<c->B, TOR_THREADS, tor_smem_bytes(), st>>>(p);
-  DDK_LAUNCH_CHECK(c);
 }
 
 }  // namespace ddk

@@ -51,6 +51,14 @@ struct Buf {
   size_t bytes = 0;
 };
 
+// kernel classes for the optional per-launch CUDA-event timing (ddk_profile_*)
+enum ProfClass { PC_SETUP = 0, PC_GRAPH, PC_PROJ, PC_ACC0, PC_ACC1, PC_ACC2, PC_ACC3, PC_CONTRACT, PC_HEADS, PC_UPDATE, PC_COUNT };
+
+struct ProfRec {
+  int cls;
+  cudaEvent_t a, b;
+};
+
 }  // namespace ddk
 
 struct DdkCtx {
@@ -84,7 +92,14 @@ struct DdkCtx {
   ddk::Buf b_xa, b_xb, b_proj, b_A, b_Bsum;
   ddk::Buf b_tr, b_rot, b_tor, b_pos;
   ddk::Buf b_step;                    // staging for ddk_sample_host
+  ddk::Buf b_edge_total;              // device uint64: edges of every combined graph built so far
   float* x_final = nullptr;           // points into xa or xb after the last conv layer
+
+  // optional profiling (off by default)
+  bool prof = false;
+  std::vector<ddk::ProfRec> prof_recs;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
 };
 
 namespace ddk {
@@ -94,6 +109,24 @@ inline int conv_id(int layer, int k) { return DDK_W_CONV_BASE + layer * DDK_W_CO
 
 template <typename T>
 inline T* ptr(const Buf& b) { return reinterpret_cast<T*>(b.p); }
+
+// RAII scope around one kernel launch: counts it and, when profiling is on, brackets it with CUDA events on `st`.
+struct LaunchScope {
+  DdkCtx* c; cudaStream_t st; int idx;
+  LaunchScope(DdkCtx* ctx, int cls, cudaStream_t stream) : c(ctx), st(stream), idx(-1) {
+    c->launches++;
+    if (!c->prof) return;
+    auto get = [&]() {
+      if (c->ev_used == c->ev_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); c->ev_pool.push_back(e); }
+      return c->ev_pool[c->ev_used++];
+    };
+    ProfRec r{cls, get(), get()};
+    cudaEventRecord(r.a, st);
+    idx = (int)c->prof_recs.size();
+    c->prof_recs.push_back(r);
+  }
+  ~LaunchScope() { if (idx >= 0) cudaEventRecord(c->prof_recs[idx].b, st); }
+};
 
 cudaError_t conv_configure();
 cudaError_t heads_configure();

@@ -179,8 +179,8 @@ void launch_update(DdkCtx* c, float* lig_pos, const float* tr, const float* rot,
   p.cf = coef;
   p.has_tor = (!c->cfg.no_torsion && c->RB > 0 && tor != nullptr) ? 1 : 0;
   size_t smem = (size_t)6 * c->maxNl * sizeof(float);
+  LaunchScope ls(c, PC_UPDATE, st);
   k_update<<<c->B, UPD_THREADS, smem, st>>>(p);
-  DDK_LAUNCH_CHECK(c);
 }
 
 void host_kabsch(const float* A, const float* Bp, int N, float* R9, float* t3) { kabsch_horn(A, Bp, N, R9, t3); }

@@ -178,6 +178,17 @@ class HeteroData:
             self._attrs[k] = _move(self._attrs[k], device)
         return self
 
+    def shallow_copy(self):
+        """New container and new stores that share the underlying tensors (cheap stand-in for the per-sample
+        ``copy.deepcopy(orig_complex_graph)`` of evaluate.py:232 when only ``['ligand'].pos`` will be rebound)."""
+        out = self.__class__()
+        for k, s in self._node_stores.items():
+            out._node_stores[k] = Store(**s._d)
+        for k, s in self._edge_stores.items():
+            out._edge_stores[k] = Store(**s._d)
+        out._attrs.update(self._attrs)
+        return out
+
     def __deepcopy__(self, memo):
         out = self.__class__()
         for k, s in self._node_stores.items():

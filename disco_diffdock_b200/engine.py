@@ -52,7 +52,8 @@ class DdkStepCoef(C.Structure):
 
 EXPORTS = ['ddk_abi_version', 'ddk_create', 'ddk_destroy', 'ddk_last_error', 'ddk_set_batch', 'ddk_score', 'ddk_embed',
            'ddk_get_node_features', 'ddk_update', 'ddk_sample', 'ddk_sample_host', 'ddk_kernel_launches',
-           'ddk_last_edge_count', 'ddk_debug_read', 'ddk_host_kabsch', 'ddk_host_axis_angle_to_matrix']
+           'ddk_last_edge_count', 'ddk_debug_read', 'ddk_host_kabsch', 'ddk_host_axis_angle_to_matrix',
+           'ddk_profile_enable', 'ddk_profile_read', 'ddk_edge_total']
 
 
 def load_library(path: Optional[str] = None):
@@ -83,7 +84,11 @@ def load_library(path: Optional[str] = None):
     lib.ddk_kernel_launches.argtypes = [C.c_void_p]
     lib.ddk_last_edge_count.restype = C.c_int64
     lib.ddk_last_edge_count.argtypes = [C.c_void_p]
+    lib.ddk_edge_total.restype = C.c_int64
+    lib.ddk_edge_total.argtypes = [C.c_void_p]
     lib.ddk_debug_read.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    lib.ddk_profile_enable.argtypes = [C.c_void_p, C.c_int32]
+    lib.ddk_profile_read.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.ddk_host_kabsch.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     lib.ddk_host_axis_angle_to_matrix.argtypes = [C.c_void_p, C.c_void_p]
     if path is None:
@@ -150,7 +155,7 @@ class Engine:
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     # ------------------------------------------------------------------------------------------ batch
-    def set_batch(self, data) -> SimpleNamespace:
+    def set_batch(self, data, assume_copies: bool = False) -> SimpleNamespace:
         """Upload the step-invariant part of a PyG-style batch (utils/sampling.py:56-67) and run the per-batch
         setup kernels.  Returns sizes / index info of the batch."""
         dev = self.device
@@ -203,8 +208,16 @@ class Engine:
         t = SimpleNamespace()
         t.lig_x = lig.x.to(dev, torch.int32).contiguous()
         t.bond_attr = data['ligand', 'ligand'].edge_attr.to(dev, torch.float32).contiguous()
-        t.rec_x = rec.x.to(dev, torch.float32).contiguous()
-        t.rec_pos = rec.pos.to(dev, torch.float32).contiguous()
+        nr0 = int(rec_ptr[1])
+        if assume_copies and B > 1 and rec.x.shape[0] == B * nr0:
+            # sampling() batches are B copies of one complex (utils/sampling.py:57): ship the receptor once
+            t.rec_x = rec.x[:nr0].to(dev, torch.float32).repeat(B, 1).contiguous()
+            t.rec_pos = rec.pos[:nr0].to(dev, torch.float32).repeat(B, 1).contiguous()
+            h2d_saved = (B - 1) * nr0 * (rec.x.shape[1] + 3) * 4
+        else:
+            t.rec_x = rec.x.to(dev, torch.float32).contiguous()
+            t.rec_pos = rec.pos.to(dev, torch.float32).contiguous()
+            h2d_saved = 0
         t.mask_rotate = mr_dev
         t.lig_latent = lig.latent_h.to(dev, torch.float32).contiguous() if L > 0 else None
         t.rec_latent = rec.latent_h.to(dev, torch.float32).contiguous() if L > 0 else None
@@ -225,7 +238,7 @@ class Engine:
             self._check(self.lib.ddk_set_batch(self.ctx, C.byref(b), self.stream()), 'ddk_set_batch')
         self._keep = [t, host]     # the context references rec_pos / bond_attr / masks / latents of the caller
         self.batch_info = SimpleNamespace(B=B, NL=b.NL, NR=b.NR, EB=b.EB, ER=b.ER, RB=RB, lig_ptr=lig_ptr, rec_ptr=rec_ptr,
-                                          h2d_bytes=sum(x.numel() * x.element_size() for x in vars(t).values() if x is not None))
+                                          h2d_bytes=sum(x.numel() * x.element_size() for x in vars(t).values() if x is not None) - h2d_saved)
         return self.batch_info
 
     # ------------------------------------------------------------------------------------------ steps
@@ -304,8 +317,24 @@ class Engine:
     def kernel_launches(self) -> int:
         return int(self.lib.ddk_kernel_launches(self.ctx))
 
+    def edge_total(self) -> int:
+        return int(self.lib.ddk_edge_total(self.ctx))
+
     def last_edge_count(self) -> int:
         return int(self.lib.ddk_last_edge_count(self.ctx))
+
+    PROFILE_CLASSES = ['setup', 'graph', 'node_proj', 'conv_accum_lv0', 'conv_accum_lv1', 'conv_accum_lv2', 'conv_accum_lv3',
+                       'conv_contract', 'heads', 'update']
+
+    def profile_enable(self, on=True):
+        self._check(self.lib.ddk_profile_enable(self.ctx, int(on)), 'ddk_profile_enable')
+
+    def profile_read(self):
+        """{class: (milliseconds, launches)} since the last read (synchronises)."""
+        ms = np.zeros(len(self.PROFILE_CLASSES), np.float64)
+        n = np.zeros(len(self.PROFILE_CLASSES), np.int64)
+        self._check(self.lib.ddk_profile_read(self.ctx, _np_ptr(ms), _np_ptr(n)), 'ddk_profile_read')
+        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(self.PROFILE_CLASSES)}
 
     def debug_read(self, name: str, dtype=np.float32) -> np.ndarray:
         n = C.c_size_t()

@@ -161,7 +161,7 @@ def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_s
                 batch['ligand'].unconditional = torch.zeros(batch['ligand'].num_nodes, 1)
                 batch['receptor'].unconditional = torch.zeros(batch['receptor'].num_nodes, 1)
             eng = sm.engine(device)
-            info = eng.set_batch(batch)
+            info = eng.set_batch(batch, assume_copies=True)
             eng._batch_key = None
             steps = build_step_tables(sm, model_args, t_to_sigma, tr_schedule, rot_schedule, tor_schedule, inference_steps, b,
                                       temp_sampling, temp_psi, temp_sigma_data, ode)

@@ -180,7 +180,17 @@ int ddk_sample_host(DdkCtx* ctx, float* lig_pos_h, int32_t n_steps, const DdkSte
 /* Introspection for tests / benchmarks (synchronising). */
 int64_t ddk_kernel_launches(const DdkCtx* ctx);        /* kernels launched by this context so far */
 int64_t ddk_last_edge_count(DdkCtx* ctx);              /* edges of the combined graph in the last ddk_score (sync) */
+int64_t ddk_edge_total(DdkCtx* ctx);                   /* cumulative *dynamic* (ligand radius + cross) edges listed since ddk_create (sync);
+                                                          the static bond / receptor-contact edges are not included */
 int ddk_debug_read(DdkCtx* ctx, const char* name, void* dst_h, size_t max_bytes, size_t* n_bytes);
+
+/* Optional per-launch timing with CUDA events on the launching stream (used by bench.py for the roofline line).
+ * Kernel classes: 0 setup, 1 graph (lists + edge embeddings), 2 node projections, 3..6 conv accumulate (basis level
+ * 0..3), 7 conv contract, 8 score heads, 9 update.  ddk_profile_read synchronises the device, adds the elapsed
+ * milliseconds / launch counts since the last read into ms[10] / launches[10] and clears the records. */
+#define DDK_PROFILE_CLASSES 10
+int ddk_profile_enable(DdkCtx* ctx, int32_t on);
+int ddk_profile_read(DdkCtx* ctx, double* ms, int64_t* launches);
 
 /* Host builds of two device routines of the update kernel, callable without a GPU (unit tests):
  * rigid alignment R a_n + t ~ b_n (utils/geometry.py:126-156) and axis-angle -> matrix (utils/geometry.py:38-85). */

@@ -2,8 +2,9 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 
-#include "ddk_internal.h"
+#include "ddk_conv.cuh"
 
 using namespace ddk;
 
@@ -125,6 +126,8 @@ int ddk_create(const DdkConfig* cfg, const float* weights_h, size_t n_floats, co
   if ((e = cudaMemset(c->b_edge_total.p, 0, 8)) != cudaSuccess) return bail("cudaMemset(counter)", e);
   if ((e = conv_configure()) != cudaSuccess) return bail("cudaFuncSetAttribute(conv)", e);
   if ((e = heads_configure()) != cudaSuccess) return bail("cudaFuncSetAttribute(heads)", e);
+  if ((e = conv2_configure()) != cudaSuccess) return bail("cudaFuncSetAttribute(conv2)", e);
+  { const char* v = getenv("DDK_CONV_V1"); c->conv_v1 = v && v[0] == '1'; }
   *out = c;
   return DDK_OK;
 }

@@ -95,6 +95,8 @@ struct DdkCtx {
   ddk::Buf b_edge_total;              // device uint64: edges of every combined graph built so far
   float* x_final = nullptr;           // points into xa or xb after the last conv layer
 
+  bool conv_v1 = false;               // DDK_CONV_V1=1: use the simple one-CTA-per-segment accumulate kernel
+
   // optional profiling (off by default)
   bool prof = false;
   std::vector<ddk::ProfRec> prof_recs;

@@ -127,6 +127,7 @@ int ddk_create(const DdkConfig* cfg, const float* weights_h, size_t n_floats, co
   if ((e = conv_configure()) != cudaSuccess) return bail("cudaFuncSetAttribute(conv)", e);
   if ((e = heads_configure()) != cudaSuccess) return bail("cudaFuncSetAttribute(heads)", e);
   if ((e = conv2_configure()) != cudaSuccess) return bail("cudaFuncSetAttribute(conv2)", e);
+  if ((e = contract2_configure()) != cudaSuccess) return bail("cudaFuncSetAttribute(contract2)", e);
   { const char* v = getenv("DDK_CONV_V1"); c->conv_v1 = v && v[0] == '1'; }
   *out = c;
   return DDK_OK;

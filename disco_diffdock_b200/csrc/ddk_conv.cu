@@ -220,17 +220,6 @@ __global__ void __launch_bounds__(ACC_THREADS, 2) k_conv_accum(AccArgs p) {
 }
 
 // ------------------------------------------------------------------------------------------------ contract
-struct ConArgs {
-  int NL;
-  int lig0, lig1, rec0, rec1;     // node ranges of this chunk (rec indices are within the receptor type)
-  const int* seg_sidx; const int* seg_cnt;
-  const float* A; const float* Bsum;
-  const float* W2p[4]; const float* b2p[4];
-  const float* bn_scale; const float* bn_shift;
-  const float* x_in; float* x_out;
-  LayerInfo li;
-};
-
 constexpr int CON_TM = 32;        // nodes per CTA
 constexpr int CON_KT = 128;       // K rows of W2p staged per pass
 
@@ -434,7 +423,12 @@ void launch_conv_layer(DdkCtx* c, int layer, const float* x_in, float* x_out, cu
     q.x_in = x_in; q.x_out = x_out;
     q.li = li;
     int blocks = (ch.lig1 - ch.lig0 + CON_TM - 1) / CON_TM + (ch.rec1 - ch.rec0 + CON_TM - 1) / CON_TM;
-    { LaunchScope ls(c, PC_CONTRACT, st); k_conv_contract<<<blocks, 256, 0, st>>>(q); }
+    if (!c->conv_v1) {
+      launch_conv_contract2(c, q, st);
+    } else {
+      LaunchScope ls(c, PC_CONTRACT, st);
+      k_conv_contract<<<blocks, 256, 0, st>>>(q);
+    }
   }
 }
 

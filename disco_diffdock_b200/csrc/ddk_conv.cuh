@@ -63,7 +63,22 @@ struct AccCfg {
 };
 
 
+// ---- contraction
+struct ConArgs {
+  int NL;
+  int lig0, lig1, rec0, rec1;     // node ranges of this chunk (rec indices are within the receptor type)
+  const int* seg_sidx; const int* seg_cnt;
+  const float* A; const float* Bsum;
+  const float* W2p[4]; const float* b2p[4];
+  const float* bn_scale; const float* bn_shift;
+  const float* x_in; float* x_out;
+  LayerInfo li;
+};
+
+
+void launch_conv_contract2(DdkCtx* c, const ConArgs& q, cudaStream_t st);
 void launch_conv_accum2(DdkCtx* c, const LayerInfo& li, const Chunk& ch, const AccArgs& a, cudaStream_t st);
 cudaError_t conv2_configure();
+cudaError_t contract2_configure();
 
 }  // namespace ddk

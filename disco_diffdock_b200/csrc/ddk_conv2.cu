@@ -94,25 +94,28 @@ __global__ void __launch_bounds__(ACC2_THREADS, 1) k_conv_accum2(AccArgs p, int 
       c0 += d.kc;
       return d;
     };
+    // chunk-invariant (edge, 16-byte piece) coordinates of the copies this thread issues
+    constexpr int XQ = DINP / 4, PQ = HID / 4, EQ = EA / 4;
+    constexpr int NX = (KC * XQ + NPROD - 1) / NPROD, NP = (KC * PQ + NPROD - 1) / NPROD;
+    int xe[NX], xq[NX], pe[NP], pq[NP];
+#pragma unroll
+    for (int r = 0; r < NX; ++r) { int i = t + r * NPROD; xe[r] = i / XQ; xq[r] = i % XQ; }
+#pragma unroll
+    for (int r = 0; r < NP; ++r) { int i = t + r * NPROD; pe[r] = i / PQ; pq[r] = i % PQ; }
+    const int ee = t / EQ, eq = t % EQ;     // KC * EQ == NPROD: exactly one edge-embedding piece per thread
+    static_assert(KC * (EA / 4) == NPROD, "one Ea piece per producer thread");
     auto issue_gather = [&](const ChunkDesc& d, typename Acc2Smem<LV>::Gather& G) {
       const int dslot = (d.g == 1 || d.g == 3) ? 3 : 2;
       const int2* lst = p.seg_list + d.base + d.c0;
-      for (int i = t; i < d.kc * (EA / 4); i += NPROD) {
-        int e = i / (EA / 4), q = i % (EA / 4);
-        int2 ent = lst[e];
-        __pipeline_memcpy_async(&G.Ea[e][4 * q], p.ea_pool + (size_t)ent.x * EA + 4 * q, 16);
-      }
-      for (int e = t; e < d.kc; e += NPROD) __pipeline_memcpy_async(&G.Sh[e][0], p.sh_pool + lst[e].x, 16);
-      for (int i = t; i < d.kc * (DINP / 4); i += NPROD) {
-        int e = i / (DINP / 4), q = i % (DINP / 4);
-        int2 ent = lst[e];
-        __pipeline_memcpy_async(&G.Xd[e][4 * q], p.x + (size_t)ent.y * D + 4 * q, 16);
-      }
-      for (int i = t; i < d.kc * (HID / 4); i += NPROD) {
-        int e = i / (HID / 4), q = i % (HID / 4);
-        int2 ent = lst[e];
-        __pipeline_memcpy_async(&G.Pd[e][4 * q], p.proj + ((size_t)ent.y * 4 + dslot) * HID + 4 * q, 16);
-      }
+      if (ee < d.kc) __pipeline_memcpy_async(&G.Ea[ee][4 * eq], p.ea_pool + (size_t)lst[ee].x * EA + 4 * eq, 16);
+      if (t < d.kc) __pipeline_memcpy_async(&G.Sh[t][0], p.sh_pool + lst[t].x, 16);
+#pragma unroll
+      for (int r = 0; r < NX; ++r)
+        if (xe[r] < d.kc) __pipeline_memcpy_async(&G.Xd[xe[r]][4 * xq[r]], p.x + (size_t)lst[xe[r]].y * D + 4 * xq[r], 16);
+#pragma unroll
+      for (int r = 0; r < NP; ++r)
+        if (pe[r] < d.kc)
+          __pipeline_memcpy_async(&G.Pd[pe[r]][4 * pq[r]], p.proj + ((size_t)lst[pe[r]].y * 4 + dslot) * HID + 4 * pq[r], 16);
       if (t < HID / 4) __pipeline_memcpy_async(&G.Ps[4 * t], p.proj + ((size_t)d.node * 4 + d.which) * HID + 4 * t, 16);
       __pipeline_commit();
     };
@@ -170,28 +173,44 @@ __global__ void __launch_bounds__(ACC2_THREADS, 1) k_conv_accum2(AccArgs p, int 
             out[q] = make_float4(fmaxf(h[4 * q], 0.f), fmaxf(h[4 * q + 1], 0.f), fmaxf(h[4 * q + 2], 0.f), fmaxf(h[4 * q + 3], 0.f));
         }
       }
-      // ---- basis functions (raw products; the constant factors live in the packed weights)
+      // ---- basis functions (raw products; the constant factors live in the packed weights).  The per-row type is
+      //      hoisted out of the edge loop so the loop bodies are straight-line LDS / FMUL / STS with constant strides.
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
         const int u = t + r * NPROD;
         if (u < BS) {
+          float* bp = &T.B[0][u];
           if (u < U) {
             const int ty = btype[r], i0 = bi0[r], m = bm[r];
-            const int c = m - 1, c1 = (c + 1) % 3, c2 = (c + 2) % 3;
+            const float* xp = &G.Xd[0][i0];
+            const float* sp = &G.Sh[0][0];
             float acc = 0.f;
-            for (int e = 0; e < cur.kc; ++e) {
-              const float* xd = &G.Xd[e][0];
-              const float* sh = &G.Sh[e][0];
-              float b;
-              if (ty == 0) b = xd[i0] * sh[m];
-              else if (ty == 1) b = xd[i0] * sh[1] + xd[i0 + 1] * sh[2] + xd[i0 + 2] * sh[3];
-              else b = xd[i0 + c1] * sh[1 + c2] - xd[i0 + c2] * sh[1 + c1];
-              T.B[e][u] = b;
-              acc += b;
+            if (ty == 0) {
+#pragma unroll 4
+              for (int e = 0; e < cur.kc; ++e) {
+                float b = xp[e * DINP] * sp[e * 4 + m];
+                bp[e * BS] = b;
+                acc += b;
+              }
+            } else if (ty == 1) {
+#pragma unroll 4
+              for (int e = 0; e < cur.kc; ++e) {
+                float b = xp[e * DINP] * sp[e * 4 + 1] + xp[e * DINP + 1] * sp[e * 4 + 2] + xp[e * DINP + 2] * sp[e * 4 + 3];
+                bp[e * BS] = b;
+                acc += b;
+              }
+            } else {
+              const int c = m - 1, c1 = (c + 1) % 3, c2 = (c + 2) % 3;
+#pragma unroll 4
+              for (int e = 0; e < cur.kc; ++e) {
+                float b = xp[e * DINP + c1] * sp[e * 4 + 1 + c2] - xp[e * DINP + c2] * sp[e * 4 + 1 + c1];
+                bp[e * BS] = b;
+                acc += b;
+              }
             }
             bsum[r] += acc;
           } else {
-            for (int e = 0; e < cur.kc; ++e) T.B[e][u] = 0.f;
+            for (int e = 0; e < cur.kc; ++e) bp[e * BS] = 0.f;
           }
         }
       }

@@ -158,7 +158,6 @@ class Engine:
     def set_batch(self, data, assume_copies: bool = False) -> SimpleNamespace:
         """Upload the step-invariant part of a PyG-style batch (utils/sampling.py:56-67) and run the per-batch
         setup kernels.  Returns sizes / index info of the batch."""
-        dev = self.device
         lig, rec = data['ligand'], data['receptor']
         B = int(data.num_graphs)
         lb = lig.batch.cpu().long() if 'batch' in lig else torch.zeros(lig.num_nodes, dtype=torch.long)
@@ -175,70 +174,117 @@ class Engine:
         RB = int(edge_mask.sum())
         # mask_rotate: list (one entry per graph, possibly nested) of [R, N] arrays; identical arrays are stored once
         mr_off = np.zeros(B, dtype=np.int64)
-        mr_dev = None
+        mr_flat = None
         if RB > 0 and not self.hyper.no_torsion:
             mr = lig.mask_rotate if 'mask_rotate' in lig else None
             if mr is None:
                 raise RuntimeError('batch has rotatable bonds but no mask_rotate')
             per_graph = [mr[g] for g in range(B)] if isinstance(mr, (list, tuple)) and len(mr) == B and B > 1 else [mr] * B
-            chunks, seen, off = [], {}, 0
+            chunks, off = [], 0
             for g in range(B):
                 m = _unwrap_mask(per_graph[g])
-                key = id(per_graph[g]) if not isinstance(per_graph[g], (list, tuple)) else id(per_graph[g][0])
                 nl = int(lig_ptr[g + 1] - lig_ptr[g])
                 rg = int(edge_mask[bond_ptr[g]:bond_ptr[g + 1]].sum())
                 if m.shape != (rg, nl):
                     raise RuntimeError(f'mask_rotate of graph {g} has shape {m.shape}, expected {(rg, nl)}')
-                h = (key, m.shape)
-                if h not in seen:
-                    found = None
-                    for (o, mm) in chunks:      # dedupe equal content (deep copies of one complex)
-                        if mm.shape == m.shape and np.array_equal(mm, m):
-                            found = o
-                            break
-                    if found is None:
-                        chunks.append((off, m))
-                        found = off
-                        off += m.size
-                    seen[h] = found
-                mr_off[g] = seen[h]
-            flat = np.concatenate([m.ravel() for _, m in chunks]) if chunks else np.zeros(1, np.uint8)
-            mr_dev = torch.from_numpy(flat).to(dev)
+                found = None
+                for (o, mm) in chunks:      # dedupe equal content (deep copies of one complex)
+                    if mm.shape == m.shape and np.array_equal(mm, m):
+                        found = o
+                        break
+                if found is None:
+                    chunks.append((off, m))
+                    found = off
+                    off += m.size
+                mr_off[g] = found
+            mr_flat = np.concatenate([m.ravel() for _, m in chunks]) if chunks else np.zeros(1, np.uint8)
         L = self.hyper.latent_dim
-        t = SimpleNamespace()
-        t.lig_x = lig.x.to(dev, torch.int32).contiguous()
-        t.bond_attr = data['ligand', 'ligand'].edge_attr.to(dev, torch.float32).contiguous()
-        nr0 = int(rec_ptr[1])
-        if assume_copies and B > 1 and rec.x.shape[0] == B * nr0:
-            # sampling() batches are B copies of one complex (utils/sampling.py:57): ship the receptor once
-            t.rec_x = rec.x[:nr0].to(dev, torch.float32).repeat(B, 1).contiguous()
-            t.rec_pos = rec.pos[:nr0].to(dev, torch.float32).repeat(B, 1).contiguous()
-            h2d_saved = (B - 1) * nr0 * (rec.x.shape[1] + 3) * 4
-        else:
-            t.rec_x = rec.x.to(dev, torch.float32).contiguous()
-            t.rec_pos = rec.pos.to(dev, torch.float32).contiguous()
-            h2d_saved = 0
-        t.mask_rotate = mr_dev
-        t.lig_latent = lig.latent_h.to(dev, torch.float32).contiguous() if L > 0 else None
-        t.rec_latent = rec.latent_h.to(dev, torch.float32).contiguous() if L > 0 else None
         unc = self.hyper.latent_droprate > 0
-        t.lig_uncond = lig.unconditional.to(dev, torch.float32).reshape(-1).contiguous() if unc and 'unconditional' in lig else None
-        t.rec_uncond = rec.unconditional.to(dev, torch.float32).reshape(-1).contiguous() if unc and 'unconditional' in rec else None
-        assert t.rec_x.shape[1] == 1281 and t.lig_x.shape[1] == 16
+        nr0 = int(rec_ptr[1])
+        share_rec = assume_copies and B > 1 and rec.x.shape[0] == B * nr0
         host = SimpleNamespace(lig_ptr=lig_ptr, rec_ptr=rec_ptr, bond_index=bond_index, bond_ptr=bond_ptr,
                                edge_mask=edge_mask, rec_index=rec_index, rec_eptr=rec_eptr, mr_off=mr_off)
-        b = DdkBatch(B=B, NL=int(lig_ptr[-1]), NR=int(rec_ptr[-1]), EB=bond_index.shape[1], ER=rec_index.shape[1], RB=RB,
-                     lig_ptr_h=_np_ptr(lig_ptr), rec_ptr_h=_np_ptr(rec_ptr), bond_index_h=_np_ptr(bond_index),
-                     bond_ptr_h=_np_ptr(bond_ptr), edge_mask_h=_np_ptr(edge_mask), rec_index_h=_np_ptr(rec_index),
-                     rec_edge_ptr_h=_np_ptr(rec_eptr), mask_rotate_off_h=_np_ptr(mr_off),
+        return self._upload(B, RB, host, mr_flat, lig_x=lig.x, bond_attr=data['ligand', 'ligand'].edge_attr,
+                            rec_x=rec.x[:nr0] if share_rec else rec.x, rec_pos=rec.pos[:nr0] if share_rec else rec.pos,
+                            rec_repeat=B if share_rec else 1, lig_repeat=1,
+                            lig_latent=lig.latent_h if L > 0 else None, rec_latent=rec.latent_h if L > 0 else None,
+                            lig_uncond=lig.unconditional if unc and 'unconditional' in lig else None,
+                            rec_uncond=rec.unconditional if unc and 'unconditional' in rec else None)
+
+    def set_batch_copies(self, proto, B: int) -> SimpleNamespace:
+        """``B`` copies of one complex (what ``sampling()`` batches are, utils/sampling.py:57) without materialising the
+        PyG batch on the host: the complex is shipped once and replicated on the device."""
+        lig, rec = proto['ligand'], proto['receptor']
+        nl, nr = int(lig.num_nodes), int(rec.num_nodes)
+        bei = proto['ligand', 'ligand'].edge_index.cpu().numpy().astype(np.int64)
+        rei = proto['receptor', 'receptor'].edge_index.cpu().numpy().astype(np.int64)
+        eb, er = bei.shape[1], rei.shape[1]
+        ar = np.arange(B, dtype=np.int64)
+        lig_ptr = (np.arange(B + 1) * nl).astype(np.int32)
+        rec_ptr = (np.arange(B + 1) * nr).astype(np.int32)
+        bond_index = np.ascontiguousarray((bei[:, None, :] + (ar * nl)[None, :, None]).reshape(2, B * eb).astype(np.int32))
+        rec_index = np.ascontiguousarray((rei[:, None, :] + (ar * nr)[None, :, None]).reshape(2, B * er).astype(np.int32))
+        bond_ptr = (np.arange(B + 1) * eb).astype(np.int32)
+        rec_eptr = (np.arange(B + 1) * er).astype(np.int32)
+        em1 = lig.edge_mask.cpu().numpy().astype(np.uint8)
+        edge_mask = np.ascontiguousarray(np.tile(em1, B))
+        RB = int(em1.sum()) * B
+        mr_flat = None
+        if RB > 0 and not self.hyper.no_torsion:
+            mr_flat = _unwrap_mask(lig.mask_rotate).ravel()
+            if mr_flat.size != int(em1.sum()) * nl:
+                raise RuntimeError('mask_rotate does not match edge_mask / ligand size')
+        host = SimpleNamespace(lig_ptr=lig_ptr, rec_ptr=rec_ptr, bond_index=bond_index, bond_ptr=bond_ptr,
+                               edge_mask=edge_mask, rec_index=rec_index, rec_eptr=rec_eptr, mr_off=np.zeros(B, dtype=np.int64))
+        if self.hyper.latent_dim > 0:
+            raise RuntimeError('set_batch_copies does not carry per-copy latents; use set_batch')
+        return self._upload(B, RB, host, mr_flat, lig_x=lig.x, bond_attr=proto['ligand', 'ligand'].edge_attr, rec_x=rec.x,
+                            rec_pos=rec.pos, rec_repeat=B, lig_repeat=B, lig_latent=None, rec_latent=None,
+                            lig_uncond=None, rec_uncond=None)
+
+    def _upload(self, B, RB, host, mr_flat, lig_x, bond_attr, rec_x, rec_pos, rec_repeat, lig_repeat, lig_latent, rec_latent,
+                lig_uncond, rec_uncond) -> SimpleNamespace:
+        dev = self.device
+        h2d = 0
+
+        def up(x, dtype, repeat=1, flat=False):
+            nonlocal h2d
+            if x is None:
+                return None
+            if not x.is_cuda:
+                h2d += x.numel() * torch.empty(0, dtype=dtype).element_size()
+            y = x.to(dev, dtype, non_blocking=True)
+            if flat:
+                y = y.reshape(-1)
+            if repeat > 1:
+                y = y.repeat(repeat, *([1] * (y.dim() - 1)))
+            return y.contiguous()
+
+        t = SimpleNamespace()
+        t.lig_x = up(lig_x, torch.int32, lig_repeat)
+        t.bond_attr = up(bond_attr, torch.float32, lig_repeat)
+        t.rec_x = up(rec_x, torch.float32, rec_repeat)
+        t.rec_pos = up(rec_pos, torch.float32, rec_repeat)
+        t.mask_rotate = up(torch.from_numpy(mr_flat), torch.uint8) if mr_flat is not None else None
+        t.lig_latent = up(lig_latent, torch.float32)
+        t.rec_latent = up(rec_latent, torch.float32)
+        t.lig_uncond = up(lig_uncond, torch.float32, flat=True)
+        t.rec_uncond = up(rec_uncond, torch.float32, flat=True)
+        assert t.rec_x.shape[1] == 1281 and t.lig_x.shape[1] == 16
+        b = DdkBatch(B=B, NL=int(host.lig_ptr[-1]), NR=int(host.rec_ptr[-1]), EB=host.bond_index.shape[1],
+                     ER=host.rec_index.shape[1], RB=RB,
+                     lig_ptr_h=_np_ptr(host.lig_ptr), rec_ptr_h=_np_ptr(host.rec_ptr), bond_index_h=_np_ptr(host.bond_index),
+                     bond_ptr_h=_np_ptr(host.bond_ptr), edge_mask_h=_np_ptr(host.edge_mask), rec_index_h=_np_ptr(host.rec_index),
+                     rec_edge_ptr_h=_np_ptr(host.rec_eptr), mask_rotate_off_h=_np_ptr(host.mr_off),
                      lig_x=_ptr(t.lig_x), bond_attr=_ptr(t.bond_attr), rec_x=_ptr(t.rec_x), rec_pos=_ptr(t.rec_pos),
                      mask_rotate=_ptr(t.mask_rotate), lig_latent=_ptr(t.lig_latent), rec_latent=_ptr(t.rec_latent),
                      lig_uncond=_ptr(t.lig_uncond), rec_uncond=_ptr(t.rec_uncond))
+        assert t.lig_x.shape[0] == b.NL and t.rec_x.shape[0] == b.NR and t.bond_attr.shape[0] == b.EB
         with torch.cuda.device(dev):
             self._check(self.lib.ddk_set_batch(self.ctx, C.byref(b), self.stream()), 'ddk_set_batch')
         self._keep = [t, host]     # the context references rec_pos / bond_attr / masks / latents of the caller
-        self.batch_info = SimpleNamespace(B=B, NL=b.NL, NR=b.NR, EB=b.EB, ER=b.ER, RB=RB, lig_ptr=lig_ptr, rec_ptr=rec_ptr,
-                                          h2d_bytes=sum(x.numel() * x.element_size() for x in vars(t).values() if x is not None) - h2d_saved)
+        self.batch_info = SimpleNamespace(B=B, NL=b.NL, NR=b.NR, EB=b.EB, ER=b.ER, RB=RB, lig_ptr=host.lig_ptr,
+                                          rec_ptr=host.rec_ptr, h2d_bytes=h2d)
         return self.batch_info
 
     # ------------------------------------------------------------------------------------------ steps

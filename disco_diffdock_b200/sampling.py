@@ -19,7 +19,7 @@ from typing import Dict, Optional
 import numpy as np
 import torch
 
-from .data import DataLoader
+from .data import Batch, DataLoader
 from .engine import StepTables, so3_score_norm, torus_score_norm
 
 
@@ -137,7 +137,6 @@ def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_s
     N = len(data_list)
     device = torch.device(device)
     sm = _score_model_of(model)
-    loader = DataLoader(data_list, batch_size=batch_size)
     confidence = [] if confidence_model is not None else None
     conf_loader = iter(DataLoader(confidence_data_list, batch_size=batch_size)) if confidence_data_list is not None else None
     latent = use_latent and getattr(model_args, 'latent_dim', 0) > 0
@@ -145,23 +144,33 @@ def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_s
         raise NotImplementedError('classifier-free guidance (two score evaluations per step) is not wired up yet')
     pose0 = 0
     with torch.no_grad():
-        for batch_id, batch in enumerate(loader):
-            b = batch.num_graphs
-            if latent:
-                if ar_model is None:
-                    raise NotImplementedError('oracle latent encoder (TPEncoder) is out of scope; pass ar_model')
-                from .latent import encode_ar_batch
-                pos_keep = batch['ligand'].pos
-                if 'ar_pos' in batch['ligand']:
-                    batch['ligand'].pos = batch['ligand'].ar_pos
-                lat_l, lat_r = encode_ar_batch(ar_model, batch, softmax_latent_temperature, device, generator=generator)
-                batch['ligand'].pos = pos_keep
-                batch['ligand'].latent_h, batch['receptor'].latent_h = lat_l, lat_r
-            if getattr(sm, 'latent_droprate', 0) > 0:
-                batch['ligand'].unconditional = torch.zeros(batch['ligand'].num_nodes, 1)
-                batch['receptor'].unconditional = torch.zeros(batch['receptor'].num_nodes, 1)
+        n_batches = (N + batch_size - 1) // batch_size
+        fast = not latent and confidence_model is None      # copies of one complex: no host-side PyG collation needed
+        for batch_id in range(n_batches):
+            items = data_list[batch_id * batch_size:(batch_id + 1) * batch_size]
+            b = len(items)
             eng = sm.engine(device)
-            info = eng.set_batch(batch, assume_copies=True)
+            if fast:
+                batch = None
+                start_pos = torch.cat([x['ligand'].pos for x in items], dim=0)
+                info = eng.set_batch_copies(items[0], b)
+            else:
+                batch = Batch.from_data_list(items)
+                if latent:
+                    if ar_model is None:
+                        raise NotImplementedError('oracle latent encoder (TPEncoder) is out of scope; pass ar_model')
+                    from .latent import encode_ar_batch
+                    pos_keep = batch['ligand'].pos
+                    if 'ar_pos' in batch['ligand']:
+                        batch['ligand'].pos = batch['ligand'].ar_pos
+                    lat_l, lat_r = encode_ar_batch(ar_model, batch, softmax_latent_temperature, device, generator=generator)
+                    batch['ligand'].pos = pos_keep
+                    batch['ligand'].latent_h, batch['receptor'].latent_h = lat_l, lat_r
+                if getattr(sm, 'latent_droprate', 0) > 0:
+                    batch['ligand'].unconditional = torch.zeros(batch['ligand'].num_nodes, 1)
+                    batch['receptor'].unconditional = torch.zeros(batch['receptor'].num_nodes, 1)
+                start_pos = batch['ligand'].pos
+                info = eng.set_batch(batch, assume_copies=True)
             eng._batch_key = None
             steps = build_step_tables(sm, model_args, t_to_sigma, tr_schedule, rot_schedule, tor_schedule, inference_steps, b,
                                       temp_sampling, temp_psi, temp_sigma_data, ode)
@@ -182,12 +191,13 @@ def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_s
                         if v is not None:
                             v[-1] = 0
             if host_buffers:
-                pos = batch['ligand'].pos.detach().to('cpu', torch.float32).contiguous()
+                pos = start_pos.detach().to('cpu', torch.float32).contiguous()
                 eng.sample_host(pos, steps, z)
             else:
-                pos = batch['ligand'].pos.to(device, torch.float32).contiguous().clone()
+                pos = start_pos.to(device, torch.float32).contiguous().clone()
                 eng.sample(pos, steps, z)
-            batch['ligand'].pos = pos
+            if batch is not None:
+                batch['ligand'].pos = pos
             len_lig = pos.shape[0] // b
             for i in range(b):
                 data_list[batch_id * batch_size + i]['ligand'].pos = pos[i * len_lig:(i + 1) * len_lig]

@@ -140,7 +140,7 @@ int ddk_destroy(DdkCtx* c) {
                 &c->b_rr_dst, &c->b_rot_u, &c->b_rot_v, &c->b_rot_ptr, &c->b_rot_graph, &c->b_mr_off, &c->b_ll_off,
                 &c->b_lr_off, &c->b_seg_base, &c->b_seg_static, &c->b_seg_cnt, &c->b_seg_list, &c->b_seg_order,
                 &c->b_seg_sidx, &c->b_lig_static, &c->b_rec_static, &c->b_rr_pre, &c->b_ea_pool, &c->b_sh_pool, &c->b_tb,
-                &c->b_xa, &c->b_xb, &c->b_proj, &c->b_A, &c->b_Bsum, &c->b_tr, &c->b_rot, &c->b_tor, &c->b_pos, &c->b_step, &c->b_edge_total};
+                &c->b_xa, &c->b_xb, &c->b_proj, &c->b_A, &c->b_Bsum, &c->b_tr, &c->b_rot, &c->b_tor, &c->b_pos, &c->b_step, &c->b_edge_total, &c->b_work, &c->b_nwork};
   for (Buf* b : all) free_buf(*b);
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   if (c->w) cudaFree(c->w);
@@ -290,6 +290,7 @@ int ddk_set_batch(DdkCtx* c, const DdkBatch* b, void* stream) {
   EN(c->b_tb, (size_t)B * TB_COUNT * NS * 4);
   EN(c->b_xa, (size_t)c->N * D * 4); EN(c->b_xb, (size_t)c->N * D * 4); EN(c->b_proj, (size_t)c->N * 4 * HID * 4);
   EN(c->b_A, (size_t)max_chunk_segs * seg_bytes); EN(c->b_Bsum, (size_t)max_chunk_segs * Umax * 4);
+  EN(c->b_work, (size_t)nsegs * 16); EN(c->b_nwork, (size_t)c->chunks.size() * 4);
   EN(c->b_tr, (size_t)B * 3 * 4); EN(c->b_rot, (size_t)B * 3 * 4); EN(c->b_tor, (size_t)std::max(c->RB, 1) * 4);
 #undef EN
   launch_setup(c, b, b->lig_x, b->rec_x, st);
@@ -304,6 +305,7 @@ static int run_embed(DdkCtx* c, const float* lig_pos, const DdkStepInputs* in, c
   launch_step_consts(c, in->sigma_emb, st);
   launch_build_lists(c, lig_pos, in->cross_cutoff, st);
   launch_edge_features(c, lig_pos, st);
+  if (!c->conv_v1) launch_build_worklist(c, st);
   float* xa = ptr<float>(c->b_xa);
   float* xb = ptr<float>(c->b_xb);
   launch_node_proj(c, 0, nullptr, xa, st);

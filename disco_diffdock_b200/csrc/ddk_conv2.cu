@@ -38,7 +38,8 @@ struct Acc2Smem {
     alignas(16) float Xd[KC][AccCfg<LV>::DINP];
     alignas(16) float Pd[KC][HID];
     alignas(16) float Ps[HID];
-  } ga[2];
+  } ga[3];
+  int2 ent[3][KC];                      // (slot, dst) entries of the chunks whose gathers are being issued
   alignas(16) float W1aT[4][EA][HID];   // [group][k][j] = W1_g[j][k], k < 24 (edge-embedding columns)
 };
 
@@ -46,8 +47,35 @@ struct ChunkDesc {
   int seg, node, which, g, base, c0, kc, last, sidx, done;
 };
 
+// Ordered compaction of the non-empty segments of one graph chunk into packed descriptors (seg, n, base, sidx), so
+// the accumulate kernel fetches a segment with ONE 16-byte load that it can issue a whole segment ahead of time.
+__global__ void __launch_bounds__(1024) k_build_worklist(const int* __restrict__ seg_order, int nseg, const int* __restrict__ seg_cnt,
+                                                         const int* __restrict__ seg_base, const int* __restrict__ seg_sidx,
+                                                         int4* __restrict__ work, int* __restrict__ n_work) {
+  __shared__ int wsum[32];
+  __shared__ int base_s;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  if (tid == 0) base_s = 0;
+  __syncthreads();
+  for (int i0 = 0; i0 < nseg; i0 += 1024) {
+    const int i = i0 + tid;
+    int seg = 0, n = 0;
+    if (i < nseg) { seg = seg_order[i]; n = seg_cnt[seg]; }
+    const unsigned m = __ballot_sync(0xffffffffu, n > 0);
+    if (lane == 0) wsum[w] = __popc(m);
+    __syncthreads();
+    int off = base_s;
+    for (int q = 0; q < w; ++q) off += wsum[q];
+    if (n > 0) work[off + __popc(m & ((1u << lane) - 1))] = make_int4(seg, n, seg_base[seg], seg_sidx[seg]);
+    __syncthreads();
+    if (tid == 0) { int t = 0; for (int q = 0; q < 32; ++q) t += wsum[q]; base_s += t; }
+    __syncthreads();
+  }
+  if (tid == 0) *n_work = base_s;
+}
+
 template <int LV>
-__global__ void __launch_bounds__(ACC2_THREADS, 1) k_conv_accum2(AccArgs p, int nseg) {
+__global__ void __launch_bounds__(ACC2_THREADS, 1) k_conv_accum2(AccArgs p, const int4* __restrict__ work, const int* __restrict__ n_work) {
   constexpr int U = AccCfg<LV>::U;
   constexpr int NA = AccCfg<LV>::NA;
   constexpr int BS = AccCfg<LV>::BS;
@@ -69,28 +97,29 @@ __global__ void __launch_bounds__(ACC2_THREADS, 1) k_conv_accum2(AccArgs p, int 
     basis_desc<LV>(t + NPROD < U ? t + NPROD : 0, btype[1], bi0[1], bm[1]);
     float bsum[2] = {0.f, 0.f};
 
-    // static round-robin walk over the LPT-ordered segment list, one chunk of <= KC edges at a time
-    int oi = blockIdx.x - gridDim.x;   // order index of the current segment
-    int seg = -1, n = 0, c0 = 0;
+    // static round-robin walk over the compacted, LPT-ordered work list, one chunk of <= KC edges at a time; the
+    // descriptor of the next segment is loaded one segment ahead so its latency never sits on the critical path
+    const int nwork = *n_work;
+    int oi = blockIdx.x;               // work index of the descriptor held in `pre`
+    int4 pre = oi < nwork ? work[oi] : make_int4(-1, 0, 0, 0);
+    int seg = -1, n = 0, c0 = 0, sbase = 0, ssidx = 0;
     auto next_desc = [&]() {
       ChunkDesc d;
       d.done = 0;
       if (seg < 0 || c0 >= n) {
-        do {
-          oi += gridDim.x;
-          if (oi >= nseg) { d.done = 1; d.kc = -1; d.seg = -1; d.node = d.which = d.g = d.base = d.c0 = d.last = d.sidx = 0; return d; }
-          seg = p.seg_order[oi];
-          n = p.seg_cnt[seg];
-        } while (n == 0);
+        if (pre.x < 0) { d.done = 1; d.kc = -1; d.seg = -1; d.node = d.which = d.g = d.base = d.c0 = d.last = d.sidx = 0; return d; }
+        seg = pre.x; n = pre.y; sbase = pre.z; ssidx = pre.w;
         c0 = 0;
+        oi += gridDim.x;
+        pre = oi < nwork ? work[oi] : make_int4(-1, 0, 0, 0);
       }
       d.seg = seg; d.node = seg >> 1; d.which = seg & 1;
       d.g = d.node < p.NL ? d.which : 2 + d.which;
-      d.base = p.seg_base[seg];
+      d.base = sbase;
       d.c0 = c0;
       d.kc = min(KC, n - c0);
       d.last = (c0 + d.kc >= n);
-      d.sidx = p.seg_sidx[seg];
+      d.sidx = ssidx;
       c0 += d.kc;
       return d;
     };
@@ -104,9 +133,8 @@ __global__ void __launch_bounds__(ACC2_THREADS, 1) k_conv_accum2(AccArgs p, int 
     for (int r = 0; r < NP; ++r) { int i = t + r * NPROD; pe[r] = i / PQ; pq[r] = i % PQ; }
     const int ee = t / EQ, eq = t % EQ;     // KC * EQ == NPROD: exactly one edge-embedding piece per thread
     static_assert(KC * (EA / 4) == NPROD, "one Ea piece per producer thread");
-    auto issue_gather = [&](const ChunkDesc& d, typename Acc2Smem<LV>::Gather& G) {
+    auto issue_gather = [&](const ChunkDesc& d, typename Acc2Smem<LV>::Gather& G, const int2* lst) {
       const int dslot = (d.g == 1 || d.g == 3) ? 3 : 2;
-      const int2* lst = p.seg_list + d.base + d.c0;
       if (ee < d.kc) __pipeline_memcpy_async(&G.Ea[ee][4 * eq], p.ea_pool + (size_t)lst[ee].x * EA + 4 * eq, 16);
       if (t < d.kc) __pipeline_memcpy_async(&G.Sh[t][0], p.sh_pool + lst[t].x, 16);
 #pragma unroll
@@ -119,19 +147,34 @@ __global__ void __launch_bounds__(ACC2_THREADS, 1) k_conv_accum2(AccArgs p, int 
       if (t < HID / 4) __pipeline_memcpy_async(&G.Ps[4 * t], p.proj + ((size_t)d.node * 4 + d.which) * HID + 4 * t, 16);
       __pipeline_commit();
     };
+    // the (slot, dst) entries themselves are fetched by one warp a full iteration before the gathers that need them
+    int2 ent_reg = make_int2(0, 0);
+    auto load_ent = [&](const ChunkDesc& d) {
+      if (!d.done && t < d.kc) ent_reg = p.seg_list[d.base + d.c0 + t];
+    };
 
-    ChunkDesc cur = next_desc();
-    if (!cur.done) issue_gather(cur, S.ga[0]);
+    // gathers run two chunks ahead of the math (three gather buffers), entry lists three chunks ahead
+    ChunkDesc dq[4];
+    dq[0] = next_desc();
+    dq[1] = dq[0].done ? dq[0] : next_desc();
+    dq[2] = dq[1].done ? dq[1] : next_desc();
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {                    // prologue: chunks 0 and 1 pay the entry latency once
+      load_ent(dq[k]);
+      if (t < KC) S.ent[k][t] = ent_reg;
+      bar_sync(BAR_PROD, NPROD);
+      if (!dq[k].done) issue_gather(dq[k], S.ga[k], S.ent[k]); else __pipeline_commit();
+    }
+    load_ent(dq[2]);
     for (int it = 0;; ++it) {
       const int s = it & 1;
-      __pipeline_wait_prior(0);                      // this thread's copies of chunk `it` have landed
-      bar_sync(BAR_PROD, NPROD);                     // ... everybody's have, and everybody is done reading ga[s ^ 1]
-      ChunkDesc nxt;
-      nxt.done = 1;
-      if (!cur.done) {
-        nxt = next_desc();
-        if (!nxt.done) issue_gather(nxt, S.ga[s ^ 1]);   // prefetch one chunk ahead; overlaps the math below
-      }
+      const ChunkDesc cur = dq[0];
+      __pipeline_wait_prior(1);                      // this thread's copies of chunk `it` have landed
+      if (t < KC) S.ent[(it + 2) % 3][t] = ent_reg;  // entries of chunk it+2 (loaded during the previous iteration)
+      bar_sync(BAR_PROD, NPROD);                     // ... everybody's have, and everybody is done with chunk it-1's buffer
+      dq[3] = dq[2].done ? dq[2] : next_desc();
+      load_ent(dq[3]);                               // entries of chunk it+3 start travelling
+      if (!dq[2].done) issue_gather(dq[2], S.ga[(it + 2) % 3], S.ent[(it + 2) % 3]); else __pipeline_commit();
       if (it >= 2) bar_sync(s ? BAR_EMPTY1 : BAR_EMPTY0, ACC2_THREADS);   // consumers released stage s
       typename Acc2Smem<LV>::Stage& T = S.st[s];
       if (cur.done) {
@@ -140,7 +183,7 @@ __global__ void __launch_bounds__(ACC2_THREADS, 1) k_conv_accum2(AccArgs p, int 
         bar_arrive(s ? BAR_FULL1 : BAR_FULL0, ACC2_THREADS);
         break;
       }
-      typename Acc2Smem<LV>::Gather& G = S.ga[s];
+      typename Acc2Smem<LV>::Gather& G = S.ga[it % 3];
       // ---- first radial-MLP layer: h = relu(W1[:, :24] ea + (W1[:,24:48] x_s + b1) + W1[:,48:72] x_d)
       {
         const int e = t & 31, jb = t >> 5;           // 12 hidden units per thread
@@ -225,7 +268,7 @@ __global__ void __launch_bounds__(ACC2_THREADS, 1) k_conv_accum2(AccArgs p, int 
       if (t == 0) { T.kc = cur.kc; T.sidx_last = cur.last ? cur.sidx : -1; }
       __threadfence_block();
       bar_arrive(s ? BAR_FULL1 : BAR_FULL0, ACC2_THREADS);
-      cur = nxt;
+      dq[0] = dq[1]; dq[1] = dq[2]; dq[2] = dq[3];
     }
     return;
   }
@@ -284,6 +327,17 @@ cudaError_t conv2_configure() {
   return cudaFuncSetAttribute(k_conv_accum2<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Acc2Smem<3>));
 }
 
+void launch_build_worklist(DdkCtx* c, cudaStream_t st) {
+  int ci = 0;
+  for (const Chunk& ch : c->chunks) {
+    LaunchScope ls(c, PC_GRAPH, st);
+    k_build_worklist<<<1, 1024, 0, st>>>(ptr<int>(c->b_seg_order) + ch.order_off, ch.nseg, ptr<int>(c->b_seg_cnt),
+                                         ptr<int>(c->b_seg_base), ptr<int>(c->b_seg_sidx),
+                                         ptr<int4>(c->b_work) + ch.order_off, ptr<int>(c->b_nwork) + ci);
+    ++ci;
+  }
+}
+
 void launch_conv_accum2(DdkCtx* c, const LayerInfo& li, const Chunk& ch, const AccArgs& a, cudaStream_t st) {
   static int sms = 0;
   if (sms == 0) {
@@ -292,12 +346,15 @@ void launch_conv_accum2(DdkCtx* c, const LayerInfo& li, const Chunk& ch, const A
     sms = prop.multiProcessorCount;
   }
   const int grid = std::min(ch.nseg, sms);
+  const int ci = (int)(&ch - c->chunks.data());
+  const int4* work = ptr<int4>(c->b_work) + ch.order_off;
+  const int* nwork = ptr<int>(c->b_nwork) + ci;
   LaunchScope ls(c, PC_ACC0 + li.lv, st);
   switch (li.lv) {
-    case 0: k_conv_accum2<0><<<grid, ACC2_THREADS, sizeof(Acc2Smem<0>), st>>>(a, ch.nseg); break;
-    case 1: k_conv_accum2<1><<<grid, ACC2_THREADS, sizeof(Acc2Smem<1>), st>>>(a, ch.nseg); break;
-    case 2: k_conv_accum2<2><<<grid, ACC2_THREADS, sizeof(Acc2Smem<2>), st>>>(a, ch.nseg); break;
-    default: k_conv_accum2<3><<<grid, ACC2_THREADS, sizeof(Acc2Smem<3>), st>>>(a, ch.nseg); break;
+    case 0: k_conv_accum2<0><<<grid, ACC2_THREADS, sizeof(Acc2Smem<0>), st>>>(a, work, nwork); break;
+    case 1: k_conv_accum2<1><<<grid, ACC2_THREADS, sizeof(Acc2Smem<1>), st>>>(a, work, nwork); break;
+    case 2: k_conv_accum2<2><<<grid, ACC2_THREADS, sizeof(Acc2Smem<2>), st>>>(a, work, nwork); break;
+    default: k_conv_accum2<3><<<grid, ACC2_THREADS, sizeof(Acc2Smem<3>), st>>>(a, work, nwork); break;
   }
 }
 

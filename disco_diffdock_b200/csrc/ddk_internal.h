@@ -92,6 +92,7 @@ struct DdkCtx {
   ddk::Buf b_xa, b_xb, b_proj, b_A, b_Bsum;
   ddk::Buf b_tr, b_rot, b_tor, b_pos;
   ddk::Buf b_step;                    // staging for ddk_sample_host
+  ddk::Buf b_work, b_nwork;           // compacted per-chunk segment work lists (rebuilt every step)
   ddk::Buf b_edge_total;              // device uint64: edges of every combined graph built so far
   float* x_final = nullptr;           // points into xa or xb after the last conv layer
 
@@ -140,6 +141,7 @@ void launch_setup(DdkCtx* c, const DdkBatch* b, const int32_t* lig_x, const floa
 void launch_step_consts(DdkCtx* c, const float* sigma_emb, cudaStream_t st);
 void launch_build_lists(DdkCtx* c, const float* lig_pos, const float* cutoff, cudaStream_t st);
 void launch_edge_features(DdkCtx* c, const float* lig_pos, cudaStream_t st);
+void launch_build_worklist(DdkCtx* c, cudaStream_t st);
 void launch_node_proj(DdkCtx* c, int layer, const float* x_in, float* x0_out, cudaStream_t st);
 void launch_conv_layer(DdkCtx* c, int layer, const float* x_in, float* x_out, cudaStream_t st);
 void launch_head_trrot(DdkCtx* c, const float* lig_pos, const float* x, const DdkStepInputs* in, float* tr, float* rot,

@@ -114,6 +114,8 @@ int ddk_create(const DdkConfig* cfg, const float* weights_h, size_t n_floats, co
   auto bail = [&](const char* what, cudaError_t err) {
     g_create_error = std::string(what) + ": " + cudaGetErrorString(err);
     if (c->w) cudaFree(c->w);
+    if (c->w2s) cudaFree(c->w2s);
+    if (c->btab) cudaFree(c->btab);
     delete c;
     return DDK_ERR_CUDA;
   };
@@ -128,7 +130,49 @@ int ddk_create(const DdkConfig* cfg, const float* weights_h, size_t n_floats, co
   if ((e = heads_configure()) != cudaSuccess) return bail("cudaFuncSetAttribute(heads)", e);
   if ((e = conv2_configure()) != cudaSuccess) return bail("cudaFuncSetAttribute(conv2)", e);
   if ((e = contract2_configure()) != cudaSuccess) return bail("cudaFuncSetAttribute(contract2)", e);
-  { const char* v = getenv("DDK_CONV_V1"); c->conv_v1 = v && v[0] == '1'; }
+  if ((e = conv3_configure()) != cudaSuccess) return bail("cudaFuncSetAttribute(conv3)", e);
+  {
+    const char* v = getenv("DDK_CONV");
+    c->conv_v1 = v && std::string(v) == "v1";
+    c->conv_v2 = v && std::string(v) == "v2";
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
+    c->sm_count = prop.multiProcessorCount;
+  }
+  {
+    // second-layer weights re-sliced for the fused kernel: W2S[l][g][r][class][f][jj][o] = W2p[l][g][class][(f, 8r+jj)][o]
+    std::vector<float> w2s;
+    c->w2s_off.assign((size_t)c->cfg.num_conv_layers * 4, 0);
+    c->con_split.resize(c->cfg.num_conv_layers);
+    for (int l = 0; l < c->cfg.num_conv_layers; ++l) {
+      const LayerInfo& li = c->layers[l];
+      build_con_split(li, c->con_split[l]);
+      for (int g = 0; g < 4; ++g) {
+        const float* src = weights_h + c->off[conv_id(l, DDK_WL_W2P + g)];
+        c->w2s_off[(size_t)l * 4 + g] = (int64_t)w2s.size();
+        for (int r = 0; r < NSL; ++r)
+          for (int k = 0; k < li.ncls; ++k) {
+            const ClassInfo& ci = li.cls[k];
+            for (int f = 0; f < ci.F; ++f)
+              for (int jj = 0; jj < J3; ++jj)
+                for (int o = 0; o < ci.O; ++o)
+                  w2s.push_back(src[ci.woff + ((int64_t)f * HID + (J3 * r + jj)) * ci.O + o]);
+          }
+      }
+    }
+    if ((e = cudaMalloc(&c->w2s, w2s.size() * sizeof(float))) != cudaSuccess) return bail("cudaMalloc(w2s)", e);
+    if ((e = cudaMemcpy(c->w2s, w2s.data(), w2s.size() * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess)
+      return bail("cudaMemcpy(w2s)", e);
+    std::vector<BasisEnt> all, tab;
+    for (int lv = 0; lv < 4; ++lv) {
+      build_basis_table(lv, tab);
+      c->btab_off[lv] = (int)all.size();
+      all.insert(all.end(), tab.begin(), tab.end());
+    }
+    if ((e = cudaMalloc(&c->btab, all.size() * sizeof(BasisEnt))) != cudaSuccess) return bail("cudaMalloc(btab)", e);
+    if ((e = cudaMemcpy(c->btab, all.data(), all.size() * sizeof(BasisEnt), cudaMemcpyHostToDevice)) != cudaSuccess)
+      return bail("cudaMemcpy(btab)", e);
+  }
   *out = c;
   return DDK_OK;
 }
@@ -140,10 +184,13 @@ int ddk_destroy(DdkCtx* c) {
                 &c->b_rr_dst, &c->b_rot_u, &c->b_rot_v, &c->b_rot_ptr, &c->b_rot_graph, &c->b_mr_off, &c->b_ll_off,
                 &c->b_lr_off, &c->b_seg_base, &c->b_seg_static, &c->b_seg_cnt, &c->b_seg_list, &c->b_seg_order,
                 &c->b_seg_sidx, &c->b_lig_static, &c->b_rec_static, &c->b_rr_pre, &c->b_ea_pool, &c->b_sh_pool, &c->b_tb,
-                &c->b_xa, &c->b_xb, &c->b_proj, &c->b_A, &c->b_Bsum, &c->b_tr, &c->b_rot, &c->b_tor, &c->b_pos, &c->b_step, &c->b_edge_total, &c->b_work, &c->b_nwork};
+                &c->b_xa, &c->b_xb, &c->b_proj, &c->b_A, &c->b_Bsum, &c->b_tr, &c->b_rot, &c->b_tor, &c->b_pos, &c->b_step, &c->b_edge_total, &c->b_work, &c->b_nwork,
+                &c->b_glist, &c->b_gcnt, &c->b_counters, &c->b_part};
   for (Buf* b : all) free_buf(*b);
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   if (c->w) cudaFree(c->w);
+  if (c->w2s) cudaFree(c->w2s);
+  if (c->btab) cudaFree(c->btab);
   delete c;
   return DDK_OK;
 }
@@ -289,8 +336,13 @@ int ddk_set_batch(DdkCtx* c, const DdkBatch* b, void* stream) {
   EN(c->b_ea_pool, (size_t)c->P * EA * 4); EN(c->b_sh_pool, (size_t)c->P * 16);
   EN(c->b_tb, (size_t)B * TB_COUNT * NS * 4);
   EN(c->b_xa, (size_t)c->N * D * 4); EN(c->b_xb, (size_t)c->N * D * 4); EN(c->b_proj, (size_t)c->N * 4 * HID * 4);
-  EN(c->b_A, (size_t)max_chunk_segs * seg_bytes); EN(c->b_Bsum, (size_t)max_chunk_segs * Umax * 4);
-  EN(c->b_work, (size_t)nsegs * 16); EN(c->b_nwork, (size_t)c->chunks.size() * 4);
+  if (c->conv_v1 || c->conv_v2) {
+    EN(c->b_A, (size_t)max_chunk_segs * seg_bytes); EN(c->b_Bsum, (size_t)max_chunk_segs * Umax * 4);
+    EN(c->b_work, (size_t)nsegs * 16); EN(c->b_nwork, (size_t)c->chunks.size() * 4);
+  } else {
+    EN(c->b_glist, (size_t)nsegs * 16); EN(c->b_gcnt, 4 * 4); EN(c->b_counters, 4 * NSL * 4);
+    EN(c->b_part, (size_t)nsegs * NSL * D * 4);
+  }
   EN(c->b_tr, (size_t)B * 3 * 4); EN(c->b_rot, (size_t)B * 3 * 4); EN(c->b_tor, (size_t)std::max(c->RB, 1) * 4);
 #undef EN
   launch_setup(c, b, b->lig_x, b->rec_x, st);
@@ -305,7 +357,8 @@ static int run_embed(DdkCtx* c, const float* lig_pos, const DdkStepInputs* in, c
   launch_step_consts(c, in->sigma_emb, st);
   launch_build_lists(c, lig_pos, in->cross_cutoff, st);
   launch_edge_features(c, lig_pos, st);
-  if (!c->conv_v1) launch_build_worklist(c, st);
+  if (c->conv_v2) launch_build_worklist(c, st);
+  else if (!c->conv_v1) launch_build_group_lists(c, st);
   float* xa = ptr<float>(c->b_xa);
   float* xb = ptr<float>(c->b_xb);
   launch_node_proj(c, 0, nullptr, xa, st);

@@ -24,6 +24,7 @@ struct ProjArgs {
   const float* W1[4];             // fc.g.0.weight of the layer, [72][72]
   const float* b1[4];
   float* proj;                    // [N][4][72]: {src group a, src group b, dst group a', dst group b'}
+  int sliced, N;                  // sliced: [NSL][N][4][J3] (hidden-unit slices of the fused conv kernel)
 };
 
 constexpr int PROJ_NODES = 16;
@@ -72,7 +73,9 @@ __global__ void __launch_bounds__(288) k_node_proj(ProjArgs p) {
     float acc = s < 2 ? sB[s][j] : 0.f;
 #pragma unroll
     for (int k = 0; k < NS; ++k) acc += sW[s][k][j] * sx[q][k];
-    p.proj[((size_t)((lig ? 0 : p.NL) + n0 + q) * 4 + s) * HID + j] = acc;
+    const size_t node = (size_t)((lig ? 0 : p.NL) + n0 + q);
+    if (p.sliced) p.proj[(((size_t)(j / J3) * p.N + node) * 4 + s) * J3 + (j % J3)] = acc;
+    else p.proj[(node * 4 + s) * HID + j] = acc;
   }
 }
 
@@ -380,6 +383,7 @@ void launch_node_proj(DdkCtx* c, int layer, const float* x_in, float* x0_out, cu
     p.b1[g] = W(c, conv_id(layer, DDK_WL_B1 + g));
   }
   p.proj = ptr<float>(c->b_proj);
+  p.sliced = !(c->conv_v1 || c->conv_v2); p.N = c->N;
   int blocks = (c->NL + PROJ_NODES - 1) / PROJ_NODES + (c->NR + PROJ_NODES - 1) / PROJ_NODES;
   LaunchScope ls(c, PC_PROJ, st);
   if (x0_out != nullptr) k_node_proj<true><<<blocks, 288, 0, st>>>(p);
@@ -387,6 +391,7 @@ void launch_node_proj(DdkCtx* c, int layer, const float* x_in, float* x0_out, cu
 }
 
 void launch_conv_layer(DdkCtx* c, int layer, const float* x_in, float* x_out, cudaStream_t st) {
+  if (!c->conv_v1 && !c->conv_v2) { launch_conv_fused(c, layer, x_in, x_out, st); return; }
   const LayerInfo& li = c->layers[layer];
   for (const Chunk& ch : c->chunks) {
     AccArgs a;

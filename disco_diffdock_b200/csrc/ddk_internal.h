@@ -51,6 +51,25 @@ struct Buf {
   size_t bytes = 0;
 };
 
+// ---- fused conv kernel (ddk_conv3.cu): hidden units are processed in NSL slices of J3
+constexpr int J3 = 8;               // hidden units per slice
+constexpr int NSL = HID / J3;       // 9 slices
+constexpr int AST = J3 + 1;         // row stride of an A slot: 8 hidden units + the sum-of-basis (bias) column
+constexpr int F3_ACC = 8;           // accumulate warps per CTA (= segments per contraction batch)
+constexpr int F3_CON = 4;           // contraction warps per CTA
+constexpr int F3_THREADS = (F3_ACC + F3_CON) * 32;
+constexpr int KC3 = 8;              // edges per gather chunk of one accumulate warp
+
+struct BasisEnt {                   // basis row evaluated by one (slot, lane): fa x[ia] sh[ma] + fb x[ib] sh[mb] + fc x[ic] sh[mc]
+  int u;                            // row of the A block (kernel order of ddk_conv.cuh), -1 = idle lane
+  int ia, ib, ic, ma, mb, mc;
+  float fa, fb, fc;
+};
+
+struct ConSplit {                   // rows [f0, f1) of each irrep class handled by each contraction warp
+  int f0[F3_CON][4], f1[F3_CON][4];
+};
+
 // kernel classes for the optional per-launch CUDA-event timing (ddk_profile_*)
 enum ProfClass { PC_SETUP = 0, PC_GRAPH, PC_PROJ, PC_ACC0, PC_ACC1, PC_ACC2, PC_ACC3, PC_CONTRACT, PC_HEADS, PC_UPDATE, PC_COUNT };
 
@@ -96,7 +115,16 @@ struct DdkCtx {
   ddk::Buf b_edge_total;              // device uint64: edges of every combined graph built so far
   float* x_final = nullptr;           // points into xa or xb after the last conv layer
 
-  bool conv_v1 = false;               // DDK_CONV_V1=1: use the simple one-CTA-per-segment accumulate kernel
+  bool conv_v1 = false;               // DDK_CONV=v1: the simple one-CTA-per-segment accumulate kernel + scratch
+  bool conv_v2 = false;               // DDK_CONV=v2: persistent accumulate + tensor-pipe contract over the scratch
+                                      // default: fused, hidden-unit-sliced kernel (ddk_conv3.cu), no scratch
+  int sm_count = 148;
+  float* w2s = nullptr;               // second-layer weights re-sliced per hidden-unit slice: [layer][group][NSL][W*J3]
+  std::vector<int64_t> w2s_off;       // [layer * 4 + group] (floats)
+  ddk::BasisEnt* btab = nullptr;      // per basis level the (slot, lane) -> basis row tables
+  int btab_off[4] = {0, 0, 0, 0};
+  std::vector<ddk::ConSplit> con_split;   // per layer
+  ddk::Buf b_glist, b_gcnt, b_counters, b_part;
 
   // optional profiling (off by default)
   bool prof = false;
@@ -132,6 +160,11 @@ struct LaunchScope {
 };
 
 cudaError_t conv_configure();
+cudaError_t conv3_configure();
+void build_basis_table(int lv, std::vector<BasisEnt>& tab);
+void build_con_split(const LayerInfo& li, ConSplit& sp);
+void launch_build_group_lists(DdkCtx* c, cudaStream_t st);
+void launch_conv_fused(DdkCtx* c, int layer, const float* x_in, float* x_out, cudaStream_t st);
 cudaError_t heads_configure();
 void host_kabsch(const float* A, const float* Bp, int N, float* R9, float* t3);   // host build of the device routine (tests)
 void host_axis_angle(const float* aa, float* R9);   // opt-in dynamic shared memory sizes (once per process / device)

@@ -140,7 +140,7 @@ int ddk_create(const DdkConfig* cfg, const float* weights_h, size_t n_floats, co
     c->sm_count = prop.multiProcessorCount;
   }
   {
-    // second-layer weights re-sliced for the fused kernel: W2S[l][g][r][class][f][jj][o] = W2p[l][g][class][(f, 8r+jj)][o]
+    // second-layer weights re-sliced for the fused kernel: W2S[l][g][r][class][f][jj][o] = W2p[l][g][class][(f, J r + jj)][o], J = f3_J(level)
     std::vector<float> w2s;
     c->w2s_off.assign((size_t)c->cfg.num_conv_layers * 4, 0);
     c->con_split.resize(c->cfg.num_conv_layers);
@@ -150,13 +150,14 @@ int ddk_create(const DdkConfig* cfg, const float* weights_h, size_t n_floats, co
       for (int g = 0; g < 4; ++g) {
         const float* src = weights_h + c->off[conv_id(l, DDK_WL_W2P + g)];
         c->w2s_off[(size_t)l * 4 + g] = (int64_t)w2s.size();
-        for (int r = 0; r < NSL; ++r)
+        const int J = f3_J(li.lv);
+        for (int r = 0; r < HID / J; ++r)
           for (int k = 0; k < li.ncls; ++k) {
             const ClassInfo& ci = li.cls[k];
             for (int f = 0; f < ci.F; ++f)
-              for (int jj = 0; jj < J3; ++jj)
+              for (int jj = 0; jj < J; ++jj)
                 for (int o = 0; o < ci.O; ++o)
-                  w2s.push_back(src[ci.woff + ((int64_t)f * HID + (J3 * r + jj)) * ci.O + o]);
+                  w2s.push_back(src[ci.woff + ((int64_t)f * HID + (J * r + jj)) * ci.O + o]);
           }
       }
     }
@@ -340,8 +341,8 @@ int ddk_set_batch(DdkCtx* c, const DdkBatch* b, void* stream) {
     EN(c->b_A, (size_t)max_chunk_segs * seg_bytes); EN(c->b_Bsum, (size_t)max_chunk_segs * Umax * 4);
     EN(c->b_work, (size_t)nsegs * 16); EN(c->b_nwork, (size_t)c->chunks.size() * 4);
   } else {
-    EN(c->b_glist, (size_t)nsegs * 16); EN(c->b_gcnt, 4 * 4); EN(c->b_counters, 4 * NSL * 4);
-    EN(c->b_part, (size_t)nsegs * NSL * D * 4);
+    EN(c->b_glist, (size_t)nsegs * 16); EN(c->b_gcnt, 4 * 4); EN(c->b_counters, 4 * NSL_MAX * 4);
+    EN(c->b_part, (size_t)nsegs * NSL_MAX * D * 4);
   }
   EN(c->b_tr, (size_t)B * 3 * 4); EN(c->b_rot, (size_t)B * 3 * 4); EN(c->b_tor, (size_t)std::max(c->RB, 1) * 4);
 #undef EN

@@ -24,7 +24,7 @@ struct ProjArgs {
   const float* W1[4];             // fc.g.0.weight of the layer, [72][72]
   const float* b1[4];
   float* proj;                    // [N][4][72]: {src group a, src group b, dst group a', dst group b'}
-  int sliced, N;                  // sliced: [NSL][N][4][J3] (hidden-unit slices of the fused conv kernel)
+  int sliced, N;                  // sliced > 0: [72 / J][N][4][J] with J = sliced (hidden-unit slices of the fused conv kernel)
 };
 
 constexpr int PROJ_NODES = 16;
@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(288) k_node_proj(ProjArgs p) {
 #pragma unroll
     for (int k = 0; k < NS; ++k) acc += sW[s][k][j] * sx[q][k];
     const size_t node = (size_t)((lig ? 0 : p.NL) + n0 + q);
-    if (p.sliced) p.proj[(((size_t)(j / J3) * p.N + node) * 4 + s) * J3 + (j % J3)] = acc;
+    if (p.sliced) p.proj[(((size_t)(j / p.sliced) * p.N + node) * 4 + s) * p.sliced + (j % p.sliced)] = acc;
     else p.proj[(node * 4 + s) * HID + j] = acc;
   }
 }
@@ -383,7 +383,7 @@ void launch_node_proj(DdkCtx* c, int layer, const float* x_in, float* x0_out, cu
     p.b1[g] = W(c, conv_id(layer, DDK_WL_B1 + g));
   }
   p.proj = ptr<float>(c->b_proj);
-  p.sliced = !(c->conv_v1 || c->conv_v2); p.N = c->N;
+  p.sliced = (c->conv_v1 || c->conv_v2) ? 0 : f3_J(c->layers[layer].lv); p.N = c->N;
   int blocks = (c->NL + PROJ_NODES - 1) / PROJ_NODES + (c->NR + PROJ_NODES - 1) / PROJ_NODES;
   LaunchScope ls(c, PC_PROJ, st);
   if (x0_out != nullptr) k_node_proj<true><<<blocks, 288, 0, st>>>(p);

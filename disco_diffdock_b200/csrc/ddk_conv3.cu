@@ -14,7 +14,7 @@
 //   - four contraction warps take the 8 slots of a batch together (so every weight read from shared memory is used for
 //     8 segments), contract them against the resident weight slice and write the 84-wide PARTIAL output of
 //     (segment, slice) to HBM: 336 B instead of 80 KB.
-// k_conv_finalize adds the 2 x 9 partials of a node in a fixed order, applies mean / batch-norm / residual.
+// k_conv_finalize adds the 2 x (72 / J) partials of a node in a fixed order, applies mean / batch-norm / residual.
 // Accumulate and contraction warps are decoupled with named barriers (one batch of slack), every warp gathers its own
 // edge stream with cp.async one chunk ahead, and CTAs claim (combo, block of segments) tasks from per-combo counters,
 // staying on a combo while it has work so the weight slice is reloaded only when a CTA migrates.
@@ -30,46 +30,50 @@
 namespace ddk {
 
 constexpr int EAS = 28;            // padded row of the staged edge embedding (conflict-free LDS.128 across 8 edges)
-constexpr int F3_NCOMBO = 4 * NSL;
+constexpr int F3_NCOMBO_MAX = 4 * NSL_MAX;
 
 enum { F3_BAR_FULL = 1, F3_BAR_EMPTY = 2, F3_BAR_CON = 3, F3_BAR_CON2 = 4 };
 
 __device__ __forceinline__ void f3_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void f3_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
+// Basis rows are laid out over (slot, lane) by SOURCE feature so that one shared-memory load feeds several rows:
+//   slots 0..3  (A) : lane -> scalar source x[i] (x0e, at level 3 also the first 8 x0o); row of slot m is x[i] * sh[m]
+//   slots 4,5   (B) : level 3, the other 16 x0o sources: lane = (i & 15, mh); rows x[i] * sh[mh], x[i] * sh[2 + mh]
+//   slot  V0        : levels 2,3: the first 32 rows  x1o/x1e[k][c] * sh[0]
+//   2 generic slots : everything else (dot / cross products and the left-over products), 3-term formula per lane
 template <int LV>
 struct F3Cfg {
   static constexpr int U = AccCfg<LV>::U;
   static constexpr int DINP = AccCfg<LV>::DINP;
-  static constexpr int NSLOT = (U + 31) / 32;
+  static constexpr int XQ = DINP / 4;
   static constexpr int W = LV == 0 ? 720 : (LV == 1 ? 936 : (LV == 2 ? 1152 : 1872));   // second-layer rows (sum F*O)
-  // basis rows of type 0 (x[i] * sh[m]) by harmonic component m
-  static constexpr int C0 = LV == 0 ? 24 : (LV == 1 ? 42 : (LV == 2 ? 60 : 84));
-  static constexpr int CC = LV == 3 ? 48 : 24;
-  static constexpr int NU0 = C0 / 32, NUC = CC / 32;
-  static constexpr int NT0U = NU0 + 3 * NUC;                 // slots whose 32 rows share one compile-time m
-  static constexpr int T0TOT = C0 + 3 * CC;
-  static constexpr int NT0 = T0TOT / 32 - NT0U;              // slots of type-0 rows with a per-lane m
-  static constexpr int NGEN = NSLOT - NT0U - NT0;            // slots evaluated with the generic 3-term formula
-  __host__ __device__ static constexpr int slot_m(int k) { return k < NU0 ? 0 : 1 + (k - NU0) / (NUC > 0 ? NUC : 1); }
+  static constexpr int J = f3_J(LV);
+  static constexpr int JQ = J / 4;
+  static constexpr int NSLV = HID / J;
+  static constexpr int AST = J + 1;          // row stride of an A slot: J hidden units + the sum-of-basis (bias) column
+  static constexpr bool HAS_B = LV == 3, HAS_V0 = LV >= 2;
+  static constexpr int NGEN = LV == 0 ? 0 : 2;
+  static constexpr int SLOT_B = 4, SLOT_V0 = 4 + (HAS_B ? 2 : 0), SLOT_G = SLOT_V0 + (HAS_V0 ? 1 : 0);
+  static constexpr int NSLOT = SLOT_G + NGEN;
 };
 
 template <int LV>
 struct F3Smem {
-  alignas(16) float Wsl[F3Cfg<LV>::W * J3];                  // [class][f][jj][o] of the resident (group, slice)
+  alignas(16) float Wsl[F3Cfg<LV>::W * F3Cfg<LV>::J];        // [class][f][jj][o] of the resident (group, slice)
   alignas(16) float Wb[F3Cfg<LV>::W];                        // packed second-layer bias (used by slice 0 only)
-  alignas(16) float As[F3_ACC][F3Cfg<LV>::U * AST];          // one slot per accumulate warp: [u][jj | bsum]
+  alignas(16) float As[F3_ACC][F3Cfg<LV>::U * F3Cfg<LV>::AST];   // one slot per accumulate warp: [u][jj | bsum]
   struct Stage {
     alignas(16) float X[2][KC3][F3Cfg<LV>::DINP];
     alignas(16) float SH[2][KC3][4];
     alignas(16) float EA[KC3][EAS];
-    alignas(16) float PD[KC3][J3];
-    alignas(16) float H[KC3][J3];
+    alignas(16) float PD[KC3][F3Cfg<LV>::J];
+    alignas(16) float H[KC3][F3Cfg<LV>::J];
   } st[F3_ACC];
-  alignas(16) float W1a[J3][EA];                             // first-layer rows of the slice, edge-embedding columns
+  alignas(16) float W1a[F3Cfg<LV>::J][EA];                   // first-layer rows of the slice, edge-embedding columns
   alignas(16) float tile[F3_CON][F3_ACC][D];                 // per contraction warp partial outputs of a batch
   int meta[F3_ACC];                                          // segment id of each slot of the batch in flight (-1: none)
-  int task[8];                                               // g, r, idx0, nseg, reload, combo cursor
+  int task[8];                                               // g, r, idx0, nseg, reload, combo cursor, resident combo
 };
 
 struct F3Args {
@@ -78,16 +82,16 @@ struct F3Args {
   const int4* glist;                 // per-group lists of non-empty segments: (seg, n, base, 0)
   int goff[4];
   const int* gcnt;                   // [4]
-  int* counters;                     // [F3_NCOMBO] next block of each combo
+  int* counters;                     // [4 * NSLV] next block of each combo
   const int2* seg_list;
   const float* x;                    // [N][84] layer input
-  const float* projs;                // [NSL][N][4][J3]
+  const float* projs;                // [NSLV][N][4][J]
   const float* ea_pool; const float4* sh_pool;
   const float* W1[4];                // [72][72]
-  const float* W2S[4];               // [NSL][W * J3]
+  const float* W2S[4];               // [NSLV][W * J]
   const float* b2p[4];               // [W]
   const BasisEnt* btab;              // [NSLOT * 32]
-  float* part;                       // [2 N][NSL][84]
+  float* part;                       // [2 N][NSLV][84]
   ConSplit split;
   ClassInfo cls[4];
   int w8off[4];                      // offset of each class inside a weight slice (floats)
@@ -127,11 +131,14 @@ __global__ void __launch_bounds__(1024) k_build_group_lists(int NL, int NR, cons
 // ---------------------------------------------------------------------------------------------- accumulate warps
 template <int LV>
 struct LaneBasis {
-  const float* xp[F3Cfg<LV>::NSLOT];                                   // &X[buf][0][i] of the first term
-  const float* sp[F3Cfg<LV>::NT0 + F3Cfg<LV>::NGEN > 0 ? F3Cfg<LV>::NT0 + F3Cfg<LV>::NGEN : 1];   // &SH[buf][0][m]
-  const float* gx[F3Cfg<LV>::NGEN > 0 ? 2 * F3Cfg<LV>::NGEN : 1];      // generic slots: second / third term
-  const float* gs[F3Cfg<LV>::NGEN > 0 ? 2 * F3Cfg<LV>::NGEN : 1];
-  float gf[F3Cfg<LV>::NGEN > 0 ? 3 * F3Cfg<LV>::NGEN : 1];
+  static constexpr int NG3 = F3Cfg<LV>::NGEN > 0 ? 3 * F3Cfg<LV>::NGEN : 1;
+  const float* pA;                   // &X[buf][0][i] of the lane's scalar source (slots A)
+  const float* pB;                   // slots B
+  const float* pV0;                  // slot V0
+  const float* gx[NG3];              // generic slots: x term pointers
+  const float* gs[NG3];              //                harmonic term pointers (&SH[buf][0][m])
+  float gf[NG3];                     //                coefficients (0, +1, -1)
+  bool mh;                           // lane >> 4 (slots B)
 };
 
 struct ChunkD {
@@ -139,26 +146,76 @@ struct ChunkD {
   bool first, last, valid, done;
 };
 
+__device__ __forceinline__ void f3_cp16(void* dst, const void* src) { __pipeline_memcpy_async(dst, src, 16); }
+
+// one edge: 8..24 hidden units of the slice against every basis row of the lane
+template <int LV, bool BIAS>
+__device__ __forceinline__ void f3_edge(float (&acc)[F3Cfg<LV>::NSLOT][F3Cfg<LV>::J], float (&bs)[F3Cfg<LV>::NSLOT],
+                                        const LaneBasis<LV>& LB, const float* __restrict__ hrow,
+                                        const float* __restrict__ shrow, const int xo, const int so) {
+  using Cfg = F3Cfg<LV>;
+  constexpr int J = Cfg::J, NSLOT = Cfg::NSLOT;
+  constexpr int JH = J > 12 ? 12 : J;           // hidden units handled per pass (keeps the live set small at J = 24)
+  // basis values of the lane's rows for this edge
+  float b[NSLOT];
+  {
+    const float4 s4 = *reinterpret_cast<const float4*>(shrow);
+    const float xa = LB.pA[xo];
+    b[0] = xa * s4.x; b[1] = xa * s4.y; b[2] = xa * s4.z; b[3] = xa * s4.w;
+    if (Cfg::HAS_B) {
+      const float xb = LB.pB[xo];
+      b[Cfg::SLOT_B] = xb * (LB.mh ? s4.y : s4.x);
+      b[Cfg::SLOT_B + 1] = xb * (LB.mh ? s4.w : s4.z);
+    }
+    if (Cfg::HAS_V0) b[Cfg::SLOT_V0] = LB.pV0[xo] * s4.x;
+#pragma unroll
+    for (int q = 0; q < Cfg::NGEN; ++q) {
+      float v = LB.gf[3 * q] * (LB.gx[3 * q][xo] * LB.gs[3 * q][so]);
+      v += LB.gf[3 * q + 1] * (LB.gx[3 * q + 1][xo] * LB.gs[3 * q + 1][so]);
+      v += LB.gf[3 * q + 2] * (LB.gx[3 * q + 2][xo] * LB.gs[3 * q + 2][so]);
+      b[Cfg::SLOT_G + q] = v;
+    }
+  }
+  if (BIAS) {
+#pragma unroll
+    for (int k = 0; k < NSLOT; ++k) bs[k] += b[k];
+  }
+#pragma unroll
+  for (int j0 = 0; j0 < J; j0 += JH) {
+    float h[JH];
+#pragma unroll
+    for (int q = 0; q < JH / 4; ++q) {
+      const float4 v = *reinterpret_cast<const float4*>(hrow + j0 + 4 * q);
+      h[4 * q] = v.x; h[4 * q + 1] = v.y; h[4 * q + 2] = v.z; h[4 * q + 3] = v.w;
+    }
+#pragma unroll
+    for (int k = 0; k < NSLOT; ++k)
+#pragma unroll
+      for (int j = 0; j < JH; ++j) acc[k][j0 + j] += b[k] * h[j];
+  }
+}
+
 template <int LV, bool BIAS>
 __device__ __forceinline__ void f3_acc_task(const F3Args& p, F3Smem<LV>& S, LaneBasis<LV>& LB, const int g, const int r,
                                             const int idx0, const int nseg, const int w, const int lane) {
   using Cfg = F3Cfg<LV>;
-  constexpr int NSLOT = Cfg::NSLOT, NT0U = Cfg::NT0U, NT0 = Cfg::NT0, NGEN = Cfg::NGEN, DINP = Cfg::DINP, U = Cfg::U;
-  constexpr int XQ = DINP / 4;
+  constexpr int NSLOT = Cfg::NSLOT, DINP = Cfg::DINP, J = Cfg::J, JQ = Cfg::JQ, AST = Cfg::AST, XQ = Cfg::XQ;
   constexpr int XBUF = KC3 * DINP, SBUF = KC3 * 4;
+  constexpr int NG3 = 3 * Cfg::NGEN;
   typename F3Smem<LV>::Stage& T = S.st[w];
   const int nb = (nseg + F3_ACC - 1) / F3_ACC;
   const int dslot = (g == 1 || g == 3) ? 3 : 2;
   const int4* wl = p.glist + p.goff[g] + idx0;
-  const float* projr = p.projs + (size_t)r * p.N * 4 * J3;
+  const float* projr = p.projs + (size_t)r * p.N * 4 * J;
+  const int ge = lane & 7, gsub = lane >> 3;        // gather / first-layer role of the lane: edge, sub-lane
 
-  float acc[NSLOT][J3];
+  float acc[NSLOT][J];
   float bs[NSLOT];
 #pragma unroll
   for (int k = 0; k < NSLOT; ++k) {
     bs[k] = 0.f;
 #pragma unroll
-    for (int j = 0; j < J3; ++j) acc[k][j] = 0.f;
+    for (int j = 0; j < J; ++j) acc[k][j] = 0.f;
   }
 
   // ---- chunk generator: batches bi = 0..nb-1, this warp's segment of a batch is idx0 + 8 bi + w (or none)
@@ -191,40 +248,33 @@ __device__ __forceinline__ void f3_acc_task(const F3Args& p, F3Smem<LV>& S, Lane
     if (d.valid && lane < d.kc) e = p.seg_list[d.base + d.c0 + lane];
     return e;
   };
-  // source-side projection of the segment's node: lanes need hidden units jg and jg + 4 (jg = lane >> 3)
-  auto load_ps = [&](const ChunkD& d, float& a, float& b) {
+  // source-side projection of the segment's node: the lane needs hidden units gsub + 4 i
+  auto load_ps = [&](const ChunkD& d, float (&v)[JQ]) {
     if (d.valid) {
-      const float* q = projr + ((size_t)d.node * 4 + d.which) * J3 + (lane >> 3);
-      a = q[0]; b = q[4];
+      const float* q = projr + ((size_t)d.node * 4 + d.which) * J + gsub;
+#pragma unroll
+      for (int i = 0; i < JQ; ++i) v[i] = q[4 * i];
     }
   };
+  // every lane copies fixed 16-byte pieces (q = gsub + 4 i) of its edge ge: two shuffles per chunk, immediate offsets
   auto gather = [&](const ChunkD& d, const int2 ent, const int buf) {
     if (d.valid) {
-      const int kc = d.kc;
+      const int slot = __shfl_sync(0xffffffffu, ent.x, ge);
+      const int dst = __shfl_sync(0xffffffffu, ent.y, ge);
+      if (ge < d.kc) {
+        const float* xs = p.x + (size_t)dst * D + 4 * gsub;
+        float* xd = &T.X[buf][ge][4 * gsub];
 #pragma unroll
-      for (int i = 0; i < (KC3 * XQ + 31) / 32; ++i) {
-        const int pc = lane + 32 * i;
-        const int e = pc / XQ, q = pc % XQ;
-        const int dst = __shfl_sync(0xffffffffu, ent.y, e & 7);
-        if (pc < KC3 * XQ && e < kc) __pipeline_memcpy_async(&T.X[buf][e][4 * q], p.x + (size_t)dst * D + 4 * q, 16);
-      }
-      {
-        const int e = lane & 7;
-        const int slot = __shfl_sync(0xffffffffu, ent.x, e);
-        if (lane < 8 && e < kc) __pipeline_memcpy_async(&T.SH[buf][e][0], p.sh_pool + slot, 16);
-      }
+        for (int i = 0; i < (XQ + 3) / 4; ++i)
+          if (gsub + 4 * i < XQ) f3_cp16(xd + 16 * i, xs + 16 * i);
+        const float* es = p.ea_pool + (size_t)slot * EA + 4 * gsub;
+        f3_cp16(&T.EA[ge][4 * gsub], es);
+        if (gsub < 2) f3_cp16(&T.EA[ge][16 + 4 * gsub], es + 16);
+        const float* pd = projr + ((size_t)dst * 4 + dslot) * J + 4 * gsub;
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int pc = lane + 32 * i;                    // 8 edges x 6 pieces = 48
-        const int e = pc / 6, q = pc % 6;
-        const int slot = __shfl_sync(0xffffffffu, ent.x, e & 7);
-        if (pc < KC3 * 6 && e < kc) __pipeline_memcpy_async(&T.EA[e][4 * q], p.ea_pool + (size_t)slot * EA + 4 * q, 16);
-      }
-      {
-        const int e = lane >> 1, q = lane & 1;            // 8 edges x 2 pieces
-        const int dst = __shfl_sync(0xffffffffu, ent.y, e & 7);
-        if (lane < 16 && e < kc)
-          __pipeline_memcpy_async(&T.PD[e][4 * q], projr + ((size_t)dst * 4 + dslot) * J3 + 4 * q, 16);
+        for (int i = 0; i < (JQ + 3) / 4; ++i)
+          if (gsub + 4 * i < JQ) f3_cp16(&T.PD[ge][4 * gsub + 16 * i], pd + 16 * i);
+        if (gsub == 0) f3_cp16(&T.SH[buf][ge][0], p.sh_pool + slot);
       }
     }
     __pipeline_commit();
@@ -233,10 +283,12 @@ __device__ __forceinline__ void f3_acc_task(const F3Args& p, F3Smem<LV>& S, Lane
   ChunkD cd0 = next_cd();
   ChunkD cd1 = cd0.done ? cd0 : next_cd();
   int2 ent1;
-  float ps0 = 0.f, ps1 = 0.f, pn0 = 0.f, pn1 = 0.f;
+  float ps[JQ], pn[JQ];
+#pragma unroll
+  for (int i = 0; i < JQ; ++i) { ps[i] = 0.f; pn[i] = 0.f; }
   {
     const int2 ent0 = load_ent(cd0);
-    load_ps(cd0, ps0, ps1);
+    load_ps(cd0, ps);
     gather(cd0, ent0, 0);
     ent1 = load_ent(cd1);
   }
@@ -246,23 +298,25 @@ __device__ __forceinline__ void f3_acc_task(const F3Args& p, F3Smem<LV>& S, Lane
     __syncwarp();
     if (cd0.valid) {
       // ---- first radial-MLP layer for the slice: h = relu(W1[:, :24] ea + (W1[:,24:48] x_s + b1) + W1[:,48:72] x_d)
-      const int e = lane & 7, jg = lane >> 3;
-      float h0 = ps0 + T.PD[e][jg], h1 = ps1 + T.PD[e][jg + 4];
+      float h[JQ];
+#pragma unroll
+      for (int i = 0; i < JQ; ++i) h[i] = ps[i] + T.PD[ge][gsub + 4 * i];
 #pragma unroll
       for (int q = 0; q < EA / 4; ++q) {
-        const float4 ea = *reinterpret_cast<const float4*>(&T.EA[e][4 * q]);
-        const float4 wa = *reinterpret_cast<const float4*>(&S.W1a[jg][4 * q]);
-        const float4 wb = *reinterpret_cast<const float4*>(&S.W1a[jg + 4][4 * q]);
-        h0 += wa.x * ea.x + wa.y * ea.y + wa.z * ea.z + wa.w * ea.w;
-        h1 += wb.x * ea.x + wb.y * ea.y + wb.z * ea.z + wb.w * ea.w;
+        const float4 ea = *reinterpret_cast<const float4*>(&T.EA[ge][4 * q]);
+#pragma unroll
+        for (int i = 0; i < JQ; ++i) {
+          const float4 wv = *reinterpret_cast<const float4*>(&S.W1a[gsub + 4 * i][4 * q]);
+          h[i] += wv.x * ea.x + wv.y * ea.y + wv.z * ea.z + wv.w * ea.w;
+        }
       }
-      T.H[e][jg] = fmaxf(h0, 0.f);
-      T.H[e][jg + 4] = fmaxf(h1, 0.f);
+#pragma unroll
+      for (int i = 0; i < JQ; ++i) T.H[ge][gsub + 4 * i] = fmaxf(h[i], 0.f);
     }
     __syncwarp();
     // ---- next chunk's gathers travel while this chunk is accumulated (EA / PD of this chunk are consumed)
     if (!cd1.done) {
-      if (cd1.first) load_ps(cd1, pn0, pn1);
+      if (cd1.first) load_ps(cd1, pn);
       gather(cd1, ent1, buf ^ 1);
     } else {
       __pipeline_commit();
@@ -271,37 +325,18 @@ __device__ __forceinline__ void f3_acc_task(const F3Args& p, F3Smem<LV>& S, Lane
     const int2 ent2 = load_ent(cd2);
 
     if (cd0.valid) {
-      const int kc = cd0.kc;
+      const float* hb = &T.H[0][0];
+      const float* sb = &T.SH[0][0][0] + buf * SBUF;
+      if (cd0.kc == KC3) {
 #pragma unroll
-      for (int e = 0; e < KC3; ++e) {
-        if (e < kc) {
-          const float4 ha = *reinterpret_cast<const float4*>(&T.H[e][0]);
-          const float4 hb = *reinterpret_cast<const float4*>(&T.H[e][4]);
-          const float4 s4 = *reinterpret_cast<const float4*>(&T.SH[0][0][0] + buf * SBUF + e * 4);
-#pragma unroll
-          for (int k = 0; k < NSLOT; ++k) {
-            float b;
-            if (k < NT0U) {
-              const int m = Cfg::slot_m(k);
-              const float sm = m == 0 ? s4.x : (m == 1 ? s4.y : (m == 2 ? s4.z : s4.w));
-              b = LB.xp[k][e * DINP] * sm;
-            } else if (k < NT0U + NT0) {
-              b = LB.xp[k][e * DINP] * LB.sp[k - NT0U][e * 4];
-            } else {
-              const int q = k - NT0U - NT0;
-              b = LB.gf[3 * q] * (LB.xp[k][e * DINP] * LB.sp[k - NT0U][e * 4]);
-              b += LB.gf[3 * q + 1] * (LB.gx[2 * q][e * DINP] * LB.gs[2 * q][e * 4]);
-              b += LB.gf[3 * q + 2] * (LB.gx[2 * q + 1][e * DINP] * LB.gs[2 * q + 1][e * 4]);
-            }
-            acc[k][0] += b * ha.x; acc[k][1] += b * ha.y; acc[k][2] += b * ha.z; acc[k][3] += b * ha.w;
-            acc[k][4] += b * hb.x; acc[k][5] += b * hb.y; acc[k][6] += b * hb.z; acc[k][7] += b * hb.w;
-            if (BIAS) bs[k] += b;
-          }
-        }
+        for (int e = 0; e < KC3; ++e) f3_edge<LV, BIAS>(acc, bs, LB, hb + e * J, sb + e * 4, e * DINP, e * 4);
+      } else {
+#pragma unroll 1
+        for (int e = 0; e < cd0.kc; ++e) f3_edge<LV, BIAS>(acc, bs, LB, hb + e * J, sb + e * 4, e * DINP, e * 4);
       }
     }
     if (cd0.last) {
-      // ---- hand the finished U x 8 block to the contraction warps
+      // ---- hand the finished U x J block to the contraction warps
       if (cd0.batch > 0) f3_bar_sync(F3_BAR_EMPTY, F3_THREADS);      // they are done with the previous batch
       if (cd0.valid) {
         float* slot = &S.As[w][0];
@@ -310,12 +345,12 @@ __device__ __forceinline__ void f3_acc_task(const F3Args& p, F3Smem<LV>& S, Lane
           const int u = p.btab[k * 32 + lane].u;
           if (u >= 0) {
 #pragma unroll
-            for (int j = 0; j < J3; ++j) slot[u * AST + j] = acc[k][j];
-            if (BIAS) slot[u * AST + J3] = bs[k];
+            for (int j = 0; j < J; ++j) slot[u * AST + j] = acc[k][j];
+            if (BIAS) slot[u * AST + J] = bs[k];
           }
           bs[k] = 0.f;
 #pragma unroll
-          for (int j = 0; j < J3; ++j) acc[k][j] = 0.f;
+          for (int j = 0; j < J; ++j) acc[k][j] = 0.f;
         }
       }
       if (lane == 0) S.meta[w] = cd0.valid ? (2 * cd0.node + cd0.which) : -1;
@@ -325,24 +360,21 @@ __device__ __forceinline__ void f3_acc_task(const F3Args& p, F3Smem<LV>& S, Lane
     // ---- rotate
     const int tog = buf ? -XBUF : XBUF;
     const int togs = buf ? -SBUF : SBUF;
+    LB.pA += tog; LB.pB += tog; LB.pV0 += tog;
 #pragma unroll
-    for (int k = 0; k < NSLOT; ++k) LB.xp[k] += tog;
-#pragma unroll
-    for (int k = 0; k < NT0 + NGEN; ++k) LB.sp[k] += togs;
-#pragma unroll
-    for (int k = 0; k < 2 * NGEN; ++k) { LB.gx[k] += tog; LB.gs[k] += togs; }
+    for (int k = 0; k < NG3; ++k) { LB.gx[k] += tog; LB.gs[k] += togs; }
     buf ^= 1;
-    if (cd1.first) { ps0 = pn0; ps1 = pn1; }
+    if (cd1.first) {
+#pragma unroll
+      for (int i = 0; i < JQ; ++i) ps[i] = pn[i];
+    }
     cd0 = cd1; cd1 = cd2; ent1 = ent2;
   }
   // leave the pointers on buffer 0 for the next task
   if (buf) {
+    LB.pA -= XBUF; LB.pB -= XBUF; LB.pV0 -= XBUF;
 #pragma unroll
-    for (int k = 0; k < NSLOT; ++k) LB.xp[k] -= XBUF;
-#pragma unroll
-    for (int k = 0; k < NT0 + NGEN; ++k) LB.sp[k] -= SBUF;
-#pragma unroll
-    for (int k = 0; k < 2 * NGEN; ++k) { LB.gx[k] -= XBUF; LB.gs[k] -= SBUF; }
+    for (int k = 0; k < NG3; ++k) { LB.gx[k] -= XBUF; LB.gs[k] -= SBUF; }
   }
   __pipeline_wait_prior(0);
 }
@@ -350,11 +382,12 @@ __device__ __forceinline__ void f3_acc_task(const F3Args& p, F3Smem<LV>& S, Lane
 // ---------------------------------------------------------------------------------------------- contraction warps
 // scalar output class (O = 24, one component): lane = (k-part kp = lane >> 2, output group og = lane & 3 -> 6 outputs),
 // 8 segments per lane; rows (f, jj) of the class are dealt round-robin to the 8 k-parts.
-template <bool BIAS, int ASLOT>
+template <bool BIAS, int J, int ASLOT>
 __device__ __forceinline__ void f3_con_scalar(const float* __restrict__ Wc, const float* __restrict__ Wbc,
                                               const float* __restrict__ As, int uoff, int f0, int f1, float* tile, int col0,
                                               int lane) {
-  constexpr int JC = BIAS ? J3 + 1 : J3;
+  constexpr int JC = BIAS ? J + 1 : J;
+  constexpr int AST = J + 1;
   const int kp = lane >> 2, og = lane & 3;
   float acc[F3_ACC][6];
 #pragma unroll
@@ -362,9 +395,9 @@ __device__ __forceinline__ void f3_con_scalar(const float* __restrict__ Wc, cons
 #pragma unroll
     for (int o = 0; o < 6; ++o) acc[s][o] = 0.f;
   const int nrows = (f1 - f0) * JC;
-  int f = f0 + kp / JC, jj = kp % JC;
+  int f = f0, jj = kp;                          // kp < 8 <= JC
   for (int q = kp; q < nrows; q += 8) {
-    const float* wp = (!BIAS || jj < J3) ? Wc + (f * J3 + jj) * 24 + 6 * og : Wbc + f * 24 + 6 * og;
+    const float* wp = (!BIAS || jj < J) ? Wc + (f * J + jj) * 24 + 6 * og : Wbc + f * 24 + 6 * og;
     const float2 w0 = *reinterpret_cast<const float2*>(wp);
     const float2 w1 = *reinterpret_cast<const float2*>(wp + 2);
     const float2 w2 = *reinterpret_cast<const float2*>(wp + 4);
@@ -392,11 +425,12 @@ __device__ __forceinline__ void f3_con_scalar(const float* __restrict__ Wc, cons
 
 // vector output class (O = 6, three components sharing the weights): lane = (kp = lane >> 2, sg = lane & 3 -> segments
 // 2 sg, 2 sg + 1), 2 x 3 x 6 accumulators per lane.
-template <bool BIAS, int ASLOT>
+template <bool BIAS, int J, int ASLOT>
 __device__ __forceinline__ void f3_con_vector(const float* __restrict__ Wc, const float* __restrict__ Wbc,
                                               const float* __restrict__ As, int uoff, int F, int f0, int f1, float* tile,
                                               int col0, int lane) {
-  constexpr int JC = BIAS ? J3 + 1 : J3;
+  constexpr int JC = BIAS ? J + 1 : J;
+  constexpr int AST = J + 1;
   const int kp = lane >> 2, sg = lane & 3;
   float acc[2][3][6];
 #pragma unroll
@@ -406,10 +440,10 @@ __device__ __forceinline__ void f3_con_vector(const float* __restrict__ Wc, cons
 #pragma unroll
       for (int o = 0; o < 6; ++o) acc[s][c][o] = 0.f;
   const int nrows = (f1 - f0) * JC;
-  int f = f0 + kp / JC, jj = kp % JC;
+  int f = f0, jj = kp;
   const float* A0 = As + (2 * sg) * ASLOT;
   for (int q = kp; q < nrows; q += 8) {
-    const float* wp = (!BIAS || jj < J3) ? Wc + (f * J3 + jj) * 6 : Wbc + f * 6;
+    const float* wp = (!BIAS || jj < J) ? Wc + (f * J + jj) * 6 : Wbc + f * 6;
     const float2 w0 = *reinterpret_cast<const float2*>(wp);
     const float2 w1 = *reinterpret_cast<const float2*>(wp + 2);
     const float2 w2 = *reinterpret_cast<const float2*>(wp + 4);
@@ -441,7 +475,8 @@ __device__ __forceinline__ void f3_con_vector(const float* __restrict__ Wc, cons
 template <int LV, bool BIAS>
 __device__ __forceinline__ void f3_con_task(const F3Args& p, F3Smem<LV>& S, const int r, const int nseg, const int cw,
                                             const int lane) {
-  constexpr int ASLOT = F3Cfg<LV>::U * AST;
+  using Cfg = F3Cfg<LV>;
+  constexpr int ASLOT = Cfg::U * Cfg::AST;
   const int nb = (nseg + F3_ACC - 1) / F3_ACC;
   const int ct = cw * 32 + lane;
   float* tile = &S.tile[cw][0][0];
@@ -456,8 +491,8 @@ __device__ __forceinline__ void f3_con_task(const F3Args& p, F3Smem<LV>& S, cons
       const ClassInfo& ci = p.cls[k];
       const float* Wc = S.Wsl + p.w8off[k];
       const float* Wbc = S.Wb + ci.boff;
-      if (ci.ncomp == 1) f3_con_scalar<BIAS, ASLOT>(Wc, Wbc, &S.As[0][0], ci.uoff, f0, f1, tile, ci.col0, lane);
-      else f3_con_vector<BIAS, ASLOT>(Wc, Wbc, &S.As[0][0], ci.uoff, ci.F, f0, f1, tile, ci.col0, lane);
+      if (ci.ncomp == 1) f3_con_scalar<BIAS, Cfg::J, ASLOT>(Wc, Wbc, &S.As[0][0], ci.uoff, f0, f1, tile, ci.col0, lane);
+      else f3_con_vector<BIAS, Cfg::J, ASLOT>(Wc, Wbc, &S.As[0][0], ci.uoff, ci.F, f0, f1, tile, ci.col0, lane);
     }
     f3_bar_sync(F3_BAR_CON, F3_CON * 32);             // every contraction warp's tile is complete
     for (int i = ct; i < F3_ACC * D; i += F3_CON * 32) {
@@ -465,7 +500,7 @@ __device__ __forceinline__ void f3_con_task(const F3Args& p, F3Smem<LV>& S, cons
       const int sid = S.meta[s];
       if (sid >= 0) {
         const float v = ((S.tile[0][s][f] + S.tile[1][s][f]) + S.tile[2][s][f]) + S.tile[3][s][f];
-        p.part[((size_t)sid * NSL + r) * D + f] = v;
+        p.part[((size_t)sid * Cfg::NSLV + r) * D + f] = v;
       }
     }
     if (b + 1 < nb) f3_bar_arrive(F3_BAR_EMPTY, F3_THREADS);   // slots and meta may be overwritten
@@ -477,7 +512,7 @@ __device__ __forceinline__ void f3_con_task(const F3Args& p, F3Smem<LV>& S, cons
 template <int LV>
 __global__ void __launch_bounds__(F3_THREADS, 1) k_conv_fused(const __grid_constant__ F3Args p) {
   using Cfg = F3Cfg<LV>;
-  constexpr int NSLOT = Cfg::NSLOT, NT0U = Cfg::NT0U, NT0 = Cfg::NT0, NGEN = Cfg::NGEN;
+  constexpr int J = Cfg::J, NSLV = Cfg::NSLV, NCOMBO = 4 * Cfg::NSLV;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   F3Smem<LV>& S = *reinterpret_cast<F3Smem<LV>*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -488,32 +523,31 @@ __global__ void __launch_bounds__(F3_THREADS, 1) k_conv_fused(const __grid_const
     typename F3Smem<LV>::Stage& T = S.st[w];
     const float* X0 = &T.X[0][0][0];
     const float* S0 = &T.SH[0][0][0];
+    LB.pA = X0 + p.btab[lane].ia;
+    LB.pB = X0 + (Cfg::HAS_B ? p.btab[Cfg::SLOT_B * 32 + lane].ia : 0);
+    LB.pV0 = X0 + (Cfg::HAS_V0 ? p.btab[Cfg::SLOT_V0 * 32 + lane].ia : 0);
+    LB.mh = (lane & 16) != 0;
 #pragma unroll
-    for (int k = 0; k < NSLOT; ++k) {
-      const BasisEnt be = p.btab[k * 32 + lane];
-      LB.xp[k] = X0 + be.ia;
-      if (k >= NT0U) LB.sp[k - NT0U] = S0 + be.ma;
-      if (k >= NT0U + NT0) {
-        const int q = k - NT0U - NT0;
-        LB.gx[2 * q] = X0 + be.ib; LB.gx[2 * q + 1] = X0 + be.ic;
-        LB.gs[2 * q] = S0 + be.mb; LB.gs[2 * q + 1] = S0 + be.mc;
-        LB.gf[3 * q] = be.fa; LB.gf[3 * q + 1] = be.fb; LB.gf[3 * q + 2] = be.fc;
-      }
+    for (int q = 0; q < Cfg::NGEN; ++q) {
+      const BasisEnt be = p.btab[(Cfg::SLOT_G + q) * 32 + lane];
+      LB.gx[3 * q] = X0 + be.ia; LB.gx[3 * q + 1] = X0 + be.ib; LB.gx[3 * q + 2] = X0 + be.ic;
+      LB.gs[3 * q] = S0 + be.ma; LB.gs[3 * q + 1] = S0 + be.mb; LB.gs[3 * q + 2] = S0 + be.mc;
+      LB.gf[3 * q] = be.fa; LB.gf[3 * q + 1] = be.fb; LB.gf[3 * q + 2] = be.fc;
     }
   }
-  if (tid == 0) { S.task[5] = blockIdx.x % F3_NCOMBO; S.task[6] = -1; }
+  if (tid == 0) { S.task[5] = blockIdx.x % NCOMBO; S.task[6] = -1; }
   __syncthreads();
 
   for (;;) {
     if (tid == 0) {
       int combo = S.task[5], found = 0;
-      for (int tries = 0; tries < F3_NCOMBO && !found; ++tries) {
-        const int g = combo / NSL;
+      for (int tries = 0; tries < NCOMBO && !found; ++tries) {
+        const int g = combo / NSLV;
         const int nblk = (p.gcnt[g] + p.nb_segs - 1) / p.nb_segs;
         if (nblk > 0) {
           const int blk = atomicAdd(p.counters + combo, 1);
           if (blk < nblk) {
-            S.task[0] = g; S.task[1] = combo % NSL; S.task[2] = blk * p.nb_segs;
+            S.task[0] = g; S.task[1] = combo % NSLV; S.task[2] = blk * p.nb_segs;
             S.task[3] = min(p.nb_segs, p.gcnt[g] - blk * p.nb_segs);
             S.task[4] = (combo != S.task[6]);
             S.task[5] = combo; S.task[6] = combo;
@@ -521,7 +555,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1) k_conv_fused(const __grid_const
             break;
           }
         }
-        combo = (combo + 1) % F3_NCOMBO;
+        combo = (combo + 1) % NCOMBO;
       }
       if (!found) S.task[0] = -1;
     }
@@ -530,13 +564,13 @@ __global__ void __launch_bounds__(F3_THREADS, 1) k_conv_fused(const __grid_const
     if (g < 0) break;
     const int r = S.task[1], idx0 = S.task[2], nseg = S.task[3];
     if (S.task[4]) {
-      const float4* src = reinterpret_cast<const float4*>(p.W2S[g] + (size_t)r * Cfg::W * J3);
+      const float4* src = reinterpret_cast<const float4*>(p.W2S[g] + (size_t)r * Cfg::W * J);
       float4* dst = reinterpret_cast<float4*>(S.Wsl);
-      for (int i = tid; i < Cfg::W * J3 / 4; i += F3_THREADS) dst[i] = src[i];
+      for (int i = tid; i < Cfg::W * J / 4; i += F3_THREADS) dst[i] = src[i];
       if (r == 0)
         for (int i = tid; i < Cfg::W / 4; i += F3_THREADS)
           reinterpret_cast<float4*>(S.Wb)[i] = reinterpret_cast<const float4*>(p.b2p[g])[i];
-      for (int i = tid; i < J3 * EA; i += F3_THREADS) S.W1a[i / EA][i % EA] = p.W1[g][(J3 * r + i / EA) * HID + i % EA];
+      for (int i = tid; i < J * EA; i += F3_THREADS) S.W1a[i / EA][i % EA] = p.W1[g][(J * r + i / EA) * HID + i % EA];
       __syncthreads();
     }
     if (is_acc) {
@@ -552,14 +586,14 @@ __global__ void __launch_bounds__(F3_THREADS, 1) k_conv_fused(const __grid_const
 
 // ---------------------------------------------------------------------------------------------- finalize
 struct FinArgs {
-  int N, dout;
+  int N, dout, nsl;
   const int* seg_cnt;
   const float* part;
   const float* bn_scale; const float* bn_shift;
   const float* x_in; float* x_out;
 };
 
-// x_out[node] = bn(mean over the edges of both groups) + x_in[node]  (tensor_layers.py:159-166); the 2 x 9 partial
+// x_out[node] = bn(mean over the edges of both groups) + x_in[node]  (tensor_layers.py:159-166); the 2 x (72 / J) partial
 // outputs of a node are added in a fixed order (group-major, slice ascending).
 __global__ void __launch_bounds__(256) k_conv_finalize(FinArgs p) {
   const int q = threadIdx.x / D, f = threadIdx.x % D;
@@ -571,14 +605,12 @@ __global__ void __launch_bounds__(256) k_conv_finalize(FinArgs p) {
   if (f < p.dout) {
     float s = 0.f;
     if (c0 > 0) {
-      const float* q0 = p.part + ((size_t)(2 * node) * NSL) * D + f;
-#pragma unroll
-      for (int r = 0; r < NSL; ++r) s += q0[r * D];
+      const float* q0 = p.part + ((size_t)(2 * node) * p.nsl) * D + f;
+      for (int r = 0; r < p.nsl; ++r) s += q0[r * D];
     }
     if (c1 > 0) {
-      const float* q1 = p.part + ((size_t)(2 * node + 1) * NSL) * D + f;
-#pragma unroll
-      for (int r = 0; r < NSL; ++r) s += q1[r * D];
+      const float* q1 = p.part + ((size_t)(2 * node + 1) * p.nsl) * D + f;
+      for (int r = 0; r < p.nsl; ++r) s += q1[r * D];
     }
     const float cn = fmaxf((float)(c0 + c1), 1.f);
     v = (s / cn) * p.bn_scale[f] + p.bn_shift[f] + p.x_in[(size_t)node * D + f];
@@ -617,27 +649,43 @@ static void basis_desc_host(int lv, int u, int& type, int& i0, int& m) {
   if (u < 6) { type = 1; i0 = X1E + 3 * u; } else { type = 0; i0 = X0O + (u - 6); m = 0; }
 }
 
-// (slot, lane) -> basis row.  Order: per harmonic component m the first floor(count_m / 32) * 32 type-0 rows (slots
-// with a compile-time m), then the remaining type-0 rows, then the dot / cross rows; idle lanes get u = -1.
+// (slot, lane) -> basis row, by source feature (see F3Cfg); idle lanes get u = -1.
 void build_basis_table(int lv, std::vector<BasisEnt>& tab) {
   const int U = lv == 0 ? 96 : (lv == 1 ? 138 : (lv == 2 ? 180 : 276));
-  const int nslot = (U + 31) / 32;
-  std::vector<int> t0[4], rest, gen, order;
+  const bool hasB = lv == 3, hasV0 = lv >= 2;
+  const int ngen = lv == 0 ? 0 : 2;
+  const int slotB = 4, slotV0 = 4 + (hasB ? 2 : 0), slotG = slotV0 + (hasV0 ? 1 : 0), nslot = slotG + ngen;
+  std::vector<int> t0row(84 * 4, -1);
+  std::vector<char> used(U, 0);
   for (int u = 0; u < U; ++u) {
     int ty, i0, m;
     basis_desc_host(lv, u, ty, i0, m);
-    if (ty == 0) t0[m].push_back(u); else gen.push_back(u);
+    if (ty == 0) t0row[i0 * 4 + m] = u;
   }
-  for (int m = 0; m < 4; ++m) {
-    const size_t nu = (t0[m].size() / 32) * 32;
-    order.insert(order.end(), t0[m].begin(), t0[m].begin() + nu);
-    rest.insert(rest.end(), t0[m].begin() + nu, t0[m].end());
-  }
-  order.insert(order.end(), rest.begin(), rest.end());
-  order.insert(order.end(), gen.begin(), gen.end());
   tab.assign((size_t)nslot * 32, BasisEnt{-1, 0, 0, 0, 0, 0, 0, 0.f, 0.f, 0.f});
-  for (size_t q = 0; q < order.size(); ++q) {
-    const int u = order[q];
+  auto put_t0 = [&](int slot, int lane, int i0, int m) {
+    const int u = t0row[i0 * 4 + m];
+    tab[(size_t)slot * 32 + lane] = BasisEnt{u, i0, i0, i0, m, 0, 0, 1.f, 0.f, 0.f};
+    if (u >= 0) used[u] = 1;
+  };
+  std::vector<int> ssrc, vsrc;
+  for (int i = 0; i < 24; ++i) ssrc.push_back(i);                       // x0e
+  if (lv == 3) for (int i = 0; i < 24; ++i) ssrc.push_back(60 + i);     // x0o
+  if (lv >= 1) for (int i = 24; i < 42; ++i) vsrc.push_back(i);         // x1o[k][c]
+  if (lv >= 2) for (int i = 42; i < 60; ++i) vsrc.push_back(i);         // x1e[k][c]
+  for (int l = 0; l < 32 && l < (int)ssrc.size(); ++l)
+    for (int m = 0; m < 4; ++m) put_t0(m, l, ssrc[l], m);
+  if (hasB)
+    for (int l = 0; l < 32; ++l) {
+      const int src = ssrc[32 + (l & 15)], mh = l >> 4;
+      put_t0(slotB, l, src, mh);
+      put_t0(slotB + 1, l, src, 2 + mh);
+    }
+  if (hasV0)
+    for (int l = 0; l < 32; ++l) put_t0(slotV0, l, vsrc[l], 0);
+  int q = 0;
+  for (int u = 0; u < U; ++u) {
+    if (used[u]) continue;
     int ty, i0, m;
     basis_desc_host(lv, u, ty, i0, m);
     BasisEnt e{u, i0, i0, i0, m, 0, 0, 1.f, 0.f, 0.f};
@@ -648,8 +696,10 @@ void build_basis_table(int lv, std::vector<BasisEnt>& tab) {
       e.ib = i0 + c2; e.mb = 1 + c1; e.fb = -1.f;
       e.ic = e.ia; e.mc = 0; e.fc = 0.f;
     }
-    tab[q] = e;
+    if (q < ngen * 32) tab[(size_t)(slotG + q / 32) * 32 + q % 32] = e;
+    ++q;
   }
+  if (q > ngen * 32) tab.clear();     // cannot happen for lv 0..3 (checked by ddk_create)
 }
 
 // contiguous, cost-balanced split of the (class, f) rows of a layer over the contraction warps
@@ -699,7 +749,8 @@ void launch_conv_fused(DdkCtx* c, int layer, const float* x_in, float* x_out, cu
   F3Args a;
   a.NL = c->NL; a.N = c->N;
   const int nsegs = 2 * c->N;
-  int nb = (int)((int64_t)nsegs * NSL / (c->sm_count * 6)) / F3_ACC * F3_ACC;
+  const int J = f3_J(li.lv), nsl = f3_nsl(li.lv);
+  int nb = (int)((int64_t)nsegs * nsl / (c->sm_count * 6)) / F3_ACC * F3_ACC;
   a.nb_segs = std::min(128, std::max(F3_ACC, nb));
   a.glist = ptr<int4>(c->b_glist);
   a.goff[0] = 0; a.goff[1] = c->NL; a.goff[2] = 2 * c->NL; a.goff[3] = 2 * c->NL + c->NR;
@@ -721,9 +772,9 @@ void launch_conv_fused(DdkCtx* c, int layer, const float* x_in, float* x_out, cu
   for (int k = 0; k < 4; ++k) {
     a.cls[k] = li.cls[k < li.ncls ? k : 0];
     a.w8off[k] = w8;
-    if (k < li.ncls) w8 += li.cls[k].F * J3 * li.cls[k].O;
+    if (k < li.ncls) w8 += li.cls[k].F * J * li.cls[k].O;
   }
-  cudaMemsetAsync(c->b_counters.p, 0, F3_NCOMBO * sizeof(int), st);
+  cudaMemsetAsync(c->b_counters.p, 0, F3_NCOMBO_MAX * sizeof(int), st);
   const int grid = c->sm_count;
   {
     LaunchScope ls(c, PC_ACC0 + li.lv, st);
@@ -735,7 +786,7 @@ void launch_conv_fused(DdkCtx* c, int layer, const float* x_in, float* x_out, cu
     }
   }
   FinArgs f;
-  f.N = c->N; f.dout = li.dout;
+  f.N = c->N; f.dout = li.dout; f.nsl = nsl;
   f.seg_cnt = ptr<int>(c->b_seg_cnt);
   f.part = ptr<float>(c->b_part);
   f.bn_scale = W(c, conv_id(layer, DDK_WL_BN_SCALE));

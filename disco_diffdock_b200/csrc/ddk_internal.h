@@ -51,10 +51,10 @@ struct Buf {
   size_t bytes = 0;
 };
 
-// ---- fused conv kernel (ddk_conv3.cu): hidden units are processed in NSL slices of J3
-constexpr int J3 = 8;               // hidden units per slice
-constexpr int NSL = HID / J3;       // 9 slices
-constexpr int AST = J3 + 1;         // row stride of an A slot: 8 hidden units + the sum-of-basis (bias) column
+// ---- fused conv kernel (ddk_conv3.cu): hidden units are processed in slices of J (per basis level)
+constexpr int NSL_MAX = 9;          // most slices of any level (72 / 8)
+__host__ __device__ constexpr int f3_J(int lv) { return lv == 1 ? 12 : (lv == 0 ? 12 : 8); }   // hidden units per slice
+__host__ __device__ constexpr int f3_nsl(int lv) { return HID / f3_J(lv); }
 constexpr int F3_ACC = 8;           // accumulate warps per CTA (= segments per contraction batch)
 constexpr int F3_CON = 4;           // contraction warps per CTA
 constexpr int F3_THREADS = (F3_ACC + F3_CON) * 32;
@@ -119,7 +119,7 @@ struct DdkCtx {
   bool conv_v2 = false;               // DDK_CONV=v2: persistent accumulate + tensor-pipe contract over the scratch
                                       // default: fused, hidden-unit-sliced kernel (ddk_conv3.cu), no scratch
   int sm_count = 148;
-  float* w2s = nullptr;               // second-layer weights re-sliced per hidden-unit slice: [layer][group][NSL][W*J3]
+  float* w2s = nullptr;               // second-layer weights re-sliced per hidden-unit slice: [layer][group][72 / J][W * J]
   std::vector<int64_t> w2s_off;       // [layer * 4 + group] (floats)
   ddk::BasisEnt* btab = nullptr;      // per basis level the (slot, lane) -> basis row tables
   int btab_off[4] = {0, 0, 0, 0};

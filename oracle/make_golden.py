@@ -33,7 +33,11 @@ CASES = {
     'forward_cfg1': dict(mseed=2, gain=1.0, cseed=11, n_lig=60, n_rec=300, B=1, t=0.9, latent=0),
     'sample_small': dict(mseed=1, gain=5.0, cseed=4, n_lig=14, n_rec=40, B=2, steps=8, temps=True, latent=0),
     'sample_mid': dict(mseed=1, gain=5.0, cseed=6, n_lig=30, n_rec=80, B=3, steps=20, temps=True, latent=0),
-    'sample_cfg1': dict(mseed=2, gain=5.0, cseed=11, n_lig=60, n_rec=300, B=1, steps=20, temps=True, latent=0),
+    # cseed 12: a WELL-CONDITIONED trajectory.  The model is discontinuous in the positions (radius-graph edges switch on
+    # and off), so a 20-step trajectory can sit next to an edge flip: with cseed 11 the oracle itself lands 3e-3 A away
+    # when its start pose is perturbed by 1e-7 A (below fp32 resolution), with cseed 12 / 15 four 2e-6 A perturbations
+    # all stay within 2e-4 A (tools/golden_conditioning.py).  A golden next to a flip tests rounding luck, not parity.
+    'sample_cfg1': dict(mseed=2, gain=5.0, cseed=12, n_lig=60, n_rec=300, B=1, steps=20, temps=True, latent=0),
 }
 
 
@@ -69,7 +73,10 @@ def main():
     out_dir = os.path.join(ROOT, 'tests', 'golden')
     os.makedirs(out_dir, exist_ok=True)
     mods = ref_loader.modules()
+    only = set(sys.argv[1:])
     for name, c in CASES.items():
+        if only and name not in only:
+            continue
         if name.startswith('forward'):
             m, sd, cfg, batch = forward_inputs(c)
             ref_model, _ = ref_loader.build_reference_model(cfg, sd)

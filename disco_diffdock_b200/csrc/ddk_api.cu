@@ -186,7 +186,7 @@ int ddk_destroy(DdkCtx* c) {
                 &c->b_lr_off, &c->b_seg_base, &c->b_seg_static, &c->b_seg_cnt, &c->b_seg_list, &c->b_seg_order,
                 &c->b_seg_sidx, &c->b_lig_static, &c->b_rec_static, &c->b_rr_pre, &c->b_ea_pool, &c->b_sh_pool, &c->b_tb,
                 &c->b_xa, &c->b_xb, &c->b_proj, &c->b_A, &c->b_Bsum, &c->b_tr, &c->b_rot, &c->b_tor, &c->b_pos, &c->b_step, &c->b_edge_total, &c->b_work, &c->b_nwork,
-                &c->b_glist, &c->b_gcnt, &c->b_counters, &c->b_part};
+                &c->b_glist, &c->b_gcnt, &c->b_counters, &c->b_part, &c->b_hs};
   for (Buf* b : all) free_buf(*b);
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   if (c->w) cudaFree(c->w);
@@ -343,6 +343,7 @@ int ddk_set_batch(DdkCtx* c, const DdkBatch* b, void* stream) {
   } else {
     EN(c->b_glist, (size_t)nsegs * 16); EN(c->b_gcnt, 4 * 4); EN(c->b_counters, 4 * NSL_MAX * 4);
     EN(c->b_part, (size_t)nsegs * NSL_MAX * D * 4);
+    EN(c->b_hs, (size_t)std::max<int64_t>(total, 1) * HID * 4);
   }
   EN(c->b_tr, (size_t)B * 3 * 4); EN(c->b_rot, (size_t)B * 3 * 4); EN(c->b_tor, (size_t)std::max(c->RB, 1) * 4);
 #undef EN

@@ -383,7 +383,7 @@ void launch_node_proj(DdkCtx* c, int layer, const float* x_in, float* x0_out, cu
     p.b1[g] = W(c, conv_id(layer, DDK_WL_B1 + g));
   }
   p.proj = ptr<float>(c->b_proj);
-  p.sliced = (c->conv_v1 || c->conv_v2) ? 0 : f3_J(c->layers[layer].lv); p.N = c->N;
+  p.sliced = 0; p.N = c->N;
   int blocks = (c->NL + PROJ_NODES - 1) / PROJ_NODES + (c->NR + PROJ_NODES - 1) / PROJ_NODES;
   LaunchScope ls(c, PC_PROJ, st);
   if (x0_out != nullptr) k_node_proj<true><<<blocks, 288, 0, st>>>(p);
@@ -391,7 +391,11 @@ void launch_node_proj(DdkCtx* c, int layer, const float* x_in, float* x0_out, cu
 }
 
 void launch_conv_layer(DdkCtx* c, int layer, const float* x_in, float* x_out, cudaStream_t st) {
-  if (!c->conv_v1 && !c->conv_v2) { launch_conv_fused(c, layer, x_in, x_out, st); return; }
+  if (!c->conv_v1 && !c->conv_v2) {
+    launch_edge_hidden(c, layer, st);
+    launch_conv_fused(c, layer, x_in, x_out, st);
+    return;
+  }
   const LayerInfo& li = c->layers[layer];
   for (const Chunk& ch : c->chunks) {
     AccArgs a;

@@ -8,8 +8,9 @@
 // weights (W_l x 8 floats, <= 60 KB) resident in shared memory, and for every segment of the group
 //   - an accumulate warp builds A_s[:, slice] (U x 8) in REGISTERS: the lane owns up to 9 basis rows u; per edge it
 //     evaluates its basis values straight from the staged destination features / harmonics (no basis tile in shared
-//     memory) and does 8 FFMA per row against the 8 hidden units h_e[slice] of the edge (first MLP layer, evaluated
-//     by the same warp from the staged edge embedding and the per-node projections);
+//     memory) and does 4 packed FFMA2 (fma.rn.f32x2: scalar basis value x pair of hidden units) per row against the 8
+//     hidden units h_e[slice] of the edge.  h_e (first radial-MLP layer) is produced once per layer for every listed
+//     edge by k_edge_hidden (ddk_hidden.cu) in slice-major list order, so a chunk's slice is one contiguous block;
 //   - at the end of the segment the U x 8 block (+ the Bsum column in slice 0) goes to a per-warp shared-memory slot;
 //   - four contraction warps take the 8 slots of a batch together (so every weight read from shared memory is used for
 //     8 segments), contract them against the resident weight slice and write the 84-wide PARTIAL output of
@@ -29,7 +30,6 @@
 
 namespace ddk {
 
-constexpr int EAS = 28;            // padded row of the staged edge embedding (conflict-free LDS.128 across 8 edges)
 constexpr int F3_NCOMBO_MAX = 4 * NSL_MAX;
 
 enum { F3_BAR_FULL = 1, F3_BAR_EMPTY = 2, F3_BAR_CON = 3, F3_BAR_CON2 = 4 };
@@ -66,11 +66,8 @@ struct F3Smem {
   struct Stage {
     alignas(16) float X[2][KC3][F3Cfg<LV>::DINP];
     alignas(16) float SH[2][KC3][4];
-    alignas(16) float EA[KC3][EAS];
-    alignas(16) float PD[KC3][F3Cfg<LV>::J];
-    alignas(16) float H[KC3][F3Cfg<LV>::J];
+    alignas(16) float H[2][KC3][F3Cfg<LV>::J];
   } st[F3_ACC];
-  alignas(16) float W1a[F3Cfg<LV>::J][EA];                   // first-layer rows of the slice, edge-embedding columns
   alignas(16) float tile[F3_CON][F3_ACC][D];                 // per contraction warp partial outputs of a batch
   int meta[F3_ACC];                                          // segment id of each slot of the batch in flight (-1: none)
   int task[8];                                               // g, r, idx0, nseg, reload, combo cursor, resident combo
@@ -85,9 +82,9 @@ struct F3Args {
   int* counters;                     // [4 * NSLV] next block of each combo
   const int2* seg_list;
   const float* x;                    // [N][84] layer input
-  const float* projs;                // [NSLV][N][4][J]
-  const float* ea_pool; const float4* sh_pool;
-  const float* W1[4];                // [72][72]
+  const float* hs;                   // [NSLV][LT][J] hidden units of every listed edge (k_edge_hidden)
+  size_t LT;                         // capacity of seg_list
+  const float4* sh_pool;
   const float* W2S[4];               // [NSLV][W * J]
   const float* b2p[4];               // [W]
   const BasisEnt* btab;              // [NSLOT * 32]
@@ -132,47 +129,60 @@ __global__ void __launch_bounds__(1024) k_build_group_lists(int NL, int NR, cons
 template <int LV>
 struct LaneBasis {
   static constexpr int NG3 = F3Cfg<LV>::NGEN > 0 ? 3 * F3Cfg<LV>::NGEN : 1;
-  const float* pA;                   // &X[buf][0][i] of the lane's scalar source (slots A)
-  const float* pB;                   // slots B
-  const float* pV0;                  // slot V0
-  const float* gx[NG3];              // generic slots: x term pointers
-  const float* gs[NG3];              //                harmonic term pointers (&SH[buf][0][m])
+  int oA;                            // column of the lane's scalar source inside a staged feature row (slots A)
+  int oB;                            // slots B
+  int oV0;                           // slot V0
+  int gx[NG3];                       // generic slots: x term columns
+  int gs[NG3];                       //                harmonic term indices (0..3)
   float gf[NG3];                     //                coefficients (0, +1, -1)
   bool mh;                           // lane >> 4 (slots B)
 };
 
-struct ChunkD {
-  int node, which, base, c0, kc, batch;
-  bool first, last, valid, done;
+struct ChunkD {                       // one gather chunk (<= KC3 consecutive list entries of a segment) of an accumulate warp
+  int pos, kc, seg, flags;           // first list position, edges, segment id (valid when CD_LAST), CD_* flags
 };
+enum { CD_VALID = 1, CD_LAST = 2, CD_DONE = 4, CD_NOT_FIRST_BATCH = 8 };
 
 __device__ __forceinline__ void f3_cp16(void* dst, const void* src) { __pipeline_memcpy_async(dst, src, 16); }
 
-// one edge: 8..24 hidden units of the slice against every basis row of the lane
+// packed fp32 pairs (sm_100a FFMA2): d.{x,y} += a.{x,y} * b.{x,y}; with a = (v, v) ptxas emits the scalar-broadcast form
+typedef unsigned long long f32x2;
+__device__ __forceinline__ void f3_ffma2(f32x2& d, const f32x2 a, const f32x2 b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ f32x2 f3_pack2(const float x, const float y) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+  return r;
+}
+__device__ __forceinline__ void f3_unpack2(const f32x2 v, float& x, float& y) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v));
+}
+
+// one edge: the J hidden units of the slice (as J / 2 packed pairs) against every basis row of the lane
 template <int LV, bool BIAS>
-__device__ __forceinline__ void f3_edge(float (&acc)[F3Cfg<LV>::NSLOT][F3Cfg<LV>::J], float (&bs)[F3Cfg<LV>::NSLOT],
+__device__ __forceinline__ void f3_edge(f32x2 (&acc)[F3Cfg<LV>::NSLOT][F3Cfg<LV>::J / 2], float (&bs)[F3Cfg<LV>::NSLOT],
                                         const LaneBasis<LV>& LB, const float* __restrict__ hrow,
-                                        const float* __restrict__ shrow, const int xo, const int so) {
+                                        const float* __restrict__ shrow, const float* __restrict__ xrow) {
   using Cfg = F3Cfg<LV>;
   constexpr int J = Cfg::J, NSLOT = Cfg::NSLOT;
-  constexpr int JH = J > 12 ? 12 : J;           // hidden units handled per pass (keeps the live set small at J = 24)
   // basis values of the lane's rows for this edge
   float b[NSLOT];
   {
     const float4 s4 = *reinterpret_cast<const float4*>(shrow);
-    const float xa = LB.pA[xo];
+    const float xa = xrow[LB.oA];
     b[0] = xa * s4.x; b[1] = xa * s4.y; b[2] = xa * s4.z; b[3] = xa * s4.w;
     if (Cfg::HAS_B) {
-      const float xb = LB.pB[xo];
+      const float xb = xrow[LB.oB];
       b[Cfg::SLOT_B] = xb * (LB.mh ? s4.y : s4.x);
       b[Cfg::SLOT_B + 1] = xb * (LB.mh ? s4.w : s4.z);
     }
-    if (Cfg::HAS_V0) b[Cfg::SLOT_V0] = LB.pV0[xo] * s4.x;
+    if (Cfg::HAS_V0) b[Cfg::SLOT_V0] = xrow[LB.oV0] * s4.x;
 #pragma unroll
     for (int q = 0; q < Cfg::NGEN; ++q) {
-      float v = LB.gf[3 * q] * (LB.gx[3 * q][xo] * LB.gs[3 * q][so]);
-      v += LB.gf[3 * q + 1] * (LB.gx[3 * q + 1][xo] * LB.gs[3 * q + 1][so]);
-      v += LB.gf[3 * q + 2] * (LB.gx[3 * q + 2][xo] * LB.gs[3 * q + 2][so]);
+      float v = LB.gf[3 * q] * (xrow[LB.gx[3 * q]] * shrow[LB.gs[3 * q]]);
+      v += LB.gf[3 * q + 1] * (xrow[LB.gx[3 * q + 1]] * shrow[LB.gs[3 * q + 1]]);
+      v += LB.gf[3 * q + 2] * (xrow[LB.gx[3 * q + 2]] * shrow[LB.gs[3 * q + 2]]);
       b[Cfg::SLOT_G + q] = v;
     }
   }
@@ -180,18 +190,17 @@ __device__ __forceinline__ void f3_edge(float (&acc)[F3Cfg<LV>::NSLOT][F3Cfg<LV>
 #pragma unroll
     for (int k = 0; k < NSLOT; ++k) bs[k] += b[k];
   }
+  f32x2 h[J / 2];
 #pragma unroll
-  for (int j0 = 0; j0 < J; j0 += JH) {
-    float h[JH];
+  for (int q = 0; q < J / 4; ++q) {
+    const float4 v = *reinterpret_cast<const float4*>(hrow + 4 * q);
+    h[2 * q] = f3_pack2(v.x, v.y); h[2 * q + 1] = f3_pack2(v.z, v.w);
+  }
 #pragma unroll
-    for (int q = 0; q < JH / 4; ++q) {
-      const float4 v = *reinterpret_cast<const float4*>(hrow + j0 + 4 * q);
-      h[4 * q] = v.x; h[4 * q + 1] = v.y; h[4 * q + 2] = v.z; h[4 * q + 3] = v.w;
-    }
+  for (int k = 0; k < NSLOT; ++k) {
+    const f32x2 bb = f3_pack2(b[k], b[k]);
 #pragma unroll
-    for (int k = 0; k < NSLOT; ++k)
-#pragma unroll
-      for (int j = 0; j < JH; ++j) acc[k][j0 + j] += b[k] * h[j];
+    for (int j = 0; j < J / 2; ++j) f3_ffma2(acc[k][j], bb, h[j]);
   }
 }
 
@@ -199,23 +208,21 @@ template <int LV, bool BIAS>
 __device__ __forceinline__ void f3_acc_task(const F3Args& p, F3Smem<LV>& S, LaneBasis<LV>& LB, const int g, const int r,
                                             const int idx0, const int nseg, const int w, const int lane) {
   using Cfg = F3Cfg<LV>;
-  constexpr int NSLOT = Cfg::NSLOT, DINP = Cfg::DINP, J = Cfg::J, JQ = Cfg::JQ, AST = Cfg::AST, XQ = Cfg::XQ;
-  constexpr int XBUF = KC3 * DINP, SBUF = KC3 * 4;
-  constexpr int NG3 = 3 * Cfg::NGEN;
+  constexpr int NSLOT = Cfg::NSLOT, DINP = Cfg::DINP, J = Cfg::J, AST = Cfg::AST, XQ = Cfg::XQ;
+  constexpr int XBUF = KC3 * DINP, SBUF = KC3 * 4, HBUF = KC3 * J;
   typename F3Smem<LV>::Stage& T = S.st[w];
   const int nb = (nseg + F3_ACC - 1) / F3_ACC;
-  const int dslot = (g == 1 || g == 3) ? 3 : 2;
   const int4* wl = p.glist + p.goff[g] + idx0;
-  const float* projr = p.projs + (size_t)r * p.N * 4 * J;
-  const int ge = lane & 7, gsub = lane >> 3;        // gather / first-layer role of the lane: edge, sub-lane
+  const float* hsr = p.hs + (size_t)r * p.LT * J;   // slice r of the hidden units, list order
+  const int ge = lane & 7, gsub = lane >> 3;        // gather role of the lane: edge, 16-byte sub-piece
 
-  float acc[NSLOT][J];
+  f32x2 acc[NSLOT][J / 2];
   float bs[NSLOT];
 #pragma unroll
   for (int k = 0; k < NSLOT; ++k) {
     bs[k] = 0.f;
 #pragma unroll
-    for (int j = 0; j < J; ++j) acc[k][j] = 0.f;
+    for (int j = 0; j < J / 2; ++j) acc[k][j] = 0ull;
   }
 
   // ---- chunk generator: batches bi = 0..nb-1, this warp's segment of a batch is idx0 + 8 bi + w (or none)
@@ -224,41 +231,33 @@ __device__ __forceinline__ void f3_acc_task(const F3Args& p, F3Smem<LV>& S, Lane
   int4 pre = (w < nseg) ? wl[w] : make_int4(-1, 0, 0, 0);
   auto next_cd = [&]() {
     ChunkD d;
-    d.done = false; d.valid = false; d.first = true; d.last = true;
-    d.node = 0; d.which = 0; d.base = 0; d.c0 = 0; d.kc = 0; d.batch = bi;
+    d.pos = 0; d.kc = 0; d.seg = -1;
+    d.flags = CD_LAST | (bi > 0 ? CD_NOT_FIRST_BATCH : 0);
     if (!in_seg) {
-      if (bi >= nb) { d.done = true; return d; }
+      if (bi >= nb) { d.flags = CD_DONE; return d; }
       const int si = F3_ACC * bi + w;
       if (si >= nseg) { ++bi; return d; }           // no segment for this warp in the batch: empty slot
       seg = pre.x; n = pre.y; sbase = pre.z; c0 = 0; in_seg = true;
       const int sn = si + F3_ACC;
       pre = (sn < nseg) ? wl[sn] : make_int4(-1, 0, 0, 0);
     }
-    d.valid = true;
-    d.node = seg >> 1; d.which = seg & 1; d.base = sbase; d.c0 = c0;
+    d.pos = sbase + c0;
     d.kc = min(KC3, n - c0);
-    d.first = (c0 == 0);
-    d.last = (c0 + d.kc >= n);
+    d.seg = seg;
     c0 += d.kc;
-    if (d.last) { in_seg = false; ++bi; }
+    d.flags = CD_VALID | (bi > 0 ? CD_NOT_FIRST_BATCH : 0);
+    if (c0 >= n) { d.flags |= CD_LAST; in_seg = false; ++bi; }
     return d;
   };
   auto load_ent = [&](const ChunkD& d) {
     int2 e = make_int2(0, 0);
-    if (d.valid && lane < d.kc) e = p.seg_list[d.base + d.c0 + lane];
+    if (lane < d.kc) e = p.seg_list[d.pos + lane];
     return e;
   };
-  // source-side projection of the segment's node: the lane needs hidden units gsub + 4 i
-  auto load_ps = [&](const ChunkD& d, float (&v)[JQ]) {
-    if (d.valid) {
-      const float* q = projr + ((size_t)d.node * 4 + d.which) * J + gsub;
-#pragma unroll
-      for (int i = 0; i < JQ; ++i) v[i] = q[4 * i];
-    }
-  };
-  // every lane copies fixed 16-byte pieces (q = gsub + 4 i) of its edge ge: two shuffles per chunk, immediate offsets
+  // every lane copies fixed 16-byte pieces (q = gsub + 4 i) of the destination features of its edge ge (two shuffles per
+  // chunk, immediate offsets); the chunk's hidden-unit slice is one contiguous block of kc * J floats
   auto gather = [&](const ChunkD& d, const int2 ent, const int buf) {
-    if (d.valid) {
+    if (d.kc > 0) {
       const int slot = __shfl_sync(0xffffffffu, ent.x, ge);
       const int dst = __shfl_sync(0xffffffffu, ent.y, ge);
       if (ge < d.kc) {
@@ -267,114 +266,72 @@ __device__ __forceinline__ void f3_acc_task(const F3Args& p, F3Smem<LV>& S, Lane
 #pragma unroll
         for (int i = 0; i < (XQ + 3) / 4; ++i)
           if (gsub + 4 * i < XQ) f3_cp16(xd + 16 * i, xs + 16 * i);
-        const float* es = p.ea_pool + (size_t)slot * EA + 4 * gsub;
-        f3_cp16(&T.EA[ge][4 * gsub], es);
-        if (gsub < 2) f3_cp16(&T.EA[ge][16 + 4 * gsub], es + 16);
-        const float* pd = projr + ((size_t)dst * 4 + dslot) * J + 4 * gsub;
-#pragma unroll
-        for (int i = 0; i < (JQ + 3) / 4; ++i)
-          if (gsub + 4 * i < JQ) f3_cp16(&T.PD[ge][4 * gsub + 16 * i], pd + 16 * i);
         if (gsub == 0) f3_cp16(&T.SH[buf][ge][0], p.sh_pool + slot);
       }
+      if (lane < d.kc * (J / 4))
+        f3_cp16(&T.H[buf][0][0] + 4 * lane, hsr + (size_t)d.pos * J + 4 * lane);
     }
     __pipeline_commit();
   };
 
   ChunkD cd0 = next_cd();
-  ChunkD cd1 = cd0.done ? cd0 : next_cd();
+  ChunkD cd1 = (cd0.flags & CD_DONE) ? cd0 : next_cd();
   int2 ent1;
-  float ps[JQ], pn[JQ];
-#pragma unroll
-  for (int i = 0; i < JQ; ++i) { ps[i] = 0.f; pn[i] = 0.f; }
   {
     const int2 ent0 = load_ent(cd0);
-    load_ps(cd0, ps);
     gather(cd0, ent0, 0);
     ent1 = load_ent(cd1);
   }
   int buf = 0;
-  while (!cd0.done) {
+  while (!(cd0.flags & CD_DONE)) {
     __pipeline_wait_prior(0);
     __syncwarp();
-    if (cd0.valid) {
-      // ---- first radial-MLP layer for the slice: h = relu(W1[:, :24] ea + (W1[:,24:48] x_s + b1) + W1[:,48:72] x_d)
-      float h[JQ];
-#pragma unroll
-      for (int i = 0; i < JQ; ++i) h[i] = ps[i] + T.PD[ge][gsub + 4 * i];
-#pragma unroll
-      for (int q = 0; q < EA / 4; ++q) {
-        const float4 ea = *reinterpret_cast<const float4*>(&T.EA[ge][4 * q]);
-#pragma unroll
-        for (int i = 0; i < JQ; ++i) {
-          const float4 wv = *reinterpret_cast<const float4*>(&S.W1a[gsub + 4 * i][4 * q]);
-          h[i] += wv.x * ea.x + wv.y * ea.y + wv.z * ea.z + wv.w * ea.w;
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < JQ; ++i) T.H[ge][gsub + 4 * i] = fmaxf(h[i], 0.f);
-    }
-    __syncwarp();
-    // ---- next chunk's gathers travel while this chunk is accumulated (EA / PD of this chunk are consumed)
-    if (!cd1.done) {
-      if (cd1.first) load_ps(cd1, pn);
-      gather(cd1, ent1, buf ^ 1);
-    } else {
-      __pipeline_commit();
-    }
-    ChunkD cd2 = cd1.done ? cd1 : next_cd();
+    // ---- next chunk's gathers travel while this chunk is accumulated (the other buffer was consumed last iteration)
+    gather(cd1, ent1, buf ^ 1);
+    ChunkD cd2 = (cd1.flags & CD_DONE) ? cd1 : next_cd();
     const int2 ent2 = load_ent(cd2);
 
-    if (cd0.valid) {
-      const float* hb = &T.H[0][0];
+    if (cd0.kc > 0) {
+      const float* hb = &T.H[0][0][0] + buf * HBUF;
       const float* sb = &T.SH[0][0][0] + buf * SBUF;
+      const float* xb = &T.X[0][0][0] + buf * XBUF;
       if (cd0.kc == KC3) {
 #pragma unroll
-        for (int e = 0; e < KC3; ++e) f3_edge<LV, BIAS>(acc, bs, LB, hb + e * J, sb + e * 4, e * DINP, e * 4);
+        for (int e = 0; e < KC3; ++e) f3_edge<LV, BIAS>(acc, bs, LB, hb + e * J, sb + e * 4, xb + e * DINP);
       } else {
 #pragma unroll 1
-        for (int e = 0; e < cd0.kc; ++e) f3_edge<LV, BIAS>(acc, bs, LB, hb + e * J, sb + e * 4, e * DINP, e * 4);
+        for (int e = 0; e < cd0.kc; ++e) f3_edge<LV, BIAS>(acc, bs, LB, hb + e * J, sb + e * 4, xb + e * DINP);
       }
     }
-    if (cd0.last) {
+    if (cd0.flags & CD_LAST) {
       // ---- hand the finished U x J block to the contraction warps
-      if (cd0.batch > 0) f3_bar_sync(F3_BAR_EMPTY, F3_THREADS);      // they are done with the previous batch
-      if (cd0.valid) {
+      if (cd0.flags & CD_NOT_FIRST_BATCH) f3_bar_sync(F3_BAR_EMPTY, F3_THREADS);   // they are done with the previous batch
+      if (cd0.flags & CD_VALID) {
         float* slot = &S.As[w][0];
 #pragma unroll
         for (int k = 0; k < NSLOT; ++k) {
           const int u = p.btab[k * 32 + lane].u;
           if (u >= 0) {
 #pragma unroll
-            for (int j = 0; j < J; ++j) slot[u * AST + j] = acc[k][j];
+            for (int j = 0; j < J / 2; ++j) {
+              float v0, v1;
+              f3_unpack2(acc[k][j], v0, v1);
+              slot[u * AST + 2 * j] = v0; slot[u * AST + 2 * j + 1] = v1;
+            }
             if (BIAS) slot[u * AST + J] = bs[k];
           }
           bs[k] = 0.f;
 #pragma unroll
-          for (int j = 0; j < J; ++j) acc[k][j] = 0.f;
+          for (int j = 0; j < J / 2; ++j) acc[k][j] = 0ull;
         }
       }
-      if (lane == 0) S.meta[w] = cd0.valid ? (2 * cd0.node + cd0.which) : -1;
+      if (lane == 0) S.meta[w] = cd0.seg;
       __threadfence_block();
       f3_bar_arrive(F3_BAR_FULL, F3_THREADS);
     }
     // ---- rotate
-    const int tog = buf ? -XBUF : XBUF;
-    const int togs = buf ? -SBUF : SBUF;
-    LB.pA += tog; LB.pB += tog; LB.pV0 += tog;
-#pragma unroll
-    for (int k = 0; k < NG3; ++k) { LB.gx[k] += tog; LB.gs[k] += togs; }
     buf ^= 1;
-    if (cd1.first) {
-#pragma unroll
-      for (int i = 0; i < JQ; ++i) ps[i] = pn[i];
-    }
     cd0 = cd1; cd1 = cd2; ent1 = ent2;
-  }
-  // leave the pointers on buffer 0 for the next task
-  if (buf) {
-    LB.pA -= XBUF; LB.pB -= XBUF; LB.pV0 -= XBUF;
-#pragma unroll
-    for (int k = 0; k < NG3; ++k) { LB.gx[k] -= XBUF; LB.gs[k] -= SBUF; }
   }
   __pipeline_wait_prior(0);
 }
@@ -389,24 +346,24 @@ __device__ __forceinline__ void f3_con_scalar(const float* __restrict__ Wc, cons
   constexpr int JC = BIAS ? J + 1 : J;
   constexpr int AST = J + 1;
   const int kp = lane >> 2, og = lane & 3;
-  float acc[F3_ACC][6];
+  f32x2 acc[F3_ACC][3];
 #pragma unroll
   for (int s = 0; s < F3_ACC; ++s)
 #pragma unroll
-    for (int o = 0; o < 6; ++o) acc[s][o] = 0.f;
+    for (int o = 0; o < 3; ++o) acc[s][o] = 0ull;
   const int nrows = (f1 - f0) * JC;
   int f = f0, jj = kp;                          // kp < 8 <= JC
   for (int q = kp; q < nrows; q += 8) {
     const float* wp = (!BIAS || jj < J) ? Wc + (f * J + jj) * 24 + 6 * og : Wbc + f * 24 + 6 * og;
-    const float2 w0 = *reinterpret_cast<const float2*>(wp);
-    const float2 w1 = *reinterpret_cast<const float2*>(wp + 2);
-    const float2 w2 = *reinterpret_cast<const float2*>(wp + 4);
+    const f32x2 w0 = *reinterpret_cast<const f32x2*>(wp);
+    const f32x2 w1 = *reinterpret_cast<const f32x2*>(wp + 2);
+    const f32x2 w2 = *reinterpret_cast<const f32x2*>(wp + 4);
     const float* ap = As + (uoff + f) * AST + jj;
 #pragma unroll
     for (int s = 0; s < F3_ACC; ++s) {
       const float a = ap[s * ASLOT];
-      acc[s][0] += a * w0.x; acc[s][1] += a * w0.y; acc[s][2] += a * w1.x;
-      acc[s][3] += a * w1.y; acc[s][4] += a * w2.x; acc[s][5] += a * w2.y;
+      const f32x2 aa = f3_pack2(a, a);
+      f3_ffma2(acc[s][0], aa, w0); f3_ffma2(acc[s][1], aa, w1); f3_ffma2(acc[s][2], aa, w2);
     }
     jj += 8;
     if (jj >= JC) { jj -= JC; ++f; }
@@ -415,7 +372,9 @@ __device__ __forceinline__ void f3_con_scalar(const float* __restrict__ Wc, cons
   for (int s = 0; s < F3_ACC; ++s)
 #pragma unroll
     for (int o = 0; o < 6; ++o) {
-      float v = acc[s][o];
+      float v0, v1;
+      f3_unpack2(acc[s][o >> 1], v0, v1);
+      float v = (o & 1) ? v1 : v0;
       v += __shfl_xor_sync(0xffffffffu, v, 4);
       v += __shfl_xor_sync(0xffffffffu, v, 8);
       v += __shfl_xor_sync(0xffffffffu, v, 16);
@@ -432,28 +391,28 @@ __device__ __forceinline__ void f3_con_vector(const float* __restrict__ Wc, cons
   constexpr int JC = BIAS ? J + 1 : J;
   constexpr int AST = J + 1;
   const int kp = lane >> 2, sg = lane & 3;
-  float acc[2][3][6];
+  f32x2 acc[2][3][3];
 #pragma unroll
   for (int s = 0; s < 2; ++s)
 #pragma unroll
     for (int c = 0; c < 3; ++c)
 #pragma unroll
-      for (int o = 0; o < 6; ++o) acc[s][c][o] = 0.f;
+      for (int o = 0; o < 3; ++o) acc[s][c][o] = 0ull;
   const int nrows = (f1 - f0) * JC;
   int f = f0, jj = kp;
   const float* A0 = As + (2 * sg) * ASLOT;
   for (int q = kp; q < nrows; q += 8) {
     const float* wp = (!BIAS || jj < J) ? Wc + (f * J + jj) * 6 : Wbc + f * 6;
-    const float2 w0 = *reinterpret_cast<const float2*>(wp);
-    const float2 w1 = *reinterpret_cast<const float2*>(wp + 2);
-    const float2 w2 = *reinterpret_cast<const float2*>(wp + 4);
+    const f32x2 w0 = *reinterpret_cast<const f32x2*>(wp);
+    const f32x2 w1 = *reinterpret_cast<const f32x2*>(wp + 2);
+    const f32x2 w2 = *reinterpret_cast<const f32x2*>(wp + 4);
 #pragma unroll
     for (int s = 0; s < 2; ++s)
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         const float a = A0[s * ASLOT + (uoff + c * F + f) * AST + jj];
-        acc[s][c][0] += a * w0.x; acc[s][c][1] += a * w0.y; acc[s][c][2] += a * w1.x;
-        acc[s][c][3] += a * w1.y; acc[s][c][4] += a * w2.x; acc[s][c][5] += a * w2.y;
+        const f32x2 aa = f3_pack2(a, a);
+        f3_ffma2(acc[s][c][0], aa, w0); f3_ffma2(acc[s][c][1], aa, w1); f3_ffma2(acc[s][c][2], aa, w2);
       }
     jj += 8;
     if (jj >= JC) { jj -= JC; ++f; }
@@ -464,7 +423,9 @@ __device__ __forceinline__ void f3_con_vector(const float* __restrict__ Wc, cons
     for (int c = 0; c < 3; ++c)
 #pragma unroll
       for (int o = 0; o < 6; ++o) {
-        float v = acc[s][c][o];
+        float v0, v1;
+        f3_unpack2(acc[s][c][o >> 1], v0, v1);
+        float v = (o & 1) ? v1 : v0;
         v += __shfl_xor_sync(0xffffffffu, v, 4);
         v += __shfl_xor_sync(0xffffffffu, v, 8);
         v += __shfl_xor_sync(0xffffffffu, v, 16);
@@ -520,18 +481,15 @@ __global__ void __launch_bounds__(F3_THREADS, 1) k_conv_fused(const __grid_const
 
   LaneBasis<LV> LB;
   if (is_acc) {
-    typename F3Smem<LV>::Stage& T = S.st[w];
-    const float* X0 = &T.X[0][0][0];
-    const float* S0 = &T.SH[0][0][0];
-    LB.pA = X0 + p.btab[lane].ia;
-    LB.pB = X0 + (Cfg::HAS_B ? p.btab[Cfg::SLOT_B * 32 + lane].ia : 0);
-    LB.pV0 = X0 + (Cfg::HAS_V0 ? p.btab[Cfg::SLOT_V0 * 32 + lane].ia : 0);
+    LB.oA = p.btab[lane].ia;
+    LB.oB = Cfg::HAS_B ? p.btab[Cfg::SLOT_B * 32 + lane].ia : 0;
+    LB.oV0 = Cfg::HAS_V0 ? p.btab[Cfg::SLOT_V0 * 32 + lane].ia : 0;
     LB.mh = (lane & 16) != 0;
 #pragma unroll
     for (int q = 0; q < Cfg::NGEN; ++q) {
       const BasisEnt be = p.btab[(Cfg::SLOT_G + q) * 32 + lane];
-      LB.gx[3 * q] = X0 + be.ia; LB.gx[3 * q + 1] = X0 + be.ib; LB.gx[3 * q + 2] = X0 + be.ic;
-      LB.gs[3 * q] = S0 + be.ma; LB.gs[3 * q + 1] = S0 + be.mb; LB.gs[3 * q + 2] = S0 + be.mc;
+      LB.gx[3 * q] = be.ia; LB.gx[3 * q + 1] = be.ib; LB.gx[3 * q + 2] = be.ic;
+      LB.gs[3 * q] = be.ma; LB.gs[3 * q + 1] = be.mb; LB.gs[3 * q + 2] = be.mc;
       LB.gf[3 * q] = be.fa; LB.gf[3 * q + 1] = be.fb; LB.gf[3 * q + 2] = be.fc;
     }
   }
@@ -570,7 +528,6 @@ __global__ void __launch_bounds__(F3_THREADS, 1) k_conv_fused(const __grid_const
       if (r == 0)
         for (int i = tid; i < Cfg::W / 4; i += F3_THREADS)
           reinterpret_cast<float4*>(S.Wb)[i] = reinterpret_cast<const float4*>(p.b2p[g])[i];
-      for (int i = tid; i < J * EA; i += F3_THREADS) S.W1a[i / EA][i % EA] = p.W1[g][(J * r + i / EA) * HID + i % EA];
       __syncthreads();
     }
     if (is_acc) {
@@ -757,10 +714,9 @@ void launch_conv_fused(DdkCtx* c, int layer, const float* x_in, float* x_out, cu
   a.gcnt = ptr<int>(c->b_gcnt);
   a.counters = ptr<int>(c->b_counters);
   a.seg_list = ptr<int2>(c->b_seg_list);
-  a.x = x_in; a.projs = ptr<float>(c->b_proj);
-  a.ea_pool = ptr<float>(c->b_ea_pool); a.sh_pool = ptr<float4>(c->b_sh_pool);
+  a.x = x_in; a.hs = ptr<float>(c->b_hs); a.LT = (size_t)c->list_total;
+  a.sh_pool = ptr<float4>(c->b_sh_pool);
   for (int g = 0; g < 4; ++g) {
-    a.W1[g] = W(c, conv_id(layer, DDK_WL_W1 + g));
     a.W2S[g] = c->w2s + c->w2s_off[layer * 4 + g];
     a.b2p[g] = W(c, conv_id(layer, DDK_WL_B2P + g));
   }

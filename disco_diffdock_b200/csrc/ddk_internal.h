@@ -71,7 +71,7 @@ struct ConSplit {                   // rows [f0, f1) of each irrep class handled
 };
 
 // kernel classes for the optional per-launch CUDA-event timing (ddk_profile_*)
-enum ProfClass { PC_SETUP = 0, PC_GRAPH, PC_PROJ, PC_ACC0, PC_ACC1, PC_ACC2, PC_ACC3, PC_CONTRACT, PC_HEADS, PC_UPDATE, PC_COUNT };
+enum ProfClass { PC_SETUP = 0, PC_GRAPH, PC_PROJ, PC_ACC0, PC_ACC1, PC_ACC2, PC_ACC3, PC_CONTRACT, PC_HEADS, PC_UPDATE, PC_HIDDEN, PC_COUNT };
 
 struct ProfRec {
   int cls;
@@ -125,6 +125,7 @@ struct DdkCtx {
   int btab_off[4] = {0, 0, 0, 0};
   std::vector<ddk::ConSplit> con_split;   // per layer
   ddk::Buf b_glist, b_gcnt, b_counters, b_part;
+  ddk::Buf b_hs;                      // [72 / J][list_total][J]: hidden units of every listed edge of the current layer
 
   // optional profiling (off by default)
   bool prof = false;
@@ -165,6 +166,7 @@ void build_basis_table(int lv, std::vector<BasisEnt>& tab);
 void build_con_split(const LayerInfo& li, ConSplit& sp);
 void launch_build_group_lists(DdkCtx* c, cudaStream_t st);
 void launch_conv_fused(DdkCtx* c, int layer, const float* x_in, float* x_out, cudaStream_t st);
+void launch_edge_hidden(DdkCtx* c, int layer, cudaStream_t st);
 cudaError_t heads_configure();
 void host_kabsch(const float* A, const float* Bp, int N, float* R9, float* t3);   // host build of the device routine (tests)
 void host_axis_angle(const float* aa, float* R9);   // opt-in dynamic shared memory sizes (once per process / device)

@@ -186,9 +186,10 @@ int ddk_debug_read(DdkCtx* ctx, const char* name, void* dst_h, size_t max_bytes,
 
 /* Optional per-launch timing with CUDA events on the launching stream (used by bench.py for the roofline line).
  * Kernel classes: 0 setup, 1 graph (lists + edge embeddings), 2 node projections, 3..6 conv accumulate (basis level
- * 0..3), 7 conv contract, 8 score heads, 9 update.  ddk_profile_read synchronises the device, adds the elapsed
- * milliseconds / launch counts since the last read into ms[10] / launches[10] and clears the records. */
-#define DDK_PROFILE_CLASSES 10
+ * 0..3), 7 conv contract / finalize, 8 score heads, 9 update, 10 first radial-MLP layer per listed edge (k_edge_hidden).
+ * ddk_profile_read synchronises the device, adds the elapsed milliseconds / launch counts since the last read into
+ * ms[11] / launches[11] and clears the records. */
+#define DDK_PROFILE_CLASSES 11
 int ddk_profile_enable(DdkCtx* ctx, int32_t on);
 int ddk_profile_read(DdkCtx* ctx, double* ms, int64_t* launches);
 

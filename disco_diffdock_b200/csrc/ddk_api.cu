@@ -115,7 +115,7 @@ int ddk_create(const DdkConfig* cfg, const float* weights_h, size_t n_floats, co
     g_create_error = std::string(what) + ": " + cudaGetErrorString(err);
     if (c->w) cudaFree(c->w);
     if (c->w2s) cudaFree(c->w2s);
-    if (c->btab) cudaFree(c->btab);
+    if (c->ltab) cudaFree(c->ltab);
     delete c;
     return DDK_ERR_CUDA;
   };
@@ -164,15 +164,16 @@ int ddk_create(const DdkConfig* cfg, const float* weights_h, size_t n_floats, co
     if ((e = cudaMalloc(&c->w2s, w2s.size() * sizeof(float))) != cudaSuccess) return bail("cudaMalloc(w2s)", e);
     if ((e = cudaMemcpy(c->w2s, w2s.data(), w2s.size() * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess)
       return bail("cudaMemcpy(w2s)", e);
-    std::vector<BasisEnt> all, tab;
-    for (int lv = 0; lv < 4; ++lv) {
-      build_basis_table(lv, tab);
-      c->btab_off[lv] = (int)all.size();
-      all.insert(all.end(), tab.begin(), tab.end());
-    }
-    if ((e = cudaMalloc(&c->btab, all.size() * sizeof(BasisEnt))) != cudaSuccess) return bail("cudaMalloc(btab)", e);
-    if ((e = cudaMemcpy(c->btab, all.data(), all.size() * sizeof(BasisEnt), cudaMemcpyHostToDevice)) != cudaSuccess)
-      return bail("cudaMemcpy(btab)", e);
+    std::vector<LaneTab> tabs(4 * 32);
+    for (int lv = 0; lv < 4; ++lv)
+      if (!build_lane_table(lv, tabs.data() + lv * 32)) {
+        g_create_error = "internal: basis rows of a level are not covered exactly once by the lane table";
+        cudaFree(c->w); cudaFree(c->w2s); delete c;
+        return DDK_ERR_STATE;
+      }
+    if ((e = cudaMalloc(&c->ltab, tabs.size() * sizeof(LaneTab))) != cudaSuccess) return bail("cudaMalloc(ltab)", e);
+    if ((e = cudaMemcpy(c->ltab, tabs.data(), tabs.size() * sizeof(LaneTab), cudaMemcpyHostToDevice)) != cudaSuccess)
+      return bail("cudaMemcpy(ltab)", e);
   }
   *out = c;
   return DDK_OK;
@@ -191,7 +192,7 @@ int ddk_destroy(DdkCtx* c) {
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   if (c->w) cudaFree(c->w);
   if (c->w2s) cudaFree(c->w2s);
-  if (c->btab) cudaFree(c->btab);
+  if (c->ltab) cudaFree(c->ltab);
   delete c;
   return DDK_OK;
 }
@@ -577,6 +578,13 @@ int ddk_host_axis_angle_to_matrix(const float* aa, float* R9_h) {
   if (!aa || !R9_h) return DDK_ERR_INVALID;
   host_axis_angle(aa, R9_h);
   return DDK_OK;
+}
+
+int ddk_host_lane_tables_check(void) {
+  LaneTab tab[32];
+  for (int lv = 0; lv < 4; ++lv)
+    if (!build_lane_table(lv, tab)) return 1 + lv;
+  return 0;
 }
 
 }  // extern "C"

@@ -32,16 +32,20 @@ namespace ddk {
 
 constexpr int F3_NCOMBO_MAX = 4 * NSL_MAX;
 
-enum { F3_BAR_FULL = 1, F3_BAR_EMPTY = 2, F3_BAR_CON = 3, F3_BAR_CON2 = 4 };
+enum { F3_BAR_FULL = 1, F3_BAR_EMPTY = 2, F3_BAR_CON = 3, F3_BAR_CON2 = 4, F3_BAR_PAIR0 = 5 };   // + one per warp pair
 
 __device__ __forceinline__ void f3_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void f3_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-// Basis rows are laid out over (slot, lane) by SOURCE feature so that one shared-memory load feeds several rows:
-//   slots 0..3  (A) : lane -> scalar source x[i] (x0e, at level 3 also the first 8 x0o); row of slot m is x[i] * sh[m]
-//   slots 4,5   (B) : level 3, the other 16 x0o sources: lane = (i & 15, mh); rows x[i] * sh[mh], x[i] * sh[2 + mh]
-//   slot  V0        : levels 2,3: the first 32 rows  x1o/x1e[k][c] * sh[0]
-//   2 generic slots : everything else (dot / cross products and the left-over products), 3-term formula per lane
+// Basis rows are laid out over (slot, lane) by SOURCE feature so that a few shared-memory loads feed many rows and every
+// slot has the same instruction sequence on all lanes (no per-lane harmonic index):
+//   mixed group (4 slots, m = 0..3): a lane is either a SCALAR lane -- source x[i]; row of slot m is x[i] * sh[m] (for a
+//                     vector component x1o/x1e[k][c] only the m = 0 row exists) -- or a VECTOR lane -- source 3-vector v
+//                     (x1o[k] or x1e[k]); slot 0 is the dot product v . s, slots 1..3 the cross product (v x s)_c.
+//                     Slots 0..3 form the first group; level 3 has a second one (slots 4..7).
+//   slot V0         : levels >= 1: rows x1o/x1e[k][c] * sh[0]
+//   generic slot    : level 2 only: the 20 left-over rows, 3-term formula with per-lane indices
+// A segment is accumulated by a PAIR of warps, each owning about half of the slots (half_of).
 template <int LV>
 struct F3Cfg {
   static constexpr int U = AccCfg<LV>::U;
@@ -49,20 +53,27 @@ struct F3Cfg {
   static constexpr int XQ = DINP / 4;
   static constexpr int W = LV == 0 ? 720 : (LV == 1 ? 936 : (LV == 2 ? 1152 : 1872));   // second-layer rows (sum F*O)
   static constexpr int J = f3_J(LV);
-  static constexpr int JQ = J / 4;
   static constexpr int NSLV = HID / J;
   static constexpr int AST = J + 1;          // row stride of an A slot: J hidden units + the sum-of-basis (bias) column
-  static constexpr bool HAS_B = LV == 3, HAS_V0 = LV >= 2;
-  static constexpr int NGEN = LV == 0 ? 0 : 2;
-  static constexpr int SLOT_B = 4, SLOT_V0 = 4 + (HAS_B ? 2 : 0), SLOT_G = SLOT_V0 + (HAS_V0 ? 1 : 0);
-  static constexpr int NSLOT = SLOT_G + NGEN;
+  static constexpr bool G0_VEC = LV == 1 || LV == 2;     // the first mixed group has vector lanes
+  static constexpr bool HAS_M = LV == 3;                 // second mixed group
+  static constexpr bool HAS_V0 = LV >= 1, HAS_G = LV == 2;
+  static constexpr int SLOT_M = 4, SLOT_V0 = HAS_M ? 8 : 4, SLOT_G = 5;
+  static constexpr int NSLOT = LV == 0 ? 4 : (LV == 1 ? 5 : (LV == 2 ? 6 : 9));
+  // half_of(k) = the warp of the pair that owns slot k
+  __host__ __device__ static constexpr int half_of(int k) {
+    if (LV == 0) return k >= 2;                          // A0 A1 | A2 A3
+    if (LV == 1) return (k == 2 || k == 3);              // A0 A1 V0 | A2 A3
+    if (LV == 2) return (k == 2 || k == 3 || k == SLOT_G);   // A0 A1 V0 | A2 A3 G
+    return k >= SLOT_M && k < SLOT_M + 4;                // A0..A3 V0 | M0..M3
+  }
 };
 
 template <int LV>
 struct F3Smem {
   alignas(16) float Wsl[F3Cfg<LV>::W * F3Cfg<LV>::J];        // [class][f][jj][o] of the resident (group, slice)
   alignas(16) float Wb[F3Cfg<LV>::W];                        // packed second-layer bias (used by slice 0 only)
-  alignas(16) float As[F3_ACC][F3Cfg<LV>::U * F3Cfg<LV>::AST];   // one slot per accumulate warp: [u][jj | bsum]
+  alignas(16) float As[F3_ACC][F3Cfg<LV>::U * F3Cfg<LV>::AST];   // one slot per accumulate warp pair: [u][jj | bsum]
   struct Stage {
     alignas(16) float X[2][KC3][F3Cfg<LV>::DINP];
     alignas(16) float SH[2][KC3][4];
@@ -87,7 +98,7 @@ struct F3Args {
   const float4* sh_pool;
   const float* W2S[4];               // [NSLV][W * J]
   const float* b2p[4];               // [W]
-  const BasisEnt* btab;              // [NSLOT * 32]
+  const LaneTab* ltab;               // [32] lane table of the level
   float* part;                       // [2 N][NSLV][84]
   ConSplit split;
   ClassInfo cls[4];
@@ -96,46 +107,49 @@ struct F3Args {
 };
 
 // ---------------------------------------------------------------------------------------------- group work lists
-// Ordered compaction of the non-empty segments of each edge group (block g = group g), node order.
+// Non-empty segments of each edge group (block g = group g), bucketed by their number of 8-edge chunks, longest first:
+// the eight segments a CTA accumulates side by side then take the same number of chunk iterations, and the long
+// segments are claimed first.  The order inside a bucket is whatever the shared-memory cursors hand out; no result
+// depends on it (every (segment, slice) partial is produced by one warp pair in a fixed order).
+constexpr int GL_BUCKETS = 64;
 __global__ void __launch_bounds__(1024) k_build_group_lists(int NL, int NR, const int* __restrict__ seg_cnt,
                                                             const int* __restrict__ seg_base, int4* __restrict__ glist,
                                                             int* __restrict__ gcnt) {
-  __shared__ int wsum[32];
-  __shared__ int base_s;
+  __shared__ int hist[GL_BUCKETS], cursor[GL_BUCKETS];
   const int g = blockIdx.x;
   const int nn = g < 2 ? NL : NR;
   const int off = g == 0 ? 0 : (g == 1 ? NL : (g == 2 ? 2 * NL : 2 * NL + NR));
-  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  if (tid == 0) base_s = 0;
+  const int tid = threadIdx.x;
+  if (tid < GL_BUCKETS) hist[tid] = 0;
   __syncthreads();
-  for (int i0 = 0; i0 < nn; i0 += 1024) {
-    const int i = i0 + tid;
-    int seg = 0, n = 0;
-    if (i < nn) { seg = g < 2 ? 2 * i + g : 2 * (NL + i) + (g - 2); n = seg_cnt[seg]; }
-    const unsigned m = __ballot_sync(0xffffffffu, n > 0);
-    if (lane == 0) wsum[w] = __popc(m);
-    __syncthreads();
-    int o = base_s;
-    for (int q = 0; q < w; ++q) o += wsum[q];
-    if (n > 0) glist[off + o + __popc(m & ((1u << lane) - 1))] = make_int4(seg, n, seg_base[seg], 0);
-    __syncthreads();
-    if (tid == 0) { int t = 0; for (int q = 0; q < 32; ++q) t += wsum[q]; base_s += t; }
-    __syncthreads();
+  for (int i = tid; i < nn; i += 1024) {
+    const int seg = g < 2 ? 2 * i + g : 2 * (NL + i) + (g - 2);
+    const int n = seg_cnt[seg];
+    if (n > 0) atomicAdd(&hist[min(GL_BUCKETS - 1, (n + KC3 - 1) / KC3)], 1);
   }
-  if (tid == 0) gcnt[g] = base_s;
+  __syncthreads();
+  if (tid == 0) {
+    int run = 0;
+    for (int bkt = GL_BUCKETS - 1; bkt >= 0; --bkt) { cursor[bkt] = run; run += hist[bkt]; }
+    gcnt[g] = run;
+  }
+  __syncthreads();
+  for (int i = tid; i < nn; i += 1024) {
+    const int seg = g < 2 ? 2 * i + g : 2 * (NL + i) + (g - 2);
+    const int n = seg_cnt[seg];
+    if (n > 0) {
+      const int o = atomicAdd(&cursor[min(GL_BUCKETS - 1, (n + KC3 - 1) / KC3)], 1);
+      glist[off + o] = make_int4(seg, n, seg_base[seg], 0);
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------- accumulate warps
-template <int LV>
-struct LaneBasis {
-  static constexpr int NG3 = F3Cfg<LV>::NGEN > 0 ? 3 * F3Cfg<LV>::NGEN : 1;
-  int oA;                            // column of the lane's scalar source inside a staged feature row (slots A)
-  int oB;                            // slots B
-  int oV0;                           // slot V0
-  int gx[NG3];                       // generic slots: x term columns
-  int gs[NG3];                       //                harmonic term indices (0..3)
-  float gf[NG3];                     //                coefficients (0, +1, -1)
-  bool mh;                           // lane >> 4 (slots B)
+struct LaneBasis {                   // the part of the LaneTab row a warp keeps in registers
+  int oS0, oV0g, oS1, oV1, oVz;      // scalar / vector source columns of the two mixed groups, source column of slot V0
+  bool vec0, vec1;                   // the lane is a vector lane of group 0 / 1
+  int gx[3], gs[3];                  // generic slot
+  float gf[3];
 };
 
 struct ChunkD {                       // one gather chunk (<= KC3 consecutive list entries of a segment) of an accumulate warp
@@ -159,10 +173,44 @@ __device__ __forceinline__ void f3_unpack2(const f32x2 v, float& x, float& y) {
   asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v));
 }
 
-// one edge: the J hidden units of the slice (as J / 2 packed pairs) against every basis row of the lane
-template <int LV, bool BIAS>
+// basis values of one mixed group (slots K0..K0+3) restricted to the slots of this half
+template <int LV, int HALF, int K0, bool HASVEC>
+__device__ __forceinline__ void f3_mixed(float (&b)[F3Cfg<LV>::NSLOT], const float* __restrict__ xrow, const float4 s4,
+                                         const int oS, const int oV, const bool isvec) {
+  using Cfg = F3Cfg<LV>;
+  constexpr bool n0 = Cfg::half_of(K0) == HALF, n1 = Cfg::half_of(K0 + 1) == HALF, n2 = Cfg::half_of(K0 + 2) == HALF,
+                 n3 = Cfg::half_of(K0 + 3) == HALF;
+  if (!(n0 || n1 || n2 || n3)) return;
+  const float xs = xrow[oS];
+  float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+  if (HASVEC) { v0 = xrow[oV]; v1 = xrow[oV + 1]; v2 = xrow[oV + 2]; }
+  if (n0) {
+    float t = xs * s4.x;
+    if (HASVEC) { float d = v0 * s4.y; d = fmaf(v1, s4.z, d); d = fmaf(v2, s4.w, d); t = isvec ? d : t; }
+    b[K0] = t;
+  }
+  if (n1) {
+    float t = xs * s4.y;
+    if (HASVEC) { const float c = fmaf(v1, s4.w, -(v2 * s4.z)); t = isvec ? c : t; }
+    b[K0 + 1] = t;
+  }
+  if (n2) {
+    float t = xs * s4.z;
+    if (HASVEC) { const float c = fmaf(v2, s4.y, -(v0 * s4.w)); t = isvec ? c : t; }
+    b[K0 + 2] = t;
+  }
+  if (n3) {
+    float t = xs * s4.w;
+    if (HASVEC) { const float c = fmaf(v0, s4.z, -(v1 * s4.y)); t = isvec ? c : t; }
+    b[K0 + 3] = t;
+  }
+}
+
+// one edge: the J hidden units of the slice (as J / 2 packed pairs) against the basis rows of the lane that belong to
+// this warp's half of the slots
+template <int LV, bool BIAS, int HALF>
 __device__ __forceinline__ void f3_edge(f32x2 (&acc)[F3Cfg<LV>::NSLOT][F3Cfg<LV>::J / 2], float (&bs)[F3Cfg<LV>::NSLOT],
-                                        const LaneBasis<LV>& LB, const float* __restrict__ hrow,
+                                        const LaneBasis& LB, const float* __restrict__ hrow,
                                         const float* __restrict__ shrow, const float* __restrict__ xrow) {
   using Cfg = F3Cfg<LV>;
   constexpr int J = Cfg::J, NSLOT = Cfg::NSLOT;
@@ -170,25 +218,20 @@ __device__ __forceinline__ void f3_edge(f32x2 (&acc)[F3Cfg<LV>::NSLOT][F3Cfg<LV>
   float b[NSLOT];
   {
     const float4 s4 = *reinterpret_cast<const float4*>(shrow);
-    const float xa = xrow[LB.oA];
-    b[0] = xa * s4.x; b[1] = xa * s4.y; b[2] = xa * s4.z; b[3] = xa * s4.w;
-    if (Cfg::HAS_B) {
-      const float xb = xrow[LB.oB];
-      b[Cfg::SLOT_B] = xb * (LB.mh ? s4.y : s4.x);
-      b[Cfg::SLOT_B + 1] = xb * (LB.mh ? s4.w : s4.z);
-    }
-    if (Cfg::HAS_V0) b[Cfg::SLOT_V0] = xrow[LB.oV0] * s4.x;
-#pragma unroll
-    for (int q = 0; q < Cfg::NGEN; ++q) {
-      float v = LB.gf[3 * q] * (xrow[LB.gx[3 * q]] * shrow[LB.gs[3 * q]]);
-      v += LB.gf[3 * q + 1] * (xrow[LB.gx[3 * q + 1]] * shrow[LB.gs[3 * q + 1]]);
-      v += LB.gf[3 * q + 2] * (xrow[LB.gx[3 * q + 2]] * shrow[LB.gs[3 * q + 2]]);
-      b[Cfg::SLOT_G + q] = v;
+    f3_mixed<LV, HALF, 0, Cfg::G0_VEC>(b, xrow, s4, LB.oS0, LB.oV0g, LB.vec0);
+    if (Cfg::HAS_M) f3_mixed<LV, HALF, Cfg::SLOT_M, true>(b, xrow, s4, LB.oS1, LB.oV1, LB.vec1);
+    if (Cfg::HAS_V0 && Cfg::half_of(Cfg::SLOT_V0) == HALF) b[Cfg::SLOT_V0] = xrow[LB.oVz] * s4.x;
+    if (Cfg::HAS_G && Cfg::half_of(Cfg::SLOT_G) == HALF) {
+      float v = LB.gf[0] * (xrow[LB.gx[0]] * shrow[LB.gs[0]]);
+      v += LB.gf[1] * (xrow[LB.gx[1]] * shrow[LB.gs[1]]);
+      v += LB.gf[2] * (xrow[LB.gx[2]] * shrow[LB.gs[2]]);
+      b[Cfg::SLOT_G] = v;
     }
   }
   if (BIAS) {
 #pragma unroll
-    for (int k = 0; k < NSLOT; ++k) bs[k] += b[k];
+    for (int k = 0; k < NSLOT; ++k)
+      if (Cfg::half_of(k) == HALF) bs[k] += b[k];
   }
   f32x2 h[J / 2];
 #pragma unroll
@@ -197,24 +240,28 @@ __device__ __forceinline__ void f3_edge(f32x2 (&acc)[F3Cfg<LV>::NSLOT][F3Cfg<LV>
     h[2 * q] = f3_pack2(v.x, v.y); h[2 * q + 1] = f3_pack2(v.z, v.w);
   }
 #pragma unroll
-  for (int k = 0; k < NSLOT; ++k) {
-    const f32x2 bb = f3_pack2(b[k], b[k]);
+  for (int k = 0; k < NSLOT; ++k)
+    if (Cfg::half_of(k) == HALF) {
+      const f32x2 bb = f3_pack2(b[k], b[k]);
 #pragma unroll
-    for (int j = 0; j < J / 2; ++j) f3_ffma2(acc[k][j], bb, h[j]);
-  }
+      for (int j = 0; j < J / 2; ++j) f3_ffma2(acc[k][j], bb, h[j]);
+    }
 }
 
-template <int LV, bool BIAS>
-__device__ __forceinline__ void f3_acc_task(const F3Args& p, F3Smem<LV>& S, LaneBasis<LV>& LB, const int g, const int r,
-                                            const int idx0, const int nseg, const int w, const int lane) {
+// One warp of the pair `pr` (HALF = 0 / 1).  Both warps run the same chunk sequence in lockstep: the pair's stage is
+// gathered cooperatively (cp.async, one chunk ahead) and handed over with one 64-thread named barrier per chunk.
+template <int LV, bool BIAS, int HALF>
+__device__ __forceinline__ void f3_acc_task(const F3Args& p, F3Smem<LV>& S, const LaneBasis& LB, const int g, const int r,
+                                            const int idx0, const int nseg, const int pr, const int lane) {
   using Cfg = F3Cfg<LV>;
   constexpr int NSLOT = Cfg::NSLOT, DINP = Cfg::DINP, J = Cfg::J, AST = Cfg::AST, XQ = Cfg::XQ;
   constexpr int XBUF = KC3 * DINP, SBUF = KC3 * 4, HBUF = KC3 * J;
-  typename F3Smem<LV>::Stage& T = S.st[w];
+  typename F3Smem<LV>::Stage& T = S.st[pr];
   const int nb = (nseg + F3_ACC - 1) / F3_ACC;
   const int4* wl = p.glist + p.goff[g] + idx0;
   const float* hsr = p.hs + (size_t)r * p.LT * J;   // slice r of the hidden units, list order
-  const int ge = lane & 7, gsub = lane >> 3;        // gather role of the lane: edge, 16-byte sub-piece
+  const int pl = HALF * 32 + lane;                  // thread of the pair
+  const int ge = pl & 7, gsub = pl >> 3;            // gather role: edge, 16-byte sub-piece (0..7)
 
   f32x2 acc[NSLOT][J / 2];
   float bs[NSLOT];
@@ -225,18 +272,18 @@ __device__ __forceinline__ void f3_acc_task(const F3Args& p, F3Smem<LV>& S, Lane
     for (int j = 0; j < J / 2; ++j) acc[k][j] = 0ull;
   }
 
-  // ---- chunk generator: batches bi = 0..nb-1, this warp's segment of a batch is idx0 + 8 bi + w (or none)
+  // ---- chunk generator: batches bi = 0..nb-1, this pair's segment of a batch is idx0 + 8 bi + pr (or none)
   int bi = 0, n = 0, sbase = 0, seg = 0, c0 = 0;
   bool in_seg = false;
-  int4 pre = (w < nseg) ? wl[w] : make_int4(-1, 0, 0, 0);
+  int4 pre = (pr < nseg) ? wl[pr] : make_int4(-1, 0, 0, 0);
   auto next_cd = [&]() {
     ChunkD d;
     d.pos = 0; d.kc = 0; d.seg = -1;
     d.flags = CD_LAST | (bi > 0 ? CD_NOT_FIRST_BATCH : 0);
     if (!in_seg) {
       if (bi >= nb) { d.flags = CD_DONE; return d; }
-      const int si = F3_ACC * bi + w;
-      if (si >= nseg) { ++bi; return d; }           // no segment for this warp in the batch: empty slot
+      const int si = F3_ACC * bi + pr;
+      if (si >= nseg) { ++bi; return d; }           // no segment for this pair in the batch: empty slot
       seg = pre.x; n = pre.y; sbase = pre.z; c0 = 0; in_seg = true;
       const int sn = si + F3_ACC;
       pre = (sn < nseg) ? wl[sn] : make_int4(-1, 0, 0, 0);
@@ -254,8 +301,8 @@ __device__ __forceinline__ void f3_acc_task(const F3Args& p, F3Smem<LV>& S, Lane
     if (lane < d.kc) e = p.seg_list[d.pos + lane];
     return e;
   };
-  // every lane copies fixed 16-byte pieces (q = gsub + 4 i) of the destination features of its edge ge (two shuffles per
-  // chunk, immediate offsets); the chunk's hidden-unit slice is one contiguous block of kc * J floats
+  // the 64 threads of the pair copy fixed 16-byte pieces (q = gsub + 8 i) of the destination features of edge ge; the
+  // chunk's hidden-unit slice is one contiguous block of kc * J floats (copied by the second warp)
   auto gather = [&](const ChunkD& d, const int2 ent, const int buf) {
     if (d.kc > 0) {
       const int slot = __shfl_sync(0xffffffffu, ent.x, ge);
@@ -264,11 +311,11 @@ __device__ __forceinline__ void f3_acc_task(const F3Args& p, F3Smem<LV>& S, Lane
         const float* xs = p.x + (size_t)dst * D + 4 * gsub;
         float* xd = &T.X[buf][ge][4 * gsub];
 #pragma unroll
-        for (int i = 0; i < (XQ + 3) / 4; ++i)
-          if (gsub + 4 * i < XQ) f3_cp16(xd + 16 * i, xs + 16 * i);
+        for (int i = 0; i < (XQ + 7) / 8; ++i)
+          if (gsub + 8 * i < XQ) f3_cp16(xd + 32 * i, xs + 32 * i);
         if (gsub == 0) f3_cp16(&T.SH[buf][ge][0], p.sh_pool + slot);
       }
-      if (lane < d.kc * (J / 4))
+      if (HALF == 1 && lane < d.kc * (J / 4))
         f3_cp16(&T.H[buf][0][0] + 4 * lane, hsr + (size_t)d.pos * J + 4 * lane);
     }
     __pipeline_commit();
@@ -285,8 +332,8 @@ __device__ __forceinline__ void f3_acc_task(const F3Args& p, F3Smem<LV>& S, Lane
   int buf = 0;
   while (!(cd0.flags & CD_DONE)) {
     __pipeline_wait_prior(0);
-    __syncwarp();
-    // ---- next chunk's gathers travel while this chunk is accumulated (the other buffer was consumed last iteration)
+    f3_bar_sync(F3_BAR_PAIR0 + pr, 64);             // both halves of chunk cd0 have landed; buf ^ 1 is consumed
+    // ---- next chunk's gathers travel while this chunk is accumulated
     gather(cd1, ent1, buf ^ 1);
     ChunkD cd2 = (cd1.flags & CD_DONE) ? cd1 : next_cd();
     const int2 ent2 = load_ent(cd2);
@@ -297,35 +344,36 @@ __device__ __forceinline__ void f3_acc_task(const F3Args& p, F3Smem<LV>& S, Lane
       const float* xb = &T.X[0][0][0] + buf * XBUF;
       if (cd0.kc == KC3) {
 #pragma unroll
-        for (int e = 0; e < KC3; ++e) f3_edge<LV, BIAS>(acc, bs, LB, hb + e * J, sb + e * 4, xb + e * DINP);
+        for (int e = 0; e < KC3; ++e) f3_edge<LV, BIAS, HALF>(acc, bs, LB, hb + e * J, sb + e * 4, xb + e * DINP);
       } else {
 #pragma unroll 1
-        for (int e = 0; e < cd0.kc; ++e) f3_edge<LV, BIAS>(acc, bs, LB, hb + e * J, sb + e * 4, xb + e * DINP);
+        for (int e = 0; e < cd0.kc; ++e) f3_edge<LV, BIAS, HALF>(acc, bs, LB, hb + e * J, sb + e * 4, xb + e * DINP);
       }
     }
     if (cd0.flags & CD_LAST) {
       // ---- hand the finished U x J block to the contraction warps
       if (cd0.flags & CD_NOT_FIRST_BATCH) f3_bar_sync(F3_BAR_EMPTY, F3_THREADS);   // they are done with the previous batch
       if (cd0.flags & CD_VALID) {
-        float* slot = &S.As[w][0];
+        float* slot = &S.As[pr][0];
 #pragma unroll
-        for (int k = 0; k < NSLOT; ++k) {
-          const int u = p.btab[k * 32 + lane].u;
-          if (u >= 0) {
+        for (int k = 0; k < NSLOT; ++k)
+          if (Cfg::half_of(k) == HALF) {
+            const int u = p.ltab[lane].u[k];
+            if (u >= 0) {
 #pragma unroll
-            for (int j = 0; j < J / 2; ++j) {
-              float v0, v1;
-              f3_unpack2(acc[k][j], v0, v1);
-              slot[u * AST + 2 * j] = v0; slot[u * AST + 2 * j + 1] = v1;
+              for (int j = 0; j < J / 2; ++j) {
+                float v0, v1;
+                f3_unpack2(acc[k][j], v0, v1);
+                slot[u * AST + 2 * j] = v0; slot[u * AST + 2 * j + 1] = v1;
+              }
+              if (BIAS) slot[u * AST + J] = bs[k];
             }
-            if (BIAS) slot[u * AST + J] = bs[k];
-          }
-          bs[k] = 0.f;
+            bs[k] = 0.f;
 #pragma unroll
-          for (int j = 0; j < J / 2; ++j) acc[k][j] = 0ull;
-        }
+            for (int j = 0; j < J / 2; ++j) acc[k][j] = 0ull;
+          }
       }
-      if (lane == 0) S.meta[w] = cd0.seg;
+      if (HALF == 0 && lane == 0) S.meta[pr] = cd0.seg;
       __threadfence_block();
       f3_bar_arrive(F3_BAR_FULL, F3_THREADS);
     }
@@ -477,21 +525,17 @@ __global__ void __launch_bounds__(F3_THREADS, 1) k_conv_fused(const __grid_const
   extern __shared__ __align__(16) unsigned char smem_raw[];
   F3Smem<LV>& S = *reinterpret_cast<F3Smem<LV>*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const bool is_acc = w < F3_ACC;
+  const bool is_acc = w < 2 * F3_ACC;
+  const int pr = w >> 1, half = w & 1;
 
-  LaneBasis<LV> LB;
-  if (is_acc) {
-    LB.oA = p.btab[lane].ia;
-    LB.oB = Cfg::HAS_B ? p.btab[Cfg::SLOT_B * 32 + lane].ia : 0;
-    LB.oV0 = Cfg::HAS_V0 ? p.btab[Cfg::SLOT_V0 * 32 + lane].ia : 0;
-    LB.mh = (lane & 16) != 0;
+  LaneBasis LB;
+  {
+    const LaneTab& lt = p.ltab[lane];
+    LB.oS0 = lt.oS[0]; LB.oV0g = lt.oV[0]; LB.vec0 = lt.isvec[0] != 0;
+    LB.oS1 = lt.oS[1]; LB.oV1 = lt.oV[1]; LB.vec1 = lt.isvec[1] != 0;
+    LB.oVz = lt.oV0;
 #pragma unroll
-    for (int q = 0; q < Cfg::NGEN; ++q) {
-      const BasisEnt be = p.btab[(Cfg::SLOT_G + q) * 32 + lane];
-      LB.gx[3 * q] = be.ia; LB.gx[3 * q + 1] = be.ib; LB.gx[3 * q + 2] = be.ic;
-      LB.gs[3 * q] = be.ma; LB.gs[3 * q + 1] = be.mb; LB.gs[3 * q + 2] = be.mc;
-      LB.gf[3 * q] = be.fa; LB.gf[3 * q + 1] = be.fb; LB.gf[3 * q + 2] = be.fc;
-    }
+    for (int k = 0; k < 3; ++k) { LB.gx[k] = lt.gi[k]; LB.gs[k] = lt.gm[k]; LB.gf[k] = lt.gf[k]; }
   }
   if (tid == 0) { S.task[5] = blockIdx.x % NCOMBO; S.task[6] = -1; }
   __syncthreads();
@@ -531,11 +575,16 @@ __global__ void __launch_bounds__(F3_THREADS, 1) k_conv_fused(const __grid_const
       __syncthreads();
     }
     if (is_acc) {
-      if (r == 0) f3_acc_task<LV, true>(p, S, LB, g, r, idx0, nseg, w, lane);
-      else f3_acc_task<LV, false>(p, S, LB, g, r, idx0, nseg, w, lane);
+      if (half == 0) {
+        if (r == 0) f3_acc_task<LV, true, 0>(p, S, LB, g, r, idx0, nseg, pr, lane);
+        else f3_acc_task<LV, false, 0>(p, S, LB, g, r, idx0, nseg, pr, lane);
+      } else {
+        if (r == 0) f3_acc_task<LV, true, 1>(p, S, LB, g, r, idx0, nseg, pr, lane);
+        else f3_acc_task<LV, false, 1>(p, S, LB, g, r, idx0, nseg, pr, lane);
+      }
     } else {
-      if (r == 0) f3_con_task<LV, true>(p, S, r, nseg, w - F3_ACC, lane);
-      else f3_con_task<LV, false>(p, S, r, nseg, w - F3_ACC, lane);
+      if (r == 0) f3_con_task<LV, true>(p, S, r, nseg, w - 2 * F3_ACC, lane);
+      else f3_con_task<LV, false>(p, S, r, nseg, w - 2 * F3_ACC, lane);
     }
     __syncthreads();
   }
@@ -606,57 +655,89 @@ static void basis_desc_host(int lv, int u, int& type, int& i0, int& m) {
   if (u < 6) { type = 1; i0 = X1E + 3 * u; } else { type = 0; i0 = X0O + (u - 6); m = 0; }
 }
 
-// (slot, lane) -> basis row, by source feature (see F3Cfg); idle lanes get u = -1.
-void build_basis_table(int lv, std::vector<BasisEnt>& tab) {
+// lane -> (rows, sources) of a basis level, see F3Cfg.  Returns false unless every row is owned exactly once.
+bool build_lane_table(int lv, LaneTab* tab) {
   const int U = lv == 0 ? 96 : (lv == 1 ? 138 : (lv == 2 ? 180 : 276));
-  const bool hasB = lv == 3, hasV0 = lv >= 2;
-  const int ngen = lv == 0 ? 0 : 2;
-  const int slotB = 4, slotV0 = 4 + (hasB ? 2 : 0), slotG = slotV0 + (hasV0 ? 1 : 0), nslot = slotG + ngen;
-  std::vector<int> t0row(84 * 4, -1);
-  std::vector<char> used(U, 0);
+  const int nslot = lv == 0 ? 4 : (lv == 1 ? 5 : (lv == 2 ? 6 : 9));
+  const int slotV0 = lv == 3 ? 8 : 4, slotG = 5;
+  std::vector<int> t0row(84 * 4, -1), dotrow(84, -1), crossrow(84 * 3, -1);
   for (int u = 0; u < U; ++u) {
     int ty, i0, m;
     basis_desc_host(lv, u, ty, i0, m);
     if (ty == 0) t0row[i0 * 4 + m] = u;
+    else if (ty == 1) dotrow[i0] = u;
+    else crossrow[i0 * 3 + (m - 1)] = u;
   }
-  tab.assign((size_t)nslot * 32, BasisEnt{-1, 0, 0, 0, 0, 0, 0, 0.f, 0.f, 0.f});
-  auto put_t0 = [&](int slot, int lane, int i0, int m) {
-    const int u = t0row[i0 * 4 + m];
-    tab[(size_t)slot * 32 + lane] = BasisEnt{u, i0, i0, i0, m, 0, 0, 1.f, 0.f, 0.f};
-    if (u >= 0) used[u] = 1;
+  for (int l = 0; l < 32; ++l) {
+    LaneTab& t = tab[l];
+    for (int k = 0; k < F3_MAXSLOT; ++k) t.u[k] = -1;
+    for (int q = 0; q < 2; ++q) { t.oS[q] = 0; t.oV[q] = 0; t.isvec[q] = 0; }
+    t.oV0 = 0;
+    for (int k = 0; k < 3; ++k) { t.gi[k] = 0; t.gm[k] = 0; t.gf[k] = 0.f; }
+  }
+  std::vector<int> used(U, 0);
+  auto own = [&](int lane, int slot, int u) { if (u >= 0) { tab[lane].u[slot] = u; used[u]++; } };
+  auto scalar_lane = [&](int grp, int lane, int i) {
+    tab[lane].oS[grp] = i; tab[lane].isvec[grp] = 0;
+    for (int m = 0; m < 4; ++m) own(lane, 4 * grp + m, t0row[i * 4 + m]);
   };
-  std::vector<int> ssrc, vsrc;
-  for (int i = 0; i < 24; ++i) ssrc.push_back(i);                       // x0e
-  if (lv == 3) for (int i = 0; i < 24; ++i) ssrc.push_back(60 + i);     // x0o
-  if (lv >= 1) for (int i = 24; i < 42; ++i) vsrc.push_back(i);         // x1o[k][c]
-  if (lv >= 2) for (int i = 42; i < 60; ++i) vsrc.push_back(i);         // x1e[k][c]
-  for (int l = 0; l < 32 && l < (int)ssrc.size(); ++l)
-    for (int m = 0; m < 4; ++m) put_t0(m, l, ssrc[l], m);
-  if (hasB)
-    for (int l = 0; l < 32; ++l) {
-      const int src = ssrc[32 + (l & 15)], mh = l >> 4;
-      put_t0(slotB, l, src, mh);
-      put_t0(slotB + 1, l, src, 2 + mh);
-    }
-  if (hasV0)
-    for (int l = 0; l < 32; ++l) put_t0(slotV0, l, vsrc[l], 0);
-  int q = 0;
-  for (int u = 0; u < U; ++u) {
-    if (used[u]) continue;
-    int ty, i0, m;
-    basis_desc_host(lv, u, ty, i0, m);
-    BasisEnt e{u, i0, i0, i0, m, 0, 0, 1.f, 0.f, 0.f};
-    if (ty == 1) { e.ia = i0; e.ib = i0 + 1; e.ic = i0 + 2; e.ma = 1; e.mb = 2; e.mc = 3; e.fa = e.fb = e.fc = 1.f; }
-    if (ty == 2) {
-      const int c = m - 1, c1 = (c + 1) % 3, c2 = (c + 2) % 3;
-      e.ia = i0 + c1; e.ma = 1 + c2; e.fa = 1.f;
-      e.ib = i0 + c2; e.mb = 1 + c1; e.fb = -1.f;
-      e.ic = e.ia; e.mc = 0; e.fc = 0.f;
-    }
-    if (q < ngen * 32) tab[(size_t)(slotG + q / 32) * 32 + q % 32] = e;
-    ++q;
+  auto vector_lane = [&](int grp, int lane, int i0) {
+    tab[lane].oV[grp] = i0; tab[lane].isvec[grp] = 1;
+    own(lane, 4 * grp, dotrow[i0]);
+    for (int c = 0; c < 3; ++c) own(lane, 4 * grp + 1 + c, crossrow[i0 * 3 + c]);
+  };
+  std::vector<int> vecs, vrows;                    // 3-vector sources (first column), vector components (x * sh[0] rows)
+  if (lv >= 1) for (int k = 0; k < 6; ++k) vecs.push_back(24 + 3 * k);
+  if (lv >= 2) for (int k = 0; k < 6; ++k) vecs.push_back(42 + 3 * k);
+  if (lv >= 1) for (int i = 24; i < (lv >= 2 ? 60 : 42); ++i) vrows.push_back(i);
+  for (int l = 0; l < 24; ++l) scalar_lane(0, l, l);                       // x0e
+  size_t nv = 0, nr = 0;
+  if (lv == 1 || lv == 2)
+    for (int l = 24; l < 32 && nv < vecs.size(); ++l) vector_lane(0, l, vecs[nv++]);
+  if (lv == 3) {
+    for (int l = 24; l < 32; ++l) scalar_lane(0, l, 60 + (l - 24));         // x0o 0..7
+    for (int l = 0; l < 12; ++l) vector_lane(1, l, vecs[nv++]);
+    for (int l = 12; l < 28; ++l) scalar_lane(1, l, 68 + (l - 12));         // x0o 8..23
   }
-  if (q > ngen * 32) tab.clear();     // cannot happen for lv 0..3 (checked by ddk_create)
+  if (lv >= 1)
+    for (int l = 0; l < 32 && nr < vrows.size(); ++l) {
+      const int i = vrows[nr++];
+      tab[l].oV0 = i;
+      own(l, slotV0, t0row[i * 4]);
+    }
+  if (lv == 3)
+    for (int l = 28; l < 32 && nr < vrows.size(); ++l) scalar_lane(1, l, vrows[nr++]);   // only their m = 0 rows exist
+  if (lv == 2) {
+    int l = 0;
+    for (; nr < vrows.size(); ++nr, ++l) {
+      const int i = vrows[nr];
+      tab[l].gi[0] = tab[l].gi[1] = tab[l].gi[2] = i; tab[l].gm[0] = 0; tab[l].gf[0] = 1.f;
+      own(l, slotG, t0row[i * 4]);
+    }
+    for (; nv < vecs.size(); ++nv) {
+      const int i0 = vecs[nv];
+      if (dotrow[i0] >= 0) {
+        if (l >= 32) return false;
+        for (int k = 0; k < 3; ++k) { tab[l].gi[k] = i0 + k; tab[l].gm[k] = 1 + k; tab[l].gf[k] = 1.f; }
+        own(l++, slotG, dotrow[i0]);
+      }
+      for (int c = 0; c < 3; ++c, ++l) {
+        if (l >= 32) return false;
+        const int c1 = (c + 1) % 3, c2 = (c + 2) % 3;
+        tab[l].gi[0] = i0 + c1; tab[l].gm[0] = 1 + c2; tab[l].gf[0] = 1.f;
+        tab[l].gi[1] = i0 + c2; tab[l].gm[1] = 1 + c1; tab[l].gf[1] = -1.f;
+        tab[l].gi[2] = i0; tab[l].gm[2] = 0; tab[l].gf[2] = 0.f;
+        own(l, slotG, crossrow[i0 * 3 + c]);
+      }
+    }
+  }
+  if (nv != vecs.size() || nr != vrows.size()) return false;
+  for (int u = 0; u < U; ++u)
+    if (used[u] != 1) return false;
+  for (int l = 0; l < 32; ++l)
+    for (int k = nslot; k < F3_MAXSLOT; ++k)
+      if (tab[l].u[k] >= 0) return false;
+  return true;
 }
 
 // contiguous, cost-balanced split of the (class, f) rows of a layer over the contraction warps
@@ -720,7 +801,7 @@ void launch_conv_fused(DdkCtx* c, int layer, const float* x_in, float* x_out, cu
     a.W2S[g] = c->w2s + c->w2s_off[layer * 4 + g];
     a.b2p[g] = W(c, conv_id(layer, DDK_WL_B2P + g));
   }
-  a.btab = c->btab + c->btab_off[li.lv];
+  a.ltab = c->ltab + li.lv * 32;
   a.part = ptr<float>(c->b_part);
   a.split = c->con_split[layer];
   a.ncls = li.ncls;

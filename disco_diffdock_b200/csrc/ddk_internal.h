@@ -55,15 +55,19 @@ struct Buf {
 constexpr int NSL_MAX = 9;          // most slices of any level (72 / 8)
 __host__ __device__ constexpr int f3_J(int lv) { return lv == 1 ? 12 : (lv == 0 ? 12 : 8); }   // hidden units per slice
 __host__ __device__ constexpr int f3_nsl(int lv) { return HID / f3_J(lv); }
-constexpr int F3_ACC = 8;           // accumulate warps per CTA (= segments per contraction batch)
+constexpr int F3_ACC = 8;           // accumulate warp PAIRS per CTA (= segments per contraction batch)
 constexpr int F3_CON = 4;           // contraction warps per CTA
-constexpr int F3_THREADS = (F3_ACC + F3_CON) * 32;
+constexpr int F3_THREADS = (2 * F3_ACC + F3_CON) * 32;
 constexpr int KC3 = 8;              // edges per gather chunk of one accumulate warp
 
-struct BasisEnt {                   // basis row evaluated by one (slot, lane): fa x[ia] sh[ma] + fb x[ib] sh[mb] + fc x[ic] sh[mc]
-  int u;                            // row of the A block (kernel order of ddk_conv.cuh), -1 = idle lane
-  int ia, ib, ic, ma, mb, mc;
-  float fa, fb, fc;
+constexpr int F3_MAXSLOT = 9;
+struct LaneTab {                    // what one lane of an accumulate warp evaluates at a basis level (k_conv_fused)
+  int u[F3_MAXSLOT];                // row of the A block (kernel order of ddk_conv.cuh) owned in each slot, -1 = none
+  int oS[2], oV[2], isvec[2];       // mixed slot groups (slots 0..3; 4..7 at level 3): column of the scalar source, first
+                                    // column of the 3-vector source, and which of the two the lane evaluates
+  int oV0;                          // slot V0: column of the source (x * sh[0])
+  int gi[3], gm[3];                 // generic slot (level 2): fa x[ia] sh[ma] + fb x[ib] sh[mb] + fc x[ic] sh[mc]
+  float gf[3];
 };
 
 struct ConSplit {                   // rows [f0, f1) of each irrep class handled by each contraction warp
@@ -121,8 +125,7 @@ struct DdkCtx {
   int sm_count = 148;
   float* w2s = nullptr;               // second-layer weights re-sliced per hidden-unit slice: [layer][group][72 / J][W * J]
   std::vector<int64_t> w2s_off;       // [layer * 4 + group] (floats)
-  ddk::BasisEnt* btab = nullptr;      // per basis level the (slot, lane) -> basis row tables
-  int btab_off[4] = {0, 0, 0, 0};
+  ddk::LaneTab* ltab = nullptr;       // [4 basis levels][32 lanes]: lane -> basis rows / sources of the fused conv kernel
   std::vector<ddk::ConSplit> con_split;   // per layer
   ddk::Buf b_glist, b_gcnt, b_counters, b_part;
   ddk::Buf b_hs;                      // [72 / J][list_total][J]: hidden units of every listed edge of the current layer
@@ -162,7 +165,7 @@ struct LaunchScope {
 
 cudaError_t conv_configure();
 cudaError_t conv3_configure();
-void build_basis_table(int lv, std::vector<BasisEnt>& tab);
+bool build_lane_table(int lv, LaneTab* tab32);
 void build_con_split(const LayerInfo& li, ConSplit& sp);
 void launch_build_group_lists(DdkCtx* c, cudaStream_t st);
 void launch_conv_fused(DdkCtx* c, int layer, const float* x_in, float* x_out, cudaStream_t st);

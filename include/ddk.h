@@ -198,6 +198,11 @@ int ddk_profile_read(DdkCtx* ctx, double* ms, int64_t* launches);
 int ddk_host_kabsch(const float* a_h, const float* b_h, int32_t n, float* R9_h, float* t3_h);
 int ddk_host_axis_angle_to_matrix(const float* axis_angle3_h, float* R9_h);
 
+/* Host-side self check of the fused conv kernel's lane tables (callable without a GPU): for basis level 0..3 every row of
+ * the FasterTensorProduct basis (models/tensor_layers.py:65-116) must be owned by exactly one (slot, lane).  Returns 0 if
+ * all four levels are covered, otherwise 1 + the first failing level. */
+int ddk_host_lane_tables_check(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -95,3 +95,9 @@ def test_host_axis_angle_matches_oracle(lib):
         R = np.zeros(9, np.float32)
         assert lib.ddk_host_axis_angle_to_matrix(v.ctypes.data, R.ctypes.data) == 0
         assert np.abs(R.reshape(3, 3) - ref[i].numpy()).max() < 1e-6
+
+
+def test_lane_tables_cover_every_basis_row(lib):
+    """k_conv_fused: every FasterTensorProduct basis row of every level is owned by exactly one (slot, lane)."""
+    lib.ddk_host_lane_tables_check.restype = ctypes.c_int
+    assert lib.ddk_host_lane_tables_check() == 0

@@ -32,10 +32,29 @@ namespace ddk {
 
 constexpr int F3_NCOMBO_MAX = 4 * NSL_MAX;
 
-enum { F3_BAR_FULL = 1, F3_BAR_EMPTY = 2, F3_BAR_CON = 3, F3_BAR_CON2 = 4, F3_BAR_PAIR0 = 5 };   // + one per warp pair
+enum { F3_BAR_CON = 1, F3_BAR_CON2 = 2, F3_BAR_PAIR0 = 3 };   // named barriers; + one per warp pair
 
 __device__ __forceinline__ void f3_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-__device__ __forceinline__ void f3_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+// mbarriers between the accumulate warps and the contraction warps: FULL (one arrival per accumulate warp and batch) and
+// EMPTY (one arrival per contraction warp and batch).  Unlike a named barrier an accumulate pair only waits for the
+// contraction warps, never for the other pairs.
+__device__ __forceinline__ unsigned f3_smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void f3_mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared.b64 [%0], %1;" ::"r"(f3_smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void f3_mbar_arrive(unsigned long long* bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared.b64 st, [%0];\n\t}" ::"r"(f3_smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void f3_mbar_wait(unsigned long long* bar, int parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared.b64 p, [%0], %1;\n\t"
+      "@p bra.uni DONE_%=;\n\t"
+      "bra.uni WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(f3_smem_addr(bar)), "r"(parity) : "memory");
+}
 
 // Basis rows are laid out over (slot, lane) by SOURCE feature so that a few shared-memory loads feed many rows and every
 // slot has the same instruction sequence on all lanes (no per-lane harmonic index):
@@ -80,6 +99,7 @@ struct F3Smem {
     alignas(16) float H[2][KC3][F3Cfg<LV>::J];
   } st[F3_ACC];
   alignas(16) float tile[F3_CON][F3_ACC][D];                 // per contraction warp partial outputs of a batch
+  alignas(8) unsigned long long bar_full, bar_empty;         // mbarriers, see f3_mbar_*
   int meta[F3_ACC];                                          // segment id of each slot of the batch in flight (-1: none)
   int task[8];                                               // g, r, idx0, nseg, reload, combo cursor, resident combo
 };
@@ -252,7 +272,7 @@ __device__ __forceinline__ void f3_edge(f32x2 (&acc)[F3Cfg<LV>::NSLOT][F3Cfg<LV>
 // gathered cooperatively (cp.async, one chunk ahead) and handed over with one 64-thread named barrier per chunk.
 template <int LV, bool BIAS, int HALF>
 __device__ __forceinline__ void f3_acc_task(const F3Args& p, F3Smem<LV>& S, const LaneBasis& LB, const int g, const int r,
-                                            const int idx0, const int nseg, const int pr, const int lane) {
+                                            const int idx0, const int nseg, const int pr, const int lane, int& nflush) {
   using Cfg = F3Cfg<LV>;
   constexpr int NSLOT = Cfg::NSLOT, DINP = Cfg::DINP, J = Cfg::J, AST = Cfg::AST, XQ = Cfg::XQ;
   constexpr int XBUF = KC3 * DINP, SBUF = KC3 * 4, HBUF = KC3 * J;
@@ -352,7 +372,7 @@ __device__ __forceinline__ void f3_acc_task(const F3Args& p, F3Smem<LV>& S, cons
     }
     if (cd0.flags & CD_LAST) {
       // ---- hand the finished U x J block to the contraction warps
-      if (cd0.flags & CD_NOT_FIRST_BATCH) f3_bar_sync(F3_BAR_EMPTY, F3_THREADS);   // they are done with the previous batch
+      if (nflush > 0) f3_mbar_wait(&S.bar_empty, (nflush - 1) & 1);   // the contraction warps are done with the previous batch
       if (cd0.flags & CD_VALID) {
         float* slot = &S.As[pr][0];
 #pragma unroll
@@ -374,8 +394,9 @@ __device__ __forceinline__ void f3_acc_task(const F3Args& p, F3Smem<LV>& S, cons
           }
       }
       if (HALF == 0 && lane == 0) S.meta[pr] = cd0.seg;
-      __threadfence_block();
-      f3_bar_arrive(F3_BAR_FULL, F3_THREADS);
+      __syncwarp();
+      if (lane == 0) f3_mbar_arrive(&S.bar_full);
+      ++nflush;
     }
     // ---- rotate
     buf ^= 1;
@@ -386,7 +407,9 @@ __device__ __forceinline__ void f3_acc_task(const F3Args& p, F3Smem<LV>& S, cons
 
 // ---------------------------------------------------------------------------------------------- contraction warps
 // scalar output class (O = 24, one component): lane = (k-part kp = lane >> 2, output group og = lane & 3 -> 6 outputs),
-// 8 segments per lane; rows (f, jj) of the class are dealt round-robin to the 8 k-parts.
+// 8 segments per lane; rows (f, jj) of the class are dealt round-robin to the 8 k-parts.  The loads of the next row
+// travel while the current one is multiplied; the 8 k-parts are summed with a halving exchange (24 + 12 + 6 shuffles),
+// after which lane (kp, og) holds the 6 outputs of segment kp.
 template <bool BIAS, int J, int ASLOT>
 __device__ __forceinline__ void f3_con_scalar(const float* __restrict__ Wc, const float* __restrict__ Wbc,
                                               const float* __restrict__ As, int uoff, int f0, int f1, float* tile, int col0,
@@ -401,37 +424,82 @@ __device__ __forceinline__ void f3_con_scalar(const float* __restrict__ Wc, cons
     for (int o = 0; o < 3; ++o) acc[s][o] = 0ull;
   const int nrows = (f1 - f0) * JC;
   int f = f0, jj = kp;                          // kp < 8 <= JC
-  for (int q = kp; q < nrows; q += 8) {
-    const float* wp = (!BIAS || jj < J) ? Wc + (f * J + jj) * 24 + 6 * og : Wbc + f * 24 + 6 * og;
-    const f32x2 w0 = *reinterpret_cast<const f32x2*>(wp);
-    const f32x2 w1 = *reinterpret_cast<const f32x2*>(wp + 2);
-    const f32x2 w2 = *reinterpret_cast<const f32x2*>(wp + 4);
-    const float* ap = As + (uoff + f) * AST + jj;
-#pragma unroll
-    for (int s = 0; s < F3_ACC; ++s) {
-      const float a = ap[s * ASLOT];
-      const f32x2 aa = f3_pack2(a, a);
-      f3_ffma2(acc[s][0], aa, w0); f3_ffma2(acc[s][1], aa, w1); f3_ffma2(acc[s][2], aa, w2);
-    }
-    jj += 8;
-    if (jj >= JC) { jj -= JC; ++f; }
+  // rows are processed in ping-pong pairs: the loads of one row are in flight while the other is multiplied
+#define F3_CS_LOAD(W_, A_)                                                                                              \
+  {                                                                                                                     \
+    const float* wp = (!BIAS || jj < J) ? Wc + (f * J + jj) * 24 + 6 * og : Wbc + f * 24 + 6 * og;                      \
+    W_##0 = *reinterpret_cast<const f32x2*>(wp);                                                                        \
+    W_##1 = *reinterpret_cast<const f32x2*>(wp + 2);                                                                    \
+    W_##2 = *reinterpret_cast<const f32x2*>(wp + 4);                                                                    \
+    const float* ap = As + (uoff + f) * AST + jj;                                                                       \
+    A_##0 = ap[0]; A_##1 = ap[ASLOT]; A_##2 = ap[2 * ASLOT]; A_##3 = ap[3 * ASLOT];                                     \
+    A_##4 = ap[4 * ASLOT]; A_##5 = ap[5 * ASLOT]; A_##6 = ap[6 * ASLOT]; A_##7 = ap[7 * ASLOT];                         \
+    jj += 8;                                                                                                            \
+    if (jj >= JC) { jj -= JC; ++f; }                                                                                    \
   }
+#define F3_CS_FMA1(S_, AV_, W_)                                                                                         \
+  {                                                                                                                     \
+    const f32x2 t = f3_pack2(AV_, AV_);                                                                                 \
+    f3_ffma2(acc[S_][0], t, W_##0); f3_ffma2(acc[S_][1], t, W_##1); f3_ffma2(acc[S_][2], t, W_##2);                     \
+  }
+#define F3_CS_FMA(W_, A_)                                                                                               \
+  F3_CS_FMA1(0, A_##0, W_) F3_CS_FMA1(1, A_##1, W_) F3_CS_FMA1(2, A_##2, W_) F3_CS_FMA1(3, A_##3, W_)                   \
+  F3_CS_FMA1(4, A_##4, W_) F3_CS_FMA1(5, A_##5, W_) F3_CS_FMA1(6, A_##6, W_) F3_CS_FMA1(7, A_##7, W_)
+  static_assert(F3_ACC == 8, "f3_con_scalar is written for 8 segments per batch");
+  f32x2 wa0 = 0ull, wa1 = 0ull, wa2 = 0ull, wb0 = 0ull, wb1 = 0ull, wb2 = 0ull;
+  float aa0 = 0.f, aa1 = 0.f, aa2 = 0.f, aa3 = 0.f, aa4 = 0.f, aa5 = 0.f, aa6 = 0.f, aa7 = 0.f;
+  float ab0 = 0.f, ab1 = 0.f, ab2 = 0.f, ab3 = 0.f, ab4 = 0.f, ab5 = 0.f, ab6 = 0.f, ab7 = 0.f;
+  if (kp < nrows) F3_CS_LOAD(wa, aa)
+  for (int q = kp; q < nrows; q += 16) {
+    const bool hb = q + 8 < nrows;
+    if (hb) F3_CS_LOAD(wb, ab)
+    F3_CS_FMA(wa, aa)
+    if (hb) {
+      if (q + 16 < nrows) F3_CS_LOAD(wa, aa)
+      F3_CS_FMA(wb, ab)
+    }
+  }
+#undef F3_CS_LOAD
+#undef F3_CS_FMA1
+#undef F3_CS_FMA
+  // ---- sum over the 8 k-parts: after the three exchanges lane kp holds segment s = kp
+  float v[F3_ACC][6];
 #pragma unroll
   for (int s = 0; s < F3_ACC; ++s)
 #pragma unroll
+    for (int o = 0; o < 3; ++o) f3_unpack2(acc[s][o], v[s][2 * o], v[s][2 * o + 1]);
+  const bool b2 = (lane & 16) != 0, b1 = (lane & 8) != 0, b0 = (lane & 4) != 0;
+  float r4[4][6], r2[2][6], r1[6];
+#pragma unroll
+  for (int s = 0; s < 4; ++s)
+#pragma unroll
     for (int o = 0; o < 6; ++o) {
-      float v0, v1;
-      f3_unpack2(acc[s][o >> 1], v0, v1);
-      float v = (o & 1) ? v1 : v0;
-      v += __shfl_xor_sync(0xffffffffu, v, 4);
-      v += __shfl_xor_sync(0xffffffffu, v, 8);
-      v += __shfl_xor_sync(0xffffffffu, v, 16);
-      if (kp == 0) tile[s * D + col0 + 6 * og + o] += v;
+      const float send = b2 ? v[s][o] : v[s + 4][o];
+      const float keep = b2 ? v[s + 4][o] : v[s][o];
+      r4[s][o] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
     }
+#pragma unroll
+  for (int s = 0; s < 2; ++s)
+#pragma unroll
+    for (int o = 0; o < 6; ++o) {
+      const float send = b1 ? r4[s][o] : r4[s + 2][o];
+      const float keep = b1 ? r4[s + 2][o] : r4[s][o];
+      r2[s][o] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+#pragma unroll
+  for (int o = 0; o < 6; ++o) {
+    const float send = b0 ? r2[0][o] : r2[1][o];
+    const float keep = b0 ? r2[1][o] : r2[0][o];
+    r1[o] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  float* tp = tile + kp * D + col0 + 6 * og;    // segment 4 b2 + 2 b1 + b0 = kp
+#pragma unroll
+  for (int o = 0; o < 6; ++o) tp[o] += r1[o];
 }
 
 // vector output class (O = 6, three components sharing the weights): lane = (kp = lane >> 2, sg = lane & 3 -> segments
-// 2 sg, 2 sg + 1), 2 x 3 x 6 accumulators per lane.
+// 2 sg, 2 sg + 1), 2 x 3 x 6 accumulators per lane; same pipelining, halving exchanges over (segment, output half), then a
+// plain exchange for the last step.
 template <bool BIAS, int J, int ASLOT>
 __device__ __forceinline__ void f3_con_vector(const float* __restrict__ Wc, const float* __restrict__ Wbc,
                                               const float* __restrict__ As, int uoff, int F, int f0, int f1, float* tile,
@@ -449,41 +517,83 @@ __device__ __forceinline__ void f3_con_vector(const float* __restrict__ Wc, cons
   const int nrows = (f1 - f0) * JC;
   int f = f0, jj = kp;
   const float* A0 = As + (2 * sg) * ASLOT;
-  for (int q = kp; q < nrows; q += 8) {
-    const float* wp = (!BIAS || jj < J) ? Wc + (f * J + jj) * 6 : Wbc + f * 6;
-    const f32x2 w0 = *reinterpret_cast<const f32x2*>(wp);
-    const f32x2 w1 = *reinterpret_cast<const f32x2*>(wp + 2);
-    const f32x2 w2 = *reinterpret_cast<const f32x2*>(wp + 4);
-#pragma unroll
-    for (int s = 0; s < 2; ++s)
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const float a = A0[s * ASLOT + (uoff + c * F + f) * AST + jj];
-        const f32x2 aa = f3_pack2(a, a);
-        f3_ffma2(acc[s][c][0], aa, w0); f3_ffma2(acc[s][c][1], aa, w1); f3_ffma2(acc[s][c][2], aa, w2);
-      }
-    jj += 8;
-    if (jj >= JC) { jj -= JC; ++f; }
+#define F3_CV_LOAD(W_, A_)                                                                                              \
+  {                                                                                                                     \
+    const float* wp = (!BIAS || jj < J) ? Wc + (f * J + jj) * 6 : Wbc + f * 6;                                          \
+    W_##0 = *reinterpret_cast<const f32x2*>(wp);                                                                        \
+    W_##1 = *reinterpret_cast<const f32x2*>(wp + 2);                                                                    \
+    W_##2 = *reinterpret_cast<const f32x2*>(wp + 4);                                                                    \
+    const float* ap = A0 + (uoff + f) * AST + jj;                                                                       \
+    A_##0 = ap[0]; A_##1 = ap[F * AST]; A_##2 = ap[2 * F * AST];                                                        \
+    A_##3 = ap[ASLOT]; A_##4 = ap[ASLOT + F * AST]; A_##5 = ap[ASLOT + 2 * F * AST];                                    \
+    jj += 8;                                                                                                            \
+    if (jj >= JC) { jj -= JC; ++f; }                                                                                    \
   }
+#define F3_CV_FMA1(S_, C_, AV_, W_)                                                                                     \
+  {                                                                                                                     \
+    const f32x2 t = f3_pack2(AV_, AV_);                                                                                 \
+    f3_ffma2(acc[S_][C_][0], t, W_##0); f3_ffma2(acc[S_][C_][1], t, W_##1); f3_ffma2(acc[S_][C_][2], t, W_##2);         \
+  }
+#define F3_CV_FMA(W_, A_)                                                                                               \
+  F3_CV_FMA1(0, 0, A_##0, W_) F3_CV_FMA1(0, 1, A_##1, W_) F3_CV_FMA1(0, 2, A_##2, W_)                                   \
+  F3_CV_FMA1(1, 0, A_##3, W_) F3_CV_FMA1(1, 1, A_##4, W_) F3_CV_FMA1(1, 2, A_##5, W_)
+  f32x2 wa0 = 0ull, wa1 = 0ull, wa2 = 0ull, wb0 = 0ull, wb1 = 0ull, wb2 = 0ull;
+  float aa0 = 0.f, aa1 = 0.f, aa2 = 0.f, aa3 = 0.f, aa4 = 0.f, aa5 = 0.f;
+  float ab0 = 0.f, ab1 = 0.f, ab2 = 0.f, ab3 = 0.f, ab4 = 0.f, ab5 = 0.f;
+  if (kp < nrows) F3_CV_LOAD(wa, aa)
+  for (int q = kp; q < nrows; q += 16) {
+    const bool hb = q + 8 < nrows;
+    if (hb) F3_CV_LOAD(wb, ab)
+    F3_CV_FMA(wa, aa)
+    if (hb) {
+      if (q + 16 < nrows) F3_CV_LOAD(wa, aa)
+      F3_CV_FMA(wb, ab)
+    }
+  }
+#undef F3_CV_LOAD
+#undef F3_CV_FMA1
+#undef F3_CV_FMA
+  float v[2][3][6];
 #pragma unroll
   for (int s = 0; s < 2; ++s)
 #pragma unroll
     for (int c = 0; c < 3; ++c)
 #pragma unroll
-      for (int o = 0; o < 6; ++o) {
-        float v0, v1;
-        f3_unpack2(acc[s][c][o >> 1], v0, v1);
-        float v = (o & 1) ? v1 : v0;
-        v += __shfl_xor_sync(0xffffffffu, v, 4);
-        v += __shfl_xor_sync(0xffffffffu, v, 8);
-        v += __shfl_xor_sync(0xffffffffu, v, 16);
-        if (kp == 0) tile[(2 * sg + s) * D + col0 + 3 * o + c] += v;
-      }
+      for (int o = 0; o < 3; ++o) f3_unpack2(acc[s][c][o], v[s][c][2 * o], v[s][c][2 * o + 1]);
+  const bool b2 = (lane & 16) != 0, b1 = (lane & 8) != 0, b0 = (lane & 4) != 0;
+  float r1[3][6], r2[3][3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int o = 0; o < 6; ++o) {               // b2 selects the segment of the pair
+      const float send = b2 ? v[0][c][o] : v[1][c][o];
+      const float keep = b2 ? v[1][c][o] : v[0][c][o];
+      r1[c][o] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int o = 0; o < 3; ++o) {               // b1 selects the output half
+      const float send = b1 ? r1[c][o] : r1[c][o + 3];
+      const float keep = b1 ? r1[c][o + 3] : r1[c][o];
+      r2[c][o] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int o = 0; o < 3; ++o) r2[c][o] += __shfl_xor_sync(0xffffffffu, r2[c][o], 4);
+  if (!b0) {
+    float* tp = tile + (2 * sg + (b2 ? 1 : 0)) * D + col0 + 3 * (b1 ? 3 : 0);
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int o = 0; o < 3; ++o) tp[3 * o + c] += r2[c][o];
+  }
 }
 
 template <int LV, bool BIAS>
 __device__ __forceinline__ void f3_con_task(const F3Args& p, F3Smem<LV>& S, const int r, const int nseg, const int cw,
-                                            const int lane) {
+                                            const int lane, int& nbatch) {
   using Cfg = F3Cfg<LV>;
   constexpr int ASLOT = Cfg::U * Cfg::AST;
   const int nb = (nseg + F3_ACC - 1) / F3_ACC;
@@ -491,7 +601,7 @@ __device__ __forceinline__ void f3_con_task(const F3Args& p, F3Smem<LV>& S, cons
   float* tile = &S.tile[cw][0][0];
   for (int b = 0; b < nb; ++b) {
     for (int i = lane; i < F3_ACC * D; i += 32) tile[i] = 0.f;
-    f3_bar_sync(F3_BAR_FULL, F3_THREADS);            // the 8 slots of batch b are written
+    f3_mbar_wait(&S.bar_full, nbatch & 1);           // the 8 slots of batch b are written
     __syncwarp();
 #pragma unroll 1
     for (int k = 0; k < p.ncls; ++k) {
@@ -512,7 +622,9 @@ __device__ __forceinline__ void f3_con_task(const F3Args& p, F3Smem<LV>& S, cons
         p.part[((size_t)sid * Cfg::NSLV + r) * D + f] = v;
       }
     }
-    if (b + 1 < nb) f3_bar_arrive(F3_BAR_EMPTY, F3_THREADS);   // slots and meta may be overwritten
+    __syncwarp();
+    if (lane == 0) f3_mbar_arrive(&S.bar_empty);      // this warp is done with the slots and meta
+    ++nbatch;
     f3_bar_sync(F3_BAR_CON2, F3_CON * 32);            // tiles may be cleared
   }
 }
@@ -537,8 +649,13 @@ __global__ void __launch_bounds__(F3_THREADS, 1) k_conv_fused(const __grid_const
 #pragma unroll
     for (int k = 0; k < 3; ++k) { LB.gx[k] = lt.gi[k]; LB.gs[k] = lt.gm[k]; LB.gf[k] = lt.gf[k]; }
   }
-  if (tid == 0) { S.task[5] = blockIdx.x % NCOMBO; S.task[6] = -1; }
+  if (tid == 0) {
+    S.task[5] = blockIdx.x % NCOMBO; S.task[6] = -1;
+    f3_mbar_init(&S.bar_full, 2 * F3_ACC);
+    f3_mbar_init(&S.bar_empty, F3_CON);
+  }
   __syncthreads();
+  int nbat = 0;                      // batches handed over so far (same count on both sides of the mbarriers)
 
   for (;;) {
     if (tid == 0) {
@@ -576,15 +693,15 @@ __global__ void __launch_bounds__(F3_THREADS, 1) k_conv_fused(const __grid_const
     }
     if (is_acc) {
       if (half == 0) {
-        if (r == 0) f3_acc_task<LV, true, 0>(p, S, LB, g, r, idx0, nseg, pr, lane);
-        else f3_acc_task<LV, false, 0>(p, S, LB, g, r, idx0, nseg, pr, lane);
+        if (r == 0) f3_acc_task<LV, true, 0>(p, S, LB, g, r, idx0, nseg, pr, lane, nbat);
+        else f3_acc_task<LV, false, 0>(p, S, LB, g, r, idx0, nseg, pr, lane, nbat);
       } else {
-        if (r == 0) f3_acc_task<LV, true, 1>(p, S, LB, g, r, idx0, nseg, pr, lane);
-        else f3_acc_task<LV, false, 1>(p, S, LB, g, r, idx0, nseg, pr, lane);
+        if (r == 0) f3_acc_task<LV, true, 1>(p, S, LB, g, r, idx0, nseg, pr, lane, nbat);
+        else f3_acc_task<LV, false, 1>(p, S, LB, g, r, idx0, nseg, pr, lane, nbat);
       }
     } else {
-      if (r == 0) f3_con_task<LV, true>(p, S, r, nseg, w - 2 * F3_ACC, lane);
-      else f3_con_task<LV, false>(p, S, r, nseg, w - 2 * F3_ACC, lane);
+      if (r == 0) f3_con_task<LV, true>(p, S, r, nseg, w - 2 * F3_ACC, lane, nbat);
+      else f3_con_task<LV, false>(p, S, r, nseg, w - 2 * F3_ACC, lane, nbat);
     }
     __syncthreads();
   }

@@ -29,10 +29,13 @@ struct HidArgs {
   float* hs; size_t LT; int J;
 };
 
-struct HidTile {                   // one tile in flight: this thread's pieces of it, still in registers
+struct HidDesc {                   // a tile of <= HT consecutive list entries of one segment
+  int kc, pos;                     // entries, first list position (kc = 0: no more tiles)
+  const float* psr;                // source-node term of the segment (this thread's hidden units)
+};
+struct HidData {                   // this thread's pieces of a tile, still in registers
   float4 ea, pd[3];
   float ps[3];
-  int kc, pos;                     // entries, first list position (kc = 0: no more tiles)
 };
 
 __global__ void __launch_bounds__(HID_THREADS) k_edge_hidden(const __grid_constant__ HidArgs p) {
@@ -64,43 +67,54 @@ __global__ void __launch_bounds__(HID_THREADS) k_edge_hidden(const __grid_consta
     }
     const int dslot = (g == 1 || g == 3) ? 3 : 2;
     const int4* gl = p.glist + p.goff[g];
-    // tile iterator over the CTA's segments of this group; the loads of a tile are issued one tile ahead
+    // Three tiles are in flight: the list entries of tile t + 2 and, through the entries fetched one iteration earlier,
+    // the edge embeddings / destination-node terms of tile t + 1 travel while tile t is computed from shared memory.
     int si = q0, c0 = 0;
     int4 sg = gl[si];
-    auto fetch = [&](HidTile& R) {
-      R.kc = 0; R.pos = 0;
+    auto gen = [&](HidDesc& d, int2& ent) {
+      d.kc = 0; d.pos = 0; d.psr = p.proj;
+      ent = make_int2(0, 0);
       if (si >= nsg) return;
-      R.pos = sg.z + c0;
-      R.kc = min(HT, sg.y - c0);
-      const float* psr = p.proj + ((size_t)(sg.x >> 1) * 4 + (sg.x & 1)) * HID + jg;
-#pragma unroll
-      for (int i = 0; i < 3; ++i) R.ps[i] = __ldg(psr + 24 * i);
-      if (te < R.kc) {
-        const int2 ent = p.seg_list[R.pos + te];
-        R.ea = __ldg(reinterpret_cast<const float4*>(p.ea_pool + (size_t)ent.x * EA) + tsub);
-        const float4* pdr = reinterpret_cast<const float4*>(p.proj + ((size_t)ent.y * 4 + dslot) * HID) + tsub;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) R.pd[k] = __ldg(pdr + 6 * k);
-      }
+      d.pos = sg.z + c0;
+      d.kc = min(HT, sg.y - c0);
+      d.psr = p.proj + ((size_t)(sg.x >> 1) * 4 + (sg.x & 1)) * HID + jg;
+      if (te < d.kc) ent = p.seg_list[d.pos + te];
       c0 += HT;
       if (c0 >= sg.y) {
         si += nq; c0 = 0;
         if (si < nsg) sg = gl[si];
       }
     };
-    HidTile R;
-    fetch(R);
-    while (R.kc > 0) {
+    auto load = [&](const HidDesc& d, const int2 ent, HidData& R) {
+      if (d.kc == 0) return;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) R.ps[i] = __ldg(d.psr + 24 * i);
+      if (te < d.kc) {
+        R.ea = __ldg(reinterpret_cast<const float4*>(p.ea_pool + (size_t)ent.x * EA) + tsub);
+        const float4* pdr = reinterpret_cast<const float4*>(p.proj + ((size_t)ent.y * 4 + dslot) * HID) + tsub;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) R.pd[k] = __ldg(pdr + 6 * k);
+      }
+    };
+    HidDesc d0, d1;
+    int2 e0, e1;
+    HidData R;
+    gen(d0, e0);
+    gen(d1, e1);
+    load(d0, e0, R);
+    while (d0.kc > 0) {
       __syncthreads();                              // the previous tile is consumed
-      if (te < R.kc) {
+      if (te < d0.kc) {
         *reinterpret_cast<float4*>(&sEA[te][4 * tsub]) = R.ea;
 #pragma unroll
         for (int k = 0; k < 3; ++k) *reinterpret_cast<float4*>(&sPD[te][4 * (tsub + 6 * k)]) = R.pd[k];
       }
       __syncthreads();
-      const int kc = R.kc, pos = R.pos;
+      const int kc = d0.kc, pos = d0.pos;
       const float ps[3] = {R.ps[0], R.ps[1], R.ps[2]};
-      fetch(R);                                     // next tile's loads travel while this one is computed
+      d0 = d1; e0 = e1;
+      gen(d1, e1);                                  // entries of tile t + 2
+      load(d0, e0, R);                              // data of tile t + 1 (its entries arrived during the last iteration)
 #pragma unroll
       for (int q = 0; q < HT / 4; ++q) {
         const int e = es + 4 * q;
@@ -136,7 +150,7 @@ void launch_edge_hidden(DdkCtx* c, int layer, cudaStream_t st) {
   for (int g = 0; g < 4; ++g) a.W1[g] = W(c, conv_id(layer, DDK_WL_W1 + g));
   a.hs = ptr<float>(c->b_hs); a.LT = (size_t)c->list_total; a.J = f3_J(c->layers[layer].lv);
   const int nsegs = 2 * c->N;
-  const int grid = std::min(c->sm_count * 5, std::max(1, nsegs / 8));
+  const int grid = std::min(c->sm_count * 4, std::max(1, nsegs / 8));   // 4 CTAs of 96 threads are resident per SM
   LaunchScope ls(c, PC_HIDDEN, st);
   k_edge_hidden<<<grid, HID_THREADS, 0, st>>>(a);
 }

@@ -28,6 +28,14 @@ __device__ __forceinline__ float smear1(const float* __restrict__ sm, float d, i
   return expf(sm[32] * (t * t));
 }
 
+// (seg, n, base) of a work-list entry stored as int4 (the fourth word is padding).  Loaded as 8 + 4 bytes: with a 16-byte
+// load ptxas treats the unused fourth destination register as free and later writes to it stall on the pending load.
+__device__ __forceinline__ int4 load_seg_entry(const int4* __restrict__ e) {
+  const int2 a = __ldg(reinterpret_cast<const int2*>(e));
+  const int b = __ldg(reinterpret_cast<const int*>(e) + 2);
+  return make_int4(a.x, a.y, b, 0);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

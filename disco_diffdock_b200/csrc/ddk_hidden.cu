@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(HID_THREADS) k_edge_hidden(const __grid_consta
     // Three tiles are in flight: the list entries of tile t + 2 and, through the entries fetched one iteration earlier,
     // the edge embeddings / destination-node terms of tile t + 1 travel while tile t is computed from shared memory.
     int si = q0, c0 = 0;
-    int4 sg = gl[si];
+    int4 sg = load_seg_entry(gl + si);
     auto gen = [&](HidDesc& d, int2& ent) {
       d.kc = 0; d.pos = 0; d.psr = p.proj;
       ent = make_int2(0, 0);
@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(HID_THREADS) k_edge_hidden(const __grid_consta
       c0 += HT;
       if (c0 >= sg.y) {
         si += nq; c0 = 0;
-        if (si < nsg) sg = gl[si];
+        if (si < nsg) sg = load_seg_entry(gl + si);
       }
     };
     auto load = [&](const HidDesc& d, const int2 ent, HidData& R) {

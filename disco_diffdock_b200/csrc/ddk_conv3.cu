@@ -253,19 +253,23 @@ __device__ __forceinline__ void f3_edge(f32x2 (&acc)[F3Cfg<LV>::NSLOT][F3Cfg<LV>
     for (int k = 0; k < NSLOT; ++k)
       if (Cfg::half_of(k) == HALF) bs[k] += b[k];
   }
-  f32x2 h[J / 2];
+  constexpr int JH = J > 12 ? 12 : J;             // hidden units per pass (keeps the live set small at J = 24)
 #pragma unroll
-  for (int q = 0; q < J / 4; ++q) {
-    const float4 v = *reinterpret_cast<const float4*>(hrow + 4 * q);
-    h[2 * q] = f3_pack2(v.x, v.y); h[2 * q + 1] = f3_pack2(v.z, v.w);
-  }
+  for (int j0 = 0; j0 < J; j0 += JH) {
+    f32x2 h[JH / 2];
 #pragma unroll
-  for (int k = 0; k < NSLOT; ++k)
-    if (Cfg::half_of(k) == HALF) {
-      const f32x2 bb = f3_pack2(b[k], b[k]);
-#pragma unroll
-      for (int j = 0; j < J / 2; ++j) f3_ffma2(acc[k][j], bb, h[j]);
+    for (int q = 0; q < JH / 4; ++q) {
+      const float4 v = *reinterpret_cast<const float4*>(hrow + j0 + 4 * q);
+      h[2 * q] = f3_pack2(v.x, v.y); h[2 * q + 1] = f3_pack2(v.z, v.w);
     }
+#pragma unroll
+    for (int k = 0; k < NSLOT; ++k)
+      if (Cfg::half_of(k) == HALF) {
+        const f32x2 bb = f3_pack2(b[k], b[k]);
+#pragma unroll
+        for (int j = 0; j < JH / 2; ++j) f3_ffma2(acc[k][j0 / 2 + j], bb, h[j]);
+      }
+  }
 }
 
 // One warp of the pair `pr` (HALF = 0 / 1).  Both warps run the same chunk sequence in lockstep: the pair's stage is
@@ -335,8 +339,12 @@ __device__ __forceinline__ void f3_acc_task(const F3Args& p, F3Smem<LV>& S, cons
           if (gsub + 8 * i < XQ) f3_cp16(xd + 32 * i, xs + 32 * i);
         if (gsub == 0) f3_cp16(&T.SH[buf][ge][0], p.sh_pool + slot);
       }
-      if (HALF == 1 && lane < d.kc * (J / 4))
-        f3_cp16(&T.H[buf][0][0] + 4 * lane, hsr + (size_t)d.pos * J + 4 * lane);
+      if (HALF == 1) {
+#pragma unroll
+        for (int i = 0; i < (KC3 * J / 4 + 31) / 32; ++i)
+          if (lane + 32 * i < d.kc * (J / 4))
+            f3_cp16(&T.H[buf][0][0] + 4 * (lane + 32 * i), hsr + (size_t)d.pos * J + 4 * (lane + 32 * i));
+      }
     }
     __pipeline_commit();
   };

@@ -53,7 +53,7 @@ struct Buf {
 
 // ---- fused conv kernel (ddk_conv3.cu): hidden units are processed in slices of J (per basis level)
 constexpr int NSL_MAX = 9;          // most slices of any level (72 / 8)
-__host__ __device__ constexpr int f3_J(int lv) { return lv == 1 ? 12 : (lv == 0 ? 12 : 8); }   // hidden units per slice
+__host__ __device__ constexpr int f3_J(int lv) { return lv == 0 ? 24 : (lv == 3 ? 8 : 12); }   // hidden units per slice (as wide as shared memory and registers allow)
 __host__ __device__ constexpr int f3_nsl(int lv) { return HID / f3_J(lv); }
 constexpr int F3_ACC = 8;           // accumulate warp PAIRS per CTA (= segments per contraction batch)
 constexpr int F3_CON = 4;           // contraction warps per CTA

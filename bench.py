@@ -215,7 +215,7 @@ def main():
         resident_step()
     barrier()
     eng.profile_read()
-    launches0, edges0 = eng.kernel_launches(), eng.edge_total()
+    launches0, edges0, segs0 = eng.kernel_launches(), eng.edge_total(), eng.segment_total()
     sampler = ClockSampler(local_rank)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -230,6 +230,7 @@ def main():
     prof = eng.profile_read()
     launches = eng.kernel_launches() - launches0
     dyn_edges = eng.edge_total() - edges0
+    segments = eng.segment_total() - segs0                  # non-empty (node, edge group) segments, summed over reverse steps
     static_edges = (info.EB + info.ER) * REV_STEPS * args.steps
     edges = dyn_edges + static_edges
     tms = torch.tensor([ms], device=dev)
@@ -268,28 +269,34 @@ def main():
     h2d = n_complex * (bi.h2d_bytes + bi.NL * 3 * 4 + REV_STEPS * (2 * bi.B * 3 + R0) * 4 + REV_STEPS * bi.B * (32 + 4) * 4)
 
     # ---------------------------------------------------------------- roofline of the dominant kernel
+    # k_conv_fused<3> (the two 84-wide conv layers): one launch = one layer over every pose of the rank.  Work model
+    # (DESIGN.md section 5): per listed edge 2*72*U FLOP of rank-1 updates (U = 276), per non-empty segment 2*72*W FLOP of
+    # the second radial-MLP layer (W = 1872); algorithmic bytes per launch = node features in and out, the edge list, the
+    # harmonics and the 72 hidden units of every listed edge.
     hbm_peak, peak_src, peaks_raw = peaks()
     acc_ms, acc_n = prof['conv_accum_lv3']
     total_prof_ms = sum(v[0] for v in prof.values())
     n_nodes = info.NL + info.NR
-    lv3_layers = 2
-    # per launch (= one conv layer over one chunk of poses): the work model of SURVEY.md 8d / DESIGN.md
-    edges_per_layer_pass = edges / (REV_STEPS * args.steps)              # edges of all poses of the rank in one step
-    launches_per_layer_pass = max(1, acc_n // (lv3_layers * REV_STEPS * args.steps))
-    e_launch = edges_per_layer_pass / launches_per_layer_pass
-    n_launch = n_nodes / launches_per_layer_pass
-    bytes_launch = n_launch * (84 + 84) * 4 + e_launch * (8 + 96 + 16)
-    flop_launch = e_launch * 2 * (72 * 24 + U_LV3 * 72)
+    passes = REV_STEPS * args.steps                                      # reverse steps in the timed region
+    e_launch = edges / passes                                            # listed edges of all poses of the rank, one layer
+    s_launch = segments / passes
+    bytes_launch = n_nodes * (84 + 84) * 4 + e_launch * (8 + 16 + 72 * 4) + s_launch * 16
+    flop_launch = e_launch * 2 * 72 * U_LV3 + s_launch * 2 * 72 * W_CONV[3]
     t_launch = acc_ms / max(acc_n, 1) / 1000
     clocks = sampler.summary()
     sm_mhz = clocks.get('sm_mhz') or peaks_raw.get('sm_max_mhz', 1965.0)
     fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
-    roofline = {'kernel': 'k_conv_accum<3>', 'bound': 'hbm', 'achieved': bytes_launch / t_launch / 1e9, 'peak': hbm_peak,
+    conv_ms = sum(prof[k][0] for k in ('conv_accum_lv0', 'conv_accum_lv1', 'conv_accum_lv2', 'conv_accum_lv3'))
+    roofline = {'kernel': 'k_conv_fused<3>', 'bound': 'hbm', 'achieved': bytes_launch / t_launch / 1e9, 'peak': hbm_peak,
                 'unit': 'GB/s', 'frac': bytes_launch / t_launch / 1e9 / hbm_peak, 'traffic': None, 'peak_source': peak_src,
                 'launch_ms': t_launch * 1000, 'launches': acc_n, 'share_of_step': acc_ms / max(total_prof_ms, 1e-9),
+                'conv_share_of_step': conv_ms / max(total_prof_ms, 1e-9),
+                'edges_per_launch': e_launch, 'segments_per_launch': s_launch,
                 'fp32_fma': {'achieved_tflops': flop_launch / t_launch / 1e12, 'peak_tflops_at_measured_clock': fp32_peak,
                              'frac': flop_launch / t_launch / 1e12 / fp32_peak,
-                             'note': 'the kernel is FP32-FMA bound (re-associated tensor product, SURVEY 0.6); HBM fraction is low by design'},
+                             'note': 'the kernel is bound by the FP32 FMA pipe and shared-memory issue, not by HBM (re-associated '
+                                     'tensor product, SURVEY 8d); the HBM fraction is low by design; ncu DRAM traffic of this kernel: '
+                                     'profiles/ (captured at 80 poses per launch, so not comparable per launch)'},
                 'kernel_ms': {k: round(v[0], 3) for k, v in prof.items()}}
     ref_equiv_tflops = edges * FLOP_PER_EDGE_REF / (ms / 1000) / 1e12
 
@@ -297,7 +304,7 @@ def main():
             'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic, fresh-init weights (seeded)',
             'config': {'workload': WORKLOAD, 'poses_per_gpu': n_poses, 'reverse_steps': REV_STEPS,
-                       'l2': 'inputs larger than L2: per-layer working set (edge features + outer-product scratch) is >1 GB per pass',
+                       'l2': 'inputs larger than L2: the per-layer working set (edge embeddings, hidden units and harmonics of 5.2 M listed edges) is about 2 GB per pass',
                        'edges_per_pose_step': edges / (n_poses * REV_STEPS * args.steps),
                        'reference_formulation_equiv_tflops': ref_equiv_tflops, 'parallelism': f'pose-sharded x{world}'},
             'e2e': {'value': e2e_value, 'unit': 'poses/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h)},

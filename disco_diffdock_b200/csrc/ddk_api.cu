@@ -123,9 +123,9 @@ int ddk_create(const DdkConfig* cfg, const float* weights_h, size_t n_floats, co
   if ((e = cudaMalloc(&c->w, n_floats * sizeof(float))) != cudaSuccess) return bail("cudaMalloc(weights)", e);
   if ((e = cudaMemcpy(c->w, weights_h, n_floats * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess)
     return bail("cudaMemcpy(weights)", e);
-  if ((e = cudaMalloc(&c->b_edge_total.p, 8)) != cudaSuccess) return bail("cudaMalloc(counter)", e);
-  c->b_edge_total.bytes = 8;
-  if ((e = cudaMemset(c->b_edge_total.p, 0, 8)) != cudaSuccess) return bail("cudaMemset(counter)", e);
+  if ((e = cudaMalloc(&c->b_edge_total.p, 16)) != cudaSuccess) return bail("cudaMalloc(counter)", e);
+  c->b_edge_total.bytes = 16;   // [0] dynamic edges, [1] non-empty (node, group) segments, both cumulative
+  if ((e = cudaMemset(c->b_edge_total.p, 0, 16)) != cudaSuccess) return bail("cudaMemset(counter)", e);
   if ((e = conv_configure()) != cudaSuccess) return bail("cudaFuncSetAttribute(conv)", e);
   if ((e = heads_configure()) != cudaSuccess) return bail("cudaFuncSetAttribute(heads)", e);
   if ((e = conv2_configure()) != cudaSuccess) return bail("cudaFuncSetAttribute(conv2)", e);
@@ -513,6 +513,15 @@ int64_t ddk_edge_total(DdkCtx* c) {
   unsigned long long v = 0;
   if (cudaDeviceSynchronize() != cudaSuccess) return -1;
   if (cudaMemcpy(&v, c->b_edge_total.p, 8, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return (int64_t)v;
+}
+
+int64_t ddk_segment_total(DdkCtx* c) {
+  if (!c) return -1;
+  cudaSetDevice(c->device);
+  unsigned long long v = 0;
+  if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+  if (cudaMemcpy(&v, ptr<unsigned long long>(c->b_edge_total) + 1, 8, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
   return (int64_t)v;
 }
 

@@ -134,7 +134,7 @@ struct F3Args {
 constexpr int GL_BUCKETS = 64;
 __global__ void __launch_bounds__(1024) k_build_group_lists(int NL, int NR, const int* __restrict__ seg_cnt,
                                                             const int* __restrict__ seg_base, int4* __restrict__ glist,
-                                                            int* __restrict__ gcnt) {
+                                                            int* __restrict__ gcnt, unsigned long long* __restrict__ seg_total) {
   __shared__ int hist[GL_BUCKETS], cursor[GL_BUCKETS];
   const int g = blockIdx.x;
   const int nn = g < 2 ? NL : NR;
@@ -152,6 +152,7 @@ __global__ void __launch_bounds__(1024) k_build_group_lists(int NL, int NR, cons
     int run = 0;
     for (int bkt = GL_BUCKETS - 1; bkt >= 0; --bkt) { cursor[bkt] = run; run += hist[bkt]; }
     gcnt[g] = run;
+    atomicAdd(seg_total, (unsigned long long)run);
   }
   __syncthreads();
   for (int i = tid; i < nn; i += 1024) {
@@ -904,7 +905,8 @@ cudaError_t conv3_configure() {
 void launch_build_group_lists(DdkCtx* c, cudaStream_t st) {
   LaunchScope ls(c, PC_GRAPH, st);
   k_build_group_lists<<<4, 1024, 0, st>>>(c->NL, c->NR, ptr<int>(c->b_seg_cnt), ptr<int>(c->b_seg_base),
-                                          ptr<int4>(c->b_glist), ptr<int>(c->b_gcnt));
+                                          ptr<int4>(c->b_glist), ptr<int>(c->b_gcnt),
+                                          ptr<unsigned long long>(c->b_edge_total) + 1);
 }
 
 void launch_conv_fused(DdkCtx* c, int layer, const float* x_in, float* x_out, cudaStream_t st) {

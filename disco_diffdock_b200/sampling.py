@@ -127,6 +127,36 @@ def build_step_tables(score_model, model_args, t_to_sigma, tr_schedule, rot_sche
                       torch.stack(tors), coef)
 
 
+def _sample_with_guidance(sm, eng, batch, start_pos, steps, z, tr_schedule, weight, cfg_start, cfg_end, device):
+    """Classifier-free guidance (utils/sampling.py:119-135): inside [cfg_end, cfg_start] every reverse step evaluates the score
+    model twice -- with the latents, and with ``unconditional = 1`` and zeroed latents -- and extrapolates
+    ``s + w (s - s_uncond)``.  The two branches live in two libddk contexts over the same pose buffer (the latents enter the
+    step-invariant node embedding, so each branch keeps its own batch); the update runs once on the guided scores."""
+    from . import engine as _engine
+    if getattr(sm, '_engine_uncond', None) is None or sm._engine_uncond.device != eng.device:
+        sm._engine_uncond = _engine.Engine(sm.hyper(), {k: v.detach() for k, v in sm.state_dict().items()}, eng.device)
+    eng_u = sm._engine_uncond
+    ub = batch.shallow_copy()
+    for nt in ('ligand', 'receptor'):
+        ub[nt].unconditional = torch.ones(batch[nt].num_nodes, 1)
+        ub[nt].latent_h = torch.zeros_like(batch[nt].latent_h)
+    eng_u.set_batch(ub, assume_copies=True)
+    pos = start_pos.to(device, torch.float32).contiguous().clone()
+    dev = lambda t: None if t is None else t.to(device, torch.float32).contiguous()
+    for i in range(steps.n_steps):
+        args = (steps.semb[i], steps.cutoff[i], steps.tr_sigma[i], steps.rot_scale[i], steps.tor_scale[i])
+        tr, rot, tor = eng.score(pos, *args)
+        t_tr = float(tr_schedule[i])
+        if cfg_end <= t_tr <= cfg_start:
+            utr, urot, utor = eng_u.score(pos, *args)
+            tr = tr + weight * (tr - utr)
+            rot = rot + weight * (rot - urot)
+            tor = tor + weight * (tor - utor)
+        zi = (None, None, None) if z is None else (dev(z['tr'][i]), dev(z['rot'][i]), dev(z['tor'][i]) if z.get('tor') is not None else None)
+        eng.update(pos, tr, rot, tor, zi[0], zi[1], zi[2], steps.coef[i])
+    return pos
+
+
 def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_schedule, device, t_to_sigma, model_args,
              no_random=False, ode=False, visualization_list=None, confidence_model=None, confidence_data_list=None,
              confidence_model_args=None, batch_size=32, no_final_step_noise=False, use_latent=True,
@@ -140,8 +170,9 @@ def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_s
     confidence = [] if confidence_model is not None else None
     conf_loader = iter(DataLoader(confidence_data_list, batch_size=batch_size)) if confidence_data_list is not None else None
     latent = use_latent and getattr(model_args, 'latent_dim', 0) > 0
-    if classifier_free_guidance_weight != 0.0:
-        raise NotImplementedError('classifier-free guidance (two score evaluations per step) is not wired up yet')
+    cfg_on = classifier_free_guidance_weight != 0.0
+    if cfg_on and not (latent and getattr(sm, 'latent_droprate', 0) > 0):
+        raise ValueError('classifier-free guidance needs a latent-conditioned score model trained with latent drop-out')
     pose0 = 0
     with torch.no_grad():
         n_batches = (N + batch_size - 1) // batch_size
@@ -190,7 +221,10 @@ def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_s
                     for v in z.values():
                         if v is not None:
                             v[-1] = 0
-            if host_buffers:
+            if cfg_on:
+                pos = _sample_with_guidance(sm, eng, batch, start_pos, steps, z, tr_schedule, classifier_free_guidance_weight,
+                                            cfg_start, cfg_end, device)
+            elif host_buffers:
                 pos = start_pos.detach().to('cpu', torch.float32).contiguous()
                 eng.sample_host(pos, steps, z)
             else:
@@ -201,8 +235,25 @@ def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_s
             len_lig = pos.shape[0] // b
             for i in range(b):
                 data_list[batch_id * batch_size + i]['ligand'].pos = pos[i * len_lig:(i + 1) * len_lig]
-                if latent:
-                    data_list[batch_id * batch_size + i]['ligand'].latent_h = batch['ligand'].latent_h[i * len_lig:(i + 1) * len_lig]
+                if latent:                                                      # utils/sampling.py:205-222
+                    item = data_list[batch_id * batch_size + i]
+                    len_rec = batch['receptor'].num_nodes // b
+                    lig_lat = batch['ligand'].latent_h[i * len_lig:(i + 1) * len_lig]
+                    rec_lat = batch['receptor'].latent_h[i * len_rec:(i + 1) * len_rec]
+                    item['ligand'].latent_h = lig_lat
+                    centre = item.original_center.detach().cpu() if 'original_center' in item else torch.zeros(1, 3)
+                    lat_str, lat_pos = '', []
+                    for j in range(model_args.latent_dim):
+                        if float(lig_lat[:, j].sum()) == 1:
+                            idx = int(torch.argmax(lig_lat[:, j]))
+                            lat_str += 'L' + str(idx)
+                            lat_pos.append(item['ligand'].pos[idx:idx + 1].detach().cpu() + centre)
+                        else:
+                            idx = int(torch.argmax(rec_lat[:, j]))
+                            lat_str += 'R' + str(idx)
+                            lat_pos.append(item['receptor'].pos[idx:idx + 1].detach().cpu() + centre)
+                    item.latent_str = lat_str
+                    item.latent_pos = torch.cat(lat_pos, dim=0)
             pose0 += b
             if visualization_list is not None:
                 for idx, vis in enumerate(visualization_list):

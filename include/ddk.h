@@ -182,6 +182,8 @@ int64_t ddk_kernel_launches(const DdkCtx* ctx);        /* kernels launched by th
 int64_t ddk_last_edge_count(DdkCtx* ctx);              /* edges of the combined graph in the last ddk_score (sync) */
 int64_t ddk_edge_total(DdkCtx* ctx);                   /* cumulative *dynamic* (ligand radius + cross) edges listed since ddk_create (sync);
                                                           the static bond / receptor-contact edges are not included */
+int64_t ddk_segment_total(DdkCtx* ctx);                /* cumulative non-empty (node, edge group) segments since ddk_create (sync): the
+                                                          second radial-MLP layer runs once per segment and conv layer */
 int ddk_debug_read(DdkCtx* ctx, const char* name, void* dst_h, size_t max_bytes, size_t* n_bytes);
 
 /* Optional per-launch timing with CUDA events on the launching stream (used by bench.py for the roofline line).

@@ -102,6 +102,44 @@ def main():
                                 pos_fp=float(start.double().abs().sum()),
                                 rec_fp=float(lst[0]['receptor'].x.double().abs().sum()))
         print('wrote', name)
+    if not only or 'sample_disco' in only:
+        write_disco(out_dir, mods)
+
+
+def write_disco(out_dir, mods):
+    """DisCo path through the reference's own code: PretrainedScoreEncoder.encode_ar (models/model_classes.py:9-49,
+    models/pretrained_score_encoder.py:46-89; arg-max decoding) feeding utils/sampling.sampling with classifier-free
+    guidance (utils/sampling.py:119-135)."""
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        from models.pretrained_score_encoder import PretrainedScoreEncoder
+    c = helpers.DISCO_CASE
+    m, sd, cfg, lst, noise, sched, heads = helpers.disco_inputs(c)
+    ref_model, args = ref_loader.build_reference_model(cfg, sd)
+    ar = PretrainedScoreEncoder(pretrained_score_model=ref_model, ns=cfg.ns, latent_dim=1, latent_vocab=1, latent_no_batchnorm=False,
+                                latent_dropout=0.0, latent_hidden_dim=128, input_latent_dim=cfg.latent_dim, apply_gumbel_softmax=True)
+    missing = ar.load_state_dict(heads, strict=False)
+    assert all(k.startswith('pretrained_score_model.') for k in missing.missing_keys) and not missing.unexpected_keys
+    ar.eval()
+    t2s = partial(mods.diffusion_utils.t_to_sigma, args=args)
+    ref_list = [as_loader_item(x) for x in copy.deepcopy(lst)]
+    for a, b in zip(ref_list, lst):
+        a['ligand'].ar_pos = b['ligand'].ar_pos.clone()
+    with ref_loader.InjectedNormal(noise, c['steps']), torch.no_grad():
+        # the latents the AR model decodes for this batch (same call sampling() makes)
+        probe = ddata.Batch.from_data_list(copy.deepcopy(ref_list))
+        probe['ligand'].pos = probe['ligand'].ar_pos
+        lat_l, lat_r = ar.encode_ar(probe, c['softmax_latent_temperature'])
+        out_list, _ = mods.sampling.sampling(ref_list, SimpleNamespace(score_model=ref_model, encoder=None), c['steps'], sched, sched,
+                                             sched, torch.device('cpu'), t2s, args, batch_size=c['B'], no_final_step_noise=False,
+                                             ar_model=ar, classifier_free_guidance_weight=c['cfg_weight'], cfg_start=c['cfg_start'],
+                                             cfg_end=c['cfg_end'], softmax_latent_temperature=c['softmax_latent_temperature'],
+                                             **helpers.README_TEMPS)
+    pos = torch.cat([x['ligand'].pos for x in out_list])
+    np.savez_compressed(os.path.join(out_dir, 'sample_disco.npz'), pos=pos.numpy(), lat_l=lat_l.numpy(), lat_r=lat_r.numpy(),
+                        latent_str=np.array([x.latent_str for x in out_list]), weights_fp=fingerprint(sd),
+                        heads_fp=fingerprint({k: v.float() for k, v in heads.items()}))
+    print('wrote sample_disco', [x.latent_str for x in out_list])
 
 
 if __name__ == '__main__':

@@ -73,3 +73,38 @@ def draw_noise(seed, steps, B, R, no_final_step_noise=True):
 def rmsd_per_pose(a, b, B):
     a, b = a.reshape(B, -1, 3).double(), b.reshape(B, -1, 3).double()
     return ((a - b) ** 2).sum(-1).mean(-1).sqrt()
+
+
+def make_ar_heads(seed, ns=24, hidden=128, latent_dim=1):
+    """Seeded parameters of the two latent prediction heads of PretrainedScoreEncoder
+    (pretrained_score_encoder.py:23-44), batch-norm statistics randomised so the eval-mode affine is exercised."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for head in ('latent_s_predictor', 'latent_r_predictor'):
+        dims = [(2 * ns, hidden), (hidden, hidden), (hidden, latent_dim)]
+        for li, (i, o) in zip((0, 4, 8), dims):
+            sd[f'{head}.{li}.weight'] = torch.randn(o, i, generator=g) / np.sqrt(i)
+            sd[f'{head}.{li}.bias'] = torch.randn(o, generator=g) * 0.1
+        for bi in (1, 5):
+            sd[f'{head}.{bi}.weight'] = torch.rand(hidden, generator=g) + 0.5
+            sd[f'{head}.{bi}.bias'] = torch.randn(hidden, generator=g) * 0.1
+            sd[f'{head}.{bi}.running_mean'] = torch.randn(hidden, generator=g) * 0.1
+            sd[f'{head}.{bi}.running_var'] = torch.rand(hidden, generator=g) + 0.5
+            sd[f'{head}.{bi}.num_batches_tracked'] = torch.tensor(10)
+    return sd
+
+
+DISCO_CASE = dict(mseed=3, gain=5.0, cseed=9, n_lig=16, n_rec=40, B=3, steps=8, latent=2, ar_seed=21, cfg_weight=0.6,
+                  cfg_start=1.0, cfg_end=0.3, softmax_latent_temperature=100.0)
+
+
+def disco_inputs(c=DISCO_CASE):
+    """Config 4 in miniature: latent-conditioned score model + AR latent sampler + classifier-free guidance."""
+    m, sd, cfg = make_model(c['mseed'], latent_dim=c['latent'], latent_droprate=0.1, gain=c['gain'])
+    g, lst = make_pose_batch(c['cseed'], c['n_lig'], c['n_rec'], c['B'])
+    for x in lst:
+        x['ligand'].ar_pos = g['ligand'].pos.clone()          # utils/sampling.py:78-80
+    R = g['ligand'].mask_rotate.shape[0]
+    noise = draw_noise(11, c['steps'], c['B'], R)
+    sched = np.linspace(1, 0, c['steps'] + 1)[:-1]
+    return m, sd, cfg, lst, noise, sched, make_ar_heads(c['ar_seed'])

@@ -249,3 +249,38 @@ def test_sampling_matches_oracle_multi_batch():
     rmsd = helpers.rmsd_per_pose(torch.cat(want), got, N)
     dump('multi_batch', {'rmsd': rmsd.tolist()})
     assert float(rmsd.max()) < 1e-3, rmsd
+
+
+def test_disco_ar_latents_and_guidance_match_reference_golden():
+    """BASELINE config 4 in miniature: latent-conditioned score model + autoregressive latent sampler (arg-max decoding) +
+    classifier-free guidance, against poses / latents produced by the reference's own PretrainedScoreEncoder.encode_ar
+    and sampling() (oracle/make_golden.py::write_disco)."""
+    from functools import partial
+    from disco_diffdock_b200 import latent as dlatent
+    c = helpers.DISCO_CASE
+    z = np.load(os.path.join(GOLD, 'sample_disco.npz'))
+    m, sd, cfg, lst, noise, sched, heads = helpers.disco_inputs(c)
+    m = m.to('cuda')
+    ar = dlatent.PretrainedScoreEncoder(pretrained_score_model=m, ns=cfg.ns, latent_dim=1, latent_vocab=1, latent_hidden_dim=128,
+                                        input_latent_dim=cfg.latent_dim, apply_gumbel_softmax=True)
+    missing = ar.load_state_dict(heads, strict=False)
+    assert all(k.startswith('pretrained_score_model.') for k in missing.missing_keys) and not missing.unexpected_keys
+    ar = ar.to('cuda').eval()
+    # latents alone
+    probe = ddata.Batch.from_data_list([synthetic.as_loader_item(x) for x in copy.deepcopy(lst)])
+    probe['ligand'].pos = probe['ligand'].ar_pos
+    lat_l, lat_r = ar.encode_ar(probe.to('cuda'), c['softmax_latent_temperature'])
+    assert torch.equal(lat_l.cpu(), torch.from_numpy(z['lat_l'])) and torch.equal(lat_r.cpu(), torch.from_numpy(z['lat_r']))
+    # full run: AR latents -> guided reverse diffusion
+    data_list = [synthetic.as_loader_item(x) for x in copy.deepcopy(lst)]
+    for a, b in zip(data_list, lst):
+        a['ligand'].ar_pos = b['ligand'].ar_pos.clone()
+    out, _ = dsampling.sampling(data_list, m, c['steps'], sched, sched, sched, torch.device('cuda'), partial(du.t_to_sigma, args=cfg), cfg,
+                                batch_size=c['B'], no_final_step_noise=False, noise=noise, ar_model=ar,
+                                classifier_free_guidance_weight=c['cfg_weight'], cfg_start=c['cfg_start'], cfg_end=c['cfg_end'],
+                                softmax_latent_temperature=c['softmax_latent_temperature'], **helpers.README_TEMPS)
+    pos = torch.cat([x['ligand'].pos.cpu() for x in out])
+    rmsd = helpers.rmsd_per_pose(torch.from_numpy(z['pos']), pos, c['B'])
+    dump('sample_disco', {'rmsd_vs_reference': rmsd.tolist(), 'latent_str': [x.latent_str for x in out]})
+    assert [x.latent_str for x in out] == [str(s) for s in z['latent_str']]
+    assert float(rmsd.max()) < 1e-3, rmsd

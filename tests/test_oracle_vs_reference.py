@@ -65,3 +65,20 @@ def test_sampling_loop_matches_reference():
         pos = restate.sample(sd, cfg, batch, tables, sched, noise, inference_steps=steps, **helpers.README_TEMPS)
     rmsd = helpers.rmsd_per_pose(ref_pos, pos, B)
     assert float(rmsd.max()) < 2e-4, rmsd
+
+
+def test_ar_encoder_has_the_reference_parameter_names():
+    """disco_diffdock_b200.latent.PretrainedScoreEncoder must load the reference's AR checkpoints: same head parameter
+    names and shapes as models/pretrained_score_encoder.py:23-44."""
+    import contextlib, io
+    from disco_diffdock_b200 import latent as dlatent
+    ref_loader.modules()
+    with contextlib.redirect_stdout(io.StringIO()):
+        from models.pretrained_score_encoder import PretrainedScoreEncoder as RefEnc
+    m, sd, cfg = helpers.make_model(3, latent_dim=2, latent_droprate=0.1)
+    ref_model, _ = ref_loader.build_reference_model(cfg, sd)
+    ours = dlatent.PretrainedScoreEncoder(m, 24, 1, 1, input_latent_dim=2)
+    ref = RefEnc(pretrained_score_model=ref_model, ns=24, latent_dim=1, latent_vocab=1, input_latent_dim=2)
+    ko = {k: tuple(v.shape) for k, v in ours.state_dict().items() if k.startswith('latent_')}
+    kr = {k: tuple(v.shape) for k, v in ref.state_dict().items() if k.startswith('latent_')}
+    assert ko == kr and len(ko) == 2 * (3 * 2 + 2 * 5)

@@ -284,3 +284,21 @@ def test_disco_ar_latents_and_guidance_match_reference_golden():
     dump('sample_disco', {'rmsd_vs_reference': rmsd.tolist(), 'latent_str': [x.latent_str for x in out]})
     assert [x.latent_str for x in out] == [str(s) for s in z['latent_str']]
     assert float(rmsd.max()) < 1e-3, rmsd
+
+
+def test_forward_large_receptor_stress():
+    """BASELINE config 5 shape: 2000 C-alpha residues, 120-atom ligand, dynamic cross cut-off at t = 0.9 (all 240 000 cross
+    pairs listed per direction) -- two poses against the oracle."""
+    m, sd, cfg = helpers.make_model(4)
+    m = m.to('cuda')
+    _, lst = helpers.make_pose_batch(31, 120, 2000, 2)
+    batch = ddata.Batch.from_data_list(lst)
+    restate.set_time(batch, 0.9, 0.9, 0.9, 2)
+    with torch.no_grad():
+        tr_o, rot_o, tor_o = restate.forward(sd, cfg, copy.deepcopy(batch), load_tables())[:3]
+    tr, rot, tor = m(batch)
+    eng = m.engine()
+    d = {'tr': rel_err(tr, tr_o), 'rot': rel_err(rot, rot_o), 'tor': rel_err(tor, tor_o), 'edges': eng.last_edge_count()}
+    dump('large_receptor', d)
+    assert d['edges'] > 2 * 2 * 120 * 2000 * 0.95
+    assert max(d['tr'], d['rot'], d['tor']) < 5e-5, d

@@ -216,6 +216,7 @@ def main():
     barrier()
     eng.profile_read()
     launches0, edges0, segs0 = eng.kernel_launches(), eng.edge_total(), eng.segment_total()
+    ge0, gs0 = eng.group_totals()
     sampler = ClockSampler(local_rank)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -231,6 +232,8 @@ def main():
     launches = eng.kernel_launches() - launches0
     dyn_edges = eng.edge_total() - edges0
     segments = eng.segment_total() - segs0                  # non-empty (node, edge group) segments, summed over reverse steps
+    ge1, gs1 = eng.group_totals()
+    g_edges, g_segs = (ge1 - ge0).astype(float), (gs1 - gs0).astype(float)   # per edge group, summed over reverse steps
     static_edges = (info.EB + info.ER) * REV_STEPS * args.steps
     edges = dyn_edges + static_edges
     tms = torch.tensor([ms], device=dev)
@@ -278,8 +281,11 @@ def main():
     total_prof_ms = sum(v[0] for v in prof.values())
     n_nodes = info.NL + info.NR
     passes = REV_STEPS * args.steps                                      # reverse steps in the timed region
-    e_launch = edges / passes                                            # listed edges of all poses of the rank, one layer
-    s_launch = segments / passes
+    # the two level-3 launches of a step: layer 3 over every segment, layer 4 (the last before the heads) over the segments
+    # of ligand nodes only (edge groups 0, 1) -- the heads never read receptor features
+    e_launch = (g_edges.sum() + g_edges[:2].sum()) / 2 / passes           # listed edges per launch, average of the two
+    s_launch = (g_segs.sum() + g_segs[:2].sum()) / 2 / passes
+    n_nodes = (n_nodes + info.NL) / 2
     bytes_launch = n_nodes * (84 + 84) * 4 + e_launch * (8 + 16 + 72 * 4) + s_launch * 16
     flop_launch = e_launch * 2 * 72 * U_LV3 + s_launch * 2 * 72 * W_CONV[3]
     t_launch = acc_ms / max(acc_n, 1) / 1000

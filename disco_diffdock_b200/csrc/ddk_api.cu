@@ -123,9 +123,9 @@ int ddk_create(const DdkConfig* cfg, const float* weights_h, size_t n_floats, co
   if ((e = cudaMalloc(&c->w, n_floats * sizeof(float))) != cudaSuccess) return bail("cudaMalloc(weights)", e);
   if ((e = cudaMemcpy(c->w, weights_h, n_floats * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess)
     return bail("cudaMemcpy(weights)", e);
-  if ((e = cudaMalloc(&c->b_edge_total.p, 16)) != cudaSuccess) return bail("cudaMalloc(counter)", e);
-  c->b_edge_total.bytes = 16;   // [0] dynamic edges, [1] non-empty (node, group) segments, both cumulative
-  if ((e = cudaMemset(c->b_edge_total.p, 0, 16)) != cudaSuccess) return bail("cudaMemset(counter)", e);
+  if ((e = cudaMalloc(&c->b_edge_total.p, 80)) != cudaSuccess) return bail("cudaMalloc(counter)", e);
+  c->b_edge_total.bytes = 80;   // cumulative: [0] dynamic edges, [1] non-empty segments, [2..5] edges / [6..9] segments per group
+  if ((e = cudaMemset(c->b_edge_total.p, 0, 80)) != cudaSuccess) return bail("cudaMemset(counter)", e);
   if ((e = conv_configure()) != cudaSuccess) return bail("cudaFuncSetAttribute(conv)", e);
   if ((e = heads_configure()) != cudaSuccess) return bail("cudaFuncSetAttribute(heads)", e);
   if ((e = conv2_configure()) != cudaSuccess) return bail("cudaFuncSetAttribute(conv2)", e);
@@ -356,7 +356,9 @@ int ddk_set_batch(DdkCtx* c, const DdkBatch* b, void* stream) {
   return DDK_OK;
 }
 
-static int run_embed(DdkCtx* c, const float* lig_pos, const DdkStepInputs* in, cudaStream_t st) {
+// heads_only: the caller reads only ligand node features afterwards (score heads), so the last conv layer skips the
+// segments of receptor nodes (edge groups 2, 3); ddk_embed needs every node
+static int run_embed(DdkCtx* c, const float* lig_pos, const DdkStepInputs* in, cudaStream_t st, bool heads_only) {
   launch_step_consts(c, in->sigma_emb, st);
   launch_build_lists(c, lig_pos, in->cross_cutoff, st);
   launch_edge_features(c, lig_pos, st);
@@ -367,11 +369,12 @@ static int run_embed(DdkCtx* c, const float* lig_pos, const DdkStepInputs* in, c
   launch_node_proj(c, 0, nullptr, xa, st);
   float* xin = xa; float* xout = xb;
   for (int l = 0; l < c->cfg.num_conv_layers; ++l) {
-    launch_conv_layer(c, l, xin, xout, st);
+    launch_conv_layer(c, l, xin, xout, st, heads_only && l + 1 == c->cfg.num_conv_layers);
     if (l + 1 < c->cfg.num_conv_layers) launch_node_proj(c, l + 1, xout, nullptr, st);
     std::swap(xin, xout);
   }
   c->x_final = xin;
+  c->x_final_all = !heads_only;
   return DDK_OK;
 }
 
@@ -388,7 +391,7 @@ int ddk_embed(DdkCtx* c, const float* lig_pos, const DdkStepInputs* in, void* st
   int rc = check_step(c, lig_pos, in);
   if (rc) return rc;
   DDK_CUDA_TRY(c, cudaSetDevice(c->device));
-  run_embed(c, lig_pos, in, (cudaStream_t)stream);
+  run_embed(c, lig_pos, in, (cudaStream_t)stream, false);
   DDK_CUDA_TRY(c, cudaGetLastError());
   return DDK_OK;
 }
@@ -399,7 +402,7 @@ int ddk_score(DdkCtx* c, const float* lig_pos, const DdkStepInputs* in, float* t
   if (!tr || !rot) return fail(c, DDK_ERR_INVALID, "null output");
   cudaStream_t st = (cudaStream_t)stream;
   DDK_CUDA_TRY(c, cudaSetDevice(c->device));
-  run_embed(c, lig_pos, in, st);
+  run_embed(c, lig_pos, in, st, true);
   launch_head_trrot(c, lig_pos, c->x_final, in, tr, rot, st);
   if (tor) launch_head_tor(c, lig_pos, c->x_final, in, tor, st);
   DDK_CUDA_TRY(c, cudaGetLastError());
@@ -408,6 +411,7 @@ int ddk_score(DdkCtx* c, const float* lig_pos, const DdkStepInputs* in, float* t
 
 int ddk_get_node_features(DdkCtx* c, float* lig_out, float* rec_out, void* stream) {
   if (!c || !c->has_batch || !c->x_final) return fail(c, DDK_ERR_STATE, "no embedding available");
+  if (rec_out && !c->x_final_all) return fail(c, DDK_ERR_STATE, "receptor features are only complete after ddk_embed (ddk_score skips them in the last layer)");
   cudaStream_t st = (cudaStream_t)stream;
   if (lig_out) DDK_CUDA_TRY(c, cudaMemcpyAsync(lig_out, c->x_final, (size_t)c->NL * D * 4, cudaMemcpyDeviceToDevice, st));
   if (rec_out)
@@ -442,7 +446,7 @@ int ddk_sample(DdkCtx* c, float* lig_pos, int32_t n_steps, const DdkStepInputs* 
     in.tr_sigma = si->tr_sigma + (size_t)s * c->B;
     in.rot_scale = si->rot_scale + (size_t)s * c->B;
     in.tor_scale = si->tor_scale ? si->tor_scale + (size_t)s * c->B : nullptr;
-    run_embed(c, lig_pos, &in, st);
+    run_embed(c, lig_pos, &in, st, true);
     launch_head_trrot(c, lig_pos, c->x_final, &in, tr, rot, st);
     if (tor) launch_head_tor(c, lig_pos, c->x_final, &in, tor, st);
     launch_update(c, lig_pos, tr, rot, tor, z_tr ? z_tr + (size_t)s * c->B * 3 : nullptr,
@@ -523,6 +527,16 @@ int64_t ddk_segment_total(DdkCtx* c) {
   if (cudaDeviceSynchronize() != cudaSuccess) return -1;
   if (cudaMemcpy(&v, ptr<unsigned long long>(c->b_edge_total) + 1, 8, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
   return (int64_t)v;
+}
+
+int ddk_group_totals(DdkCtx* c, int64_t* edges4, int64_t* segments4) {
+  if (!c || !edges4 || !segments4) return DDK_ERR_INVALID;
+  cudaSetDevice(c->device);
+  unsigned long long v[10];
+  DDK_CUDA_TRY(c, cudaDeviceSynchronize());
+  DDK_CUDA_TRY(c, cudaMemcpy(v, c->b_edge_total.p, sizeof(v), cudaMemcpyDeviceToHost));
+  for (int g = 0; g < 4; ++g) { edges4[g] = (int64_t)v[2 + g]; segments4[g] = (int64_t)v[6 + g]; }
+  return DDK_OK;
 }
 
 int ddk_debug_read(DdkCtx* c, const char* name, void* dst_h, size_t max_bytes, size_t* n_bytes) {

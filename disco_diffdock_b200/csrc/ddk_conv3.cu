@@ -107,6 +107,7 @@ struct F3Smem {
 struct F3Args {
   int NL, N;
   int nb_segs;                       // segments per task (multiple of F3_ACC)
+  int gmask;                         // bit g set: edge group g is processed (the last layer before the heads: ligand nodes only)
   const int4* glist;                 // per-group lists of non-empty segments: (seg, n, base, 0)
   int goff[4];
   const int* gcnt;                   // [4]
@@ -136,23 +137,27 @@ __global__ void __launch_bounds__(1024) k_build_group_lists(int NL, int NR, cons
                                                             const int* __restrict__ seg_base, int4* __restrict__ glist,
                                                             int* __restrict__ gcnt, unsigned long long* __restrict__ seg_total) {
   __shared__ int hist[GL_BUCKETS], cursor[GL_BUCKETS];
+  __shared__ int nedge;
   const int g = blockIdx.x;
   const int nn = g < 2 ? NL : NR;
   const int off = g == 0 ? 0 : (g == 1 ? NL : (g == 2 ? 2 * NL : 2 * NL + NR));
   const int tid = threadIdx.x;
   if (tid < GL_BUCKETS) hist[tid] = 0;
+  if (tid == 0) nedge = 0;
   __syncthreads();
   for (int i = tid; i < nn; i += 1024) {
     const int seg = g < 2 ? 2 * i + g : 2 * (NL + i) + (g - 2);
     const int n = seg_cnt[seg];
-    if (n > 0) atomicAdd(&hist[min(GL_BUCKETS - 1, (n + KC3 - 1) / KC3)], 1);
+    if (n > 0) { atomicAdd(&hist[min(GL_BUCKETS - 1, (n + KC3 - 1) / KC3)], 1); atomicAdd(&nedge, n); }
   }
   __syncthreads();
   if (tid == 0) {
     int run = 0;
     for (int bkt = GL_BUCKETS - 1; bkt >= 0; --bkt) { cursor[bkt] = run; run += hist[bkt]; }
     gcnt[g] = run;
-    atomicAdd(seg_total, (unsigned long long)run);
+    atomicAdd(seg_total, (unsigned long long)run);                 // seg_total = &counters[1]
+    atomicAdd(seg_total + 1 + g, (unsigned long long)nedge);
+    atomicAdd(seg_total + 5 + g, (unsigned long long)run);
   }
   __syncthreads();
   for (int i = tid; i < nn; i += 1024) {
@@ -671,7 +676,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1) k_conv_fused(const __grid_const
       int combo = S.task[5], found = 0;
       for (int tries = 0; tries < NCOMBO && !found; ++tries) {
         const int g = combo / NSLV;
-        const int nblk = (p.gcnt[g] + p.nb_segs - 1) / p.nb_segs;
+        const int nblk = ((p.gmask >> g) & 1) ? (p.gcnt[g] + p.nb_segs - 1) / p.nb_segs : 0;
         if (nblk > 0) {
           const int blk = atomicAdd(p.counters + combo, 1);
           if (blk < nblk) {
@@ -909,11 +914,12 @@ void launch_build_group_lists(DdkCtx* c, cudaStream_t st) {
                                           ptr<unsigned long long>(c->b_edge_total) + 1);
 }
 
-void launch_conv_fused(DdkCtx* c, int layer, const float* x_in, float* x_out, cudaStream_t st) {
+void launch_conv_fused(DdkCtx* c, int layer, const float* x_in, float* x_out, cudaStream_t st, bool lig_only) {
   const LayerInfo& li = c->layers[layer];
   F3Args a;
   a.NL = c->NL; a.N = c->N;
-  const int nsegs = 2 * c->N;
+  a.gmask = lig_only ? 0x3 : 0xf;
+  const int nsegs = 2 * (lig_only ? c->NL : c->N);
   const int J = f3_J(li.lv), nsl = f3_nsl(li.lv);
   int nb = (int)((int64_t)nsegs * nsl / (c->sm_count * 6)) / F3_ACC * F3_ACC;
   a.nb_segs = std::min(128, std::max(F3_ACC, nb));
@@ -950,7 +956,7 @@ void launch_conv_fused(DdkCtx* c, int layer, const float* x_in, float* x_out, cu
     }
   }
   FinArgs f;
-  f.N = c->N; f.dout = li.dout; f.nsl = nsl;
+  f.N = lig_only ? c->NL : c->N; f.dout = li.dout; f.nsl = nsl;   // ligand nodes come first
   f.seg_cnt = ptr<int>(c->b_seg_cnt);
   f.part = ptr<float>(c->b_part);
   f.bn_scale = W(c, conv_id(layer, DDK_WL_BN_SCALE));
@@ -958,7 +964,7 @@ void launch_conv_fused(DdkCtx* c, int layer, const float* x_in, float* x_out, cu
   f.x_in = x_in; f.x_out = x_out;
   {
     LaunchScope ls(c, PC_CONTRACT, st);
-    k_conv_finalize<<<(c->N + 2) / 3, 256, 0, st>>>(f);
+    k_conv_finalize<<<(f.N + 2) / 3, 256, 0, st>>>(f);
   }
 }
 

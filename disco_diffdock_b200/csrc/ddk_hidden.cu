@@ -27,6 +27,7 @@ struct HidArgs {
   const float* proj;               // [N][4][72]
   const float* W1[4];              // [72][72] row-major, edge-embedding columns 0..23
   float* hs; size_t LT; int J;
+  int gmask;                       // bit g set: edge group g is processed
 };
 
 struct HidDesc {                   // a tile of <= HT consecutive list entries of one segment
@@ -53,7 +54,7 @@ __global__ void __launch_bounds__(HID_THREADS) k_edge_hidden(const __grid_consta
   }
   for (int gi = 0; gi < 4; ++gi) {
     const int g = (blockIdx.x + gi) & 3;
-    const int nsg = p.gcnt[g];
+    const int nsg = ((p.gmask >> g) & 1) ? p.gcnt[g] : 0;
     if (q0 >= nsg) continue;
     float w[3][EA];
 #pragma unroll
@@ -138,7 +139,7 @@ __global__ void __launch_bounds__(HID_THREADS) k_edge_hidden(const __grid_consta
   }
 }
 
-void launch_edge_hidden(DdkCtx* c, int layer, cudaStream_t st) {
+void launch_edge_hidden(DdkCtx* c, int layer, cudaStream_t st, bool lig_only) {
   HidArgs a;
   a.NL = c->NL;
   a.glist = ptr<int4>(c->b_glist);
@@ -148,6 +149,7 @@ void launch_edge_hidden(DdkCtx* c, int layer, cudaStream_t st) {
   a.ea_pool = ptr<float>(c->b_ea_pool);
   a.proj = ptr<float>(c->b_proj);
   for (int g = 0; g < 4; ++g) a.W1[g] = W(c, conv_id(layer, DDK_WL_W1 + g));
+  a.gmask = lig_only ? 0x3 : 0xf;
   a.hs = ptr<float>(c->b_hs); a.LT = (size_t)c->list_total; a.J = f3_J(c->layers[layer].lv);
   const int nsegs = 2 * c->N;
   const int grid = std::min(c->sm_count * 4, std::max(1, nsegs / 8));   // 4 CTAs of 96 threads are resident per SM

@@ -118,6 +118,7 @@ struct DdkCtx {
   ddk::Buf b_work, b_nwork;           // compacted per-chunk segment work lists (rebuilt every step)
   ddk::Buf b_edge_total;              // device uint64: edges of every combined graph built so far
   float* x_final = nullptr;           // points into xa or xb after the last conv layer
+  bool x_final_all = false;           // receptor rows of x_final are valid (ddk_embed); ddk_score / ddk_sample skip them
 
   bool conv_v1 = false;               // DDK_CONV=v1: the simple one-CTA-per-segment accumulate kernel + scratch
   bool conv_v2 = false;               // DDK_CONV=v2: persistent accumulate + tensor-pipe contract over the scratch
@@ -168,8 +169,8 @@ cudaError_t conv3_configure();
 bool build_lane_table(int lv, LaneTab* tab32);
 void build_con_split(const LayerInfo& li, ConSplit& sp);
 void launch_build_group_lists(DdkCtx* c, cudaStream_t st);
-void launch_conv_fused(DdkCtx* c, int layer, const float* x_in, float* x_out, cudaStream_t st);
-void launch_edge_hidden(DdkCtx* c, int layer, cudaStream_t st);
+void launch_conv_fused(DdkCtx* c, int layer, const float* x_in, float* x_out, cudaStream_t st, bool lig_only);
+void launch_edge_hidden(DdkCtx* c, int layer, cudaStream_t st, bool lig_only);
 cudaError_t heads_configure();
 void host_kabsch(const float* A, const float* Bp, int N, float* R9, float* t3);   // host build of the device routine (tests)
 void host_axis_angle(const float* aa, float* R9);   // opt-in dynamic shared memory sizes (once per process / device)
@@ -181,7 +182,7 @@ void launch_build_lists(DdkCtx* c, const float* lig_pos, const float* cutoff, cu
 void launch_edge_features(DdkCtx* c, const float* lig_pos, cudaStream_t st);
 void launch_build_worklist(DdkCtx* c, cudaStream_t st);
 void launch_node_proj(DdkCtx* c, int layer, const float* x_in, float* x0_out, cudaStream_t st);
-void launch_conv_layer(DdkCtx* c, int layer, const float* x_in, float* x_out, cudaStream_t st);
+void launch_conv_layer(DdkCtx* c, int layer, const float* x_in, float* x_out, cudaStream_t st, bool lig_only = false);
 void launch_head_trrot(DdkCtx* c, const float* lig_pos, const float* x, const DdkStepInputs* in, float* tr, float* rot,
                        cudaStream_t st);
 void launch_head_tor(DdkCtx* c, const float* lig_pos, const float* x, const DdkStepInputs* in, float* tor, cudaStream_t st);

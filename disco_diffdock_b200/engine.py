@@ -53,7 +53,7 @@ class DdkStepCoef(C.Structure):
 EXPORTS = ['ddk_abi_version', 'ddk_create', 'ddk_destroy', 'ddk_last_error', 'ddk_set_batch', 'ddk_score', 'ddk_embed',
            'ddk_get_node_features', 'ddk_update', 'ddk_sample', 'ddk_sample_host', 'ddk_kernel_launches',
            'ddk_last_edge_count', 'ddk_debug_read', 'ddk_host_kabsch', 'ddk_host_axis_angle_to_matrix', 'ddk_host_lane_tables_check',
-           'ddk_profile_enable', 'ddk_profile_read', 'ddk_edge_total', 'ddk_segment_total']
+           'ddk_profile_enable', 'ddk_profile_read', 'ddk_edge_total', 'ddk_segment_total', 'ddk_group_totals']
 
 
 def load_library(path: Optional[str] = None):
@@ -88,6 +88,7 @@ def load_library(path: Optional[str] = None):
     lib.ddk_edge_total.argtypes = [C.c_void_p]
     lib.ddk_segment_total.restype = C.c_int64
     lib.ddk_segment_total.argtypes = [C.c_void_p]
+    lib.ddk_group_totals.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.ddk_debug_read.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     lib.ddk_profile_enable.argtypes = [C.c_void_p, C.c_int32]
     lib.ddk_profile_read.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -370,6 +371,12 @@ class Engine:
 
     def segment_total(self) -> int:
         return int(self.lib.ddk_segment_total(self.ctx))
+
+    def group_totals(self):
+        """Cumulative (edges[4], segments[4]) per edge group (0 lig-lig, 1 lig<-rec, 2 rec-rec, 3 rec<-lig)."""
+        e, s = np.zeros(4, np.int64), np.zeros(4, np.int64)
+        self._check(self.lib.ddk_group_totals(self.ctx, _np_ptr(e), _np_ptr(s)), 'ddk_group_totals')
+        return e, s
 
     def last_edge_count(self) -> int:
         return int(self.lib.ddk_last_edge_count(self.ctx))

@@ -160,7 +160,9 @@ int ddk_set_batch(DdkCtx* ctx, const DdkBatch* batch, void* stream);
 int ddk_score(DdkCtx* ctx, const float* lig_pos, const DdkStepInputs* in, float* tr, float* rot, float* tor,
               void* stream);
 
-/* node features after the last conv layer: lig [NL][84], rec [NR][84] (valid after ddk_score / ddk_embed) */
+/* node features after the last conv layer: lig [NL][84], rec [NR][84].  The ligand rows are valid after ddk_score or ddk_embed; the
+ * receptor rows only after ddk_embed (before the score heads the last conv layer skips receptor nodes, whose features the
+ * heads never read: models/score_model.py:269-307) -- asking for rec_out after ddk_score returns DDK_ERR_STATE. */
 int ddk_embed(DdkCtx* ctx, const float* lig_pos, const DdkStepInputs* in, void* stream);
 int ddk_get_node_features(DdkCtx* ctx, float* lig_out, float* rec_out, void* stream);
 
@@ -184,6 +186,8 @@ int64_t ddk_edge_total(DdkCtx* ctx);                   /* cumulative *dynamic* (
                                                           the static bond / receptor-contact edges are not included */
 int64_t ddk_segment_total(DdkCtx* ctx);                /* cumulative non-empty (node, edge group) segments since ddk_create (sync): the
                                                           second radial-MLP layer runs once per segment and conv layer */
+int ddk_group_totals(DdkCtx* ctx, int64_t* edges4, int64_t* segments4);   /* cumulative listed edges / non-empty segments per edge
+                                                          group (0 lig-lig, 1 lig<-rec, 2 rec-rec, 3 rec<-lig), all steps (sync) */
 int ddk_debug_read(DdkCtx* ctx, const char* name, void* dst_h, size_t max_bytes, size_t* n_bytes);
 
 /* Optional per-launch timing with CUDA events on the launching stream (used by bench.py for the roofline line).

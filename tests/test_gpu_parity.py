@@ -121,8 +121,13 @@ def test_forward_stages(layers):
     idx_o = np.array([o_ll[(s, d, sl < nb)] for s, d, sl in groups[0]])
     diag['ll_ea'] = float(np.abs(ea[idx_k] - trc['ll_ea'].numpy()[idx_o]).max())
     diag['ll_sh'] = float(np.abs(sh[idx_k] - trc['ll_sh'].numpy()[idx_o]).max())
-    # --- node features after the last layer
+    # --- node features after the last layer: ligand rows as the score heads saw them, then every node through embed()
+    #     (before the heads the last conv layer skips receptor nodes)
+    x_score = eng.debug_read('x_final').reshape(-1, 84)[:info.NL].copy()
+    m.embed(batch)
     x = eng.debug_read('x_final').reshape(-1, 84)
+    diag['x_lig_score_vs_embed'] = float(np.abs(x_score - x[:info.NL]).max())
+    assert diag['x_lig_score_vs_embed'] == 0.0
     ref_x = torch.cat([trc['lig_h'], trc['rec_h']]).numpy()
     w = ref_x.shape[1]
     diag['x_final'] = float(np.abs(x[:, :w] - ref_x).max())

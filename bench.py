@@ -164,6 +164,10 @@ def main():
     assert torch.cuda.is_available(), 'bench.py needs a CUDA device'
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
+    # anything libraries write to stdout (e.g. NCCL's version banner) goes to stderr: stdout carries exactly one JSON line
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
 
@@ -321,9 +325,12 @@ def main():
         v, dt = cpu_reference_run(2, 6, threads)
         line['cpu_baseline'] = {'value': v, 'unit': 'poses/s', 'cores': threads, 'kind': 'port',
                                 'sample': f'2 poses x 6 of {REV_STEPS} reverse steps of the same complex shape ({dt:.1f} s), scaled'}
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
+        os.dup2(2, 1)
         dist.destroy_process_group()
 
 

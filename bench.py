@@ -285,10 +285,11 @@ def main():
     total_prof_ms = sum(v[0] for v in prof.values())
     n_nodes = info.NL + info.NR
     passes = REV_STEPS * args.steps                                      # reverse steps in the timed region
-    # the two level-3 launches of a step: layer 3 over every segment, layer 4 (the last before the heads) over the segments
-    # of ligand nodes only (edge groups 0, 1) -- the heads never read receptor features
-    e_launch = (g_edges.sum() + g_edges[:2].sum()) / 2 / passes           # listed edges per launch, average of the two
-    s_launch = (g_segs.sum() + g_segs[:2].sum()) / 2 / passes
+    # the two level-3 launches of a step: layer 3 over the segments of ligand nodes and of the residues with a cross edge
+    # (work lists 0, 1, 3 and 4 = receptor contacts of those residues), layer 4 (the last before the heads) over the segments
+    # of ligand nodes only (lists 0, 1) -- the heads never read receptor features
+    e_launch = (g_edges[[0, 1, 3, 4]].sum() + g_edges[:2].sum()) / 2 / passes   # listed edges per launch, average of the two
+    s_launch = (g_segs[[0, 1, 3, 4]].sum() + g_segs[:2].sum()) / 2 / passes
     n_nodes = (n_nodes + info.NL) / 2
     bytes_launch = n_nodes * (84 + 84) * 4 + e_launch * (8 + 16 + 72 * 4) + s_launch * 16
     flop_launch = e_launch * 2 * 72 * U_LV3 + s_launch * 2 * 72 * W_CONV[3]

@@ -123,9 +123,9 @@ int ddk_create(const DdkConfig* cfg, const float* weights_h, size_t n_floats, co
   if ((e = cudaMalloc(&c->w, n_floats * sizeof(float))) != cudaSuccess) return bail("cudaMalloc(weights)", e);
   if ((e = cudaMemcpy(c->w, weights_h, n_floats * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess)
     return bail("cudaMemcpy(weights)", e);
-  if ((e = cudaMalloc(&c->b_edge_total.p, 80)) != cudaSuccess) return bail("cudaMalloc(counter)", e);
-  c->b_edge_total.bytes = 80;   // cumulative: [0] dynamic edges, [1] non-empty segments, [2..5] edges / [6..9] segments per group
-  if ((e = cudaMemset(c->b_edge_total.p, 0, 80)) != cudaSuccess) return bail("cudaMemset(counter)", e);
+  if ((e = cudaMalloc(&c->b_edge_total.p, 96)) != cudaSuccess) return bail("cudaMalloc(counter)", e);
+  c->b_edge_total.bytes = 96;   // cumulative: [0] dynamic edges, [1] non-empty segments, [2..6] edges / [7..11] segments per work list
+  if ((e = cudaMemset(c->b_edge_total.p, 0, 96)) != cudaSuccess) return bail("cudaMemset(counter)", e);
   if ((e = conv_configure()) != cudaSuccess) return bail("cudaFuncSetAttribute(conv)", e);
   if ((e = heads_configure()) != cudaSuccess) return bail("cudaFuncSetAttribute(heads)", e);
   if ((e = conv2_configure()) != cudaSuccess) return bail("cudaFuncSetAttribute(conv2)", e);
@@ -342,7 +342,7 @@ int ddk_set_batch(DdkCtx* c, const DdkBatch* b, void* stream) {
     EN(c->b_A, (size_t)max_chunk_segs * seg_bytes); EN(c->b_Bsum, (size_t)max_chunk_segs * Umax * 4);
     EN(c->b_work, (size_t)nsegs * 16); EN(c->b_nwork, (size_t)c->chunks.size() * 4);
   } else {
-    EN(c->b_glist, (size_t)nsegs * 16); EN(c->b_gcnt, 4 * 4); EN(c->b_counters, 4 * NSL_MAX * 4);
+    EN(c->b_glist, ((size_t)nsegs + NR) * 16); EN(c->b_gcnt, 5 * 4); EN(c->b_counters, 4 * NSL_MAX * 4);
     EN(c->b_part, (size_t)nsegs * NSL_MAX * D * 4);
     EN(c->b_hs, (size_t)std::max<int64_t>(total, 1) * HID * 4);
   }
@@ -357,7 +357,8 @@ int ddk_set_batch(DdkCtx* c, const DdkBatch* b, void* stream) {
 }
 
 // heads_only: the caller reads only ligand node features afterwards (score heads), so the last conv layer skips the
-// segments of receptor nodes (edge groups 2, 3); ddk_embed needs every node
+// segments of receptor nodes (edge groups 2, 3) and the layer before it those of residues without a cross edge (the
+// last layer reads receptor features only through cross edges); ddk_embed needs every node
 static int run_embed(DdkCtx* c, const float* lig_pos, const DdkStepInputs* in, cudaStream_t st, bool heads_only) {
   launch_step_consts(c, in->sigma_emb, st);
   launch_build_lists(c, lig_pos, in->cross_cutoff, st);
@@ -369,7 +370,8 @@ static int run_embed(DdkCtx* c, const float* lig_pos, const DdkStepInputs* in, c
   launch_node_proj(c, 0, nullptr, xa, st);
   float* xin = xa; float* xout = xb;
   for (int l = 0; l < c->cfg.num_conv_layers; ++l) {
-    launch_conv_layer(c, l, xin, xout, st, heads_only && l + 1 == c->cfg.num_conv_layers);
+    const int L = c->cfg.num_conv_layers;
+    launch_conv_layer(c, l, xin, xout, st, !heads_only ? CONV_ALL : (l == L - 1 ? CONV_LIG : (l == L - 2 ? CONV_NEEDED : CONV_ALL)));
     if (l + 1 < c->cfg.num_conv_layers) launch_node_proj(c, l + 1, xout, nullptr, st);
     std::swap(xin, xout);
   }
@@ -529,13 +531,13 @@ int64_t ddk_segment_total(DdkCtx* c) {
   return (int64_t)v;
 }
 
-int ddk_group_totals(DdkCtx* c, int64_t* edges4, int64_t* segments4) {
-  if (!c || !edges4 || !segments4) return DDK_ERR_INVALID;
+int ddk_group_totals(DdkCtx* c, int64_t* edges5, int64_t* segments5) {
+  if (!c || !edges5 || !segments5) return DDK_ERR_INVALID;
   cudaSetDevice(c->device);
-  unsigned long long v[10];
+  unsigned long long v[12];
   DDK_CUDA_TRY(c, cudaDeviceSynchronize());
   DDK_CUDA_TRY(c, cudaMemcpy(v, c->b_edge_total.p, sizeof(v), cudaMemcpyDeviceToHost));
-  for (int g = 0; g < 4; ++g) { edges4[g] = (int64_t)v[2 + g]; segments4[g] = (int64_t)v[6 + g]; }
+  for (int g = 0; g < 5; ++g) { edges5[g] = (int64_t)v[2 + g]; segments5[g] = (int64_t)v[7 + g]; }
   return DDK_OK;
 }
 

@@ -390,10 +390,10 @@ void launch_node_proj(DdkCtx* c, int layer, const float* x_in, float* x0_out, cu
   else k_node_proj<false><<<blocks, 288, 0, st>>>(p);
 }
 
-void launch_conv_layer(DdkCtx* c, int layer, const float* x_in, float* x_out, cudaStream_t st, bool lig_only) {
+void launch_conv_layer(DdkCtx* c, int layer, const float* x_in, float* x_out, cudaStream_t st, int mode) {
   if (!c->conv_v1 && !c->conv_v2) {
-    launch_edge_hidden(c, layer, st, lig_only);
-    launch_conv_fused(c, layer, x_in, x_out, st, lig_only);
+    launch_edge_hidden(c, layer, st, mode);
+    launch_conv_fused(c, layer, x_in, x_out, st, mode);
     return;
   }
   const LayerInfo& li = c->layers[layer];

@@ -110,6 +110,7 @@ struct F3Args {
   int gmask;                         // bit g set: edge group g is processed (the last layer before the heads: ligand nodes only)
   const int4* glist;                 // per-group lists of non-empty segments: (seg, n, base, 0)
   int goff[4];
+  int gci[4];                        // index of each group's count in gcnt (group 2 may use the filtered list)
   const int* gcnt;                   // [4]
   int* counters;                     // [4 * NSLV] next block of each combo
   const int2* seg_list;
@@ -138,31 +139,36 @@ __global__ void __launch_bounds__(1024) k_build_group_lists(int NL, int NR, cons
                                                             int* __restrict__ gcnt, unsigned long long* __restrict__ seg_total) {
   __shared__ int hist[GL_BUCKETS], cursor[GL_BUCKETS];
   __shared__ int nedge;
-  const int g = blockIdx.x;
+  // block 4 = group 2 restricted to the residues that have at least one cross edge (non-empty group-3 segment): the only
+  // receptor nodes whose features the last conv layer before the score heads reads
+  const bool filt = blockIdx.x == 4;
+  const int g = filt ? 2 : blockIdx.x;
   const int nn = g < 2 ? NL : NR;
-  const int off = g == 0 ? 0 : (g == 1 ? NL : (g == 2 ? 2 * NL : 2 * NL + NR));
+  const int off = blockIdx.x == 0 ? 0 : (blockIdx.x == 1 ? NL : (blockIdx.x == 2 ? 2 * NL : (blockIdx.x == 3 ? 2 * NL + NR : 2 * NL + 2 * NR)));
   const int tid = threadIdx.x;
   if (tid < GL_BUCKETS) hist[tid] = 0;
   if (tid == 0) nedge = 0;
   __syncthreads();
   for (int i = tid; i < nn; i += 1024) {
     const int seg = g < 2 ? 2 * i + g : 2 * (NL + i) + (g - 2);
-    const int n = seg_cnt[seg];
+    int n = seg_cnt[seg];
+    if (filt && seg_cnt[seg + 1] == 0) n = 0;
     if (n > 0) { atomicAdd(&hist[min(GL_BUCKETS - 1, (n + KC3 - 1) / KC3)], 1); atomicAdd(&nedge, n); }
   }
   __syncthreads();
   if (tid == 0) {
     int run = 0;
     for (int bkt = GL_BUCKETS - 1; bkt >= 0; --bkt) { cursor[bkt] = run; run += hist[bkt]; }
-    gcnt[g] = run;
-    atomicAdd(seg_total, (unsigned long long)run);                 // seg_total = &counters[1]
-    atomicAdd(seg_total + 1 + g, (unsigned long long)nedge);
-    atomicAdd(seg_total + 5 + g, (unsigned long long)run);
+    gcnt[blockIdx.x] = run;
+    if (!filt) atomicAdd(seg_total, (unsigned long long)run);      // seg_total = &counters[1]
+    atomicAdd(seg_total + 1 + blockIdx.x, (unsigned long long)nedge);   // counters[2..6]: edges per list
+    atomicAdd(seg_total + 6 + blockIdx.x, (unsigned long long)run);     // counters[7..11]: segments per list
   }
   __syncthreads();
   for (int i = tid; i < nn; i += 1024) {
     const int seg = g < 2 ? 2 * i + g : 2 * (NL + i) + (g - 2);
-    const int n = seg_cnt[seg];
+    int n = seg_cnt[seg];
+    if (filt && seg_cnt[seg + 1] == 0) n = 0;
     if (n > 0) {
       const int o = atomicAdd(&cursor[min(GL_BUCKETS - 1, (n + KC3 - 1) / KC3)], 1);
       glist[off + o] = make_int4(seg, n, seg_base[seg], 0);
@@ -295,9 +301,11 @@ __device__ __forceinline__ void f3_acc_task(const F3Args& p, F3Smem<LV>& S, cons
 
   f32x2 acc[NSLOT][J / 2];
   float bs[NSLOT];
+  int urow[NSLOT];                                  // rows of the A block owned by this lane (this half's slots)
 #pragma unroll
   for (int k = 0; k < NSLOT; ++k) {
     bs[k] = 0.f;
+    urow[k] = Cfg::half_of(k) == HALF ? p.ltab[lane].u[k] : -1;
 #pragma unroll
     for (int j = 0; j < J / 2; ++j) acc[k][j] = 0ull;
   }
@@ -392,7 +400,7 @@ __device__ __forceinline__ void f3_acc_task(const F3Args& p, F3Smem<LV>& S, cons
 #pragma unroll
         for (int k = 0; k < NSLOT; ++k)
           if (Cfg::half_of(k) == HALF) {
-            const int u = p.ltab[lane].u[k];
+            const int u = urow[k];
             if (u >= 0) {
 #pragma unroll
               for (int j = 0; j < J / 2; ++j) {
@@ -676,12 +684,13 @@ __global__ void __launch_bounds__(F3_THREADS, 1) k_conv_fused(const __grid_const
       int combo = S.task[5], found = 0;
       for (int tries = 0; tries < NCOMBO && !found; ++tries) {
         const int g = combo / NSLV;
-        const int nblk = ((p.gmask >> g) & 1) ? (p.gcnt[g] + p.nb_segs - 1) / p.nb_segs : 0;
+        const int gn = ((p.gmask >> g) & 1) ? p.gcnt[p.gci[g]] : 0;
+        const int nblk = (gn + p.nb_segs - 1) / p.nb_segs;
         if (nblk > 0) {
           const int blk = atomicAdd(p.counters + combo, 1);
           if (blk < nblk) {
             S.task[0] = g; S.task[1] = combo % NSLV; S.task[2] = blk * p.nb_segs;
-            S.task[3] = min(p.nb_segs, p.gcnt[g] - blk * p.nb_segs);
+            S.task[3] = min(p.nb_segs, gn - blk * p.nb_segs);
             S.task[4] = (combo != S.task[6]);
             S.task[5] = combo; S.task[6] = combo;
             found = 1;
@@ -909,12 +918,13 @@ cudaError_t conv3_configure() {
 
 void launch_build_group_lists(DdkCtx* c, cudaStream_t st) {
   LaunchScope ls(c, PC_GRAPH, st);
-  k_build_group_lists<<<4, 1024, 0, st>>>(c->NL, c->NR, ptr<int>(c->b_seg_cnt), ptr<int>(c->b_seg_base),
+  k_build_group_lists<<<5, 1024, 0, st>>>(c->NL, c->NR, ptr<int>(c->b_seg_cnt), ptr<int>(c->b_seg_base),
                                           ptr<int4>(c->b_glist), ptr<int>(c->b_gcnt),
                                           ptr<unsigned long long>(c->b_edge_total) + 1);
 }
 
-void launch_conv_fused(DdkCtx* c, int layer, const float* x_in, float* x_out, cudaStream_t st, bool lig_only) {
+void launch_conv_fused(DdkCtx* c, int layer, const float* x_in, float* x_out, cudaStream_t st, int mode) {
+  const bool lig_only = mode == CONV_LIG;
   const LayerInfo& li = c->layers[layer];
   F3Args a;
   a.NL = c->NL; a.N = c->N;
@@ -925,6 +935,8 @@ void launch_conv_fused(DdkCtx* c, int layer, const float* x_in, float* x_out, cu
   a.nb_segs = std::min(128, std::max(F3_ACC, nb));
   a.glist = ptr<int4>(c->b_glist);
   a.goff[0] = 0; a.goff[1] = c->NL; a.goff[2] = 2 * c->NL; a.goff[3] = 2 * c->NL + c->NR;
+  for (int g = 0; g < 4; ++g) a.gci[g] = g;
+  if (mode == CONV_NEEDED) { a.goff[2] = 2 * c->NL + 2 * c->NR; a.gci[2] = 4; }
   a.gcnt = ptr<int>(c->b_gcnt);
   a.counters = ptr<int>(c->b_counters);
   a.seg_list = ptr<int2>(c->b_seg_list);

@@ -21,7 +21,7 @@ constexpr int EAP = 28;            // padded row of a staged edge embedding
 
 struct HidArgs {
   int NL;
-  const int4* glist; int goff[4]; const int* gcnt;   // non-empty segments per group: (seg, n, base, 0)
+  const int4* glist; int goff[4]; int gci[4]; const int* gcnt;   // non-empty segments per group: (seg, n, base, 0)
   const int2* seg_list;
   const float* ea_pool;            // [P][24]
   const float* proj;               // [N][4][72]
@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(HID_THREADS) k_edge_hidden(const __grid_consta
   }
   for (int gi = 0; gi < 4; ++gi) {
     const int g = (blockIdx.x + gi) & 3;
-    const int nsg = ((p.gmask >> g) & 1) ? p.gcnt[g] : 0;
+    const int nsg = ((p.gmask >> g) & 1) ? p.gcnt[p.gci[g]] : 0;
     if (q0 >= nsg) continue;
     float w[3][EA];
 #pragma unroll
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(HID_THREADS) k_edge_hidden(const __grid_consta
             const float4 ea = *reinterpret_cast<const float4*>(&sEA[e][4 * k]);
 #pragma unroll
             for (int i = 0; i < 3; ++i)
-              a[i] += w[i][4 * k] * ea.x + w[i][4 * k + 1] * ea.y + w[i][4 * k + 2] * ea.z + w[i][4 * k + 3] * ea.w;
+              a[i] = fmaf(w[i][4 * k + 3], ea.w, fmaf(w[i][4 * k + 2], ea.z, fmaf(w[i][4 * k + 1], ea.y, fmaf(w[i][4 * k], ea.x, a[i]))));
           }
           float* out = p.hs + (size_t)(pos + e) * J;
 #pragma unroll
@@ -139,11 +139,14 @@ __global__ void __launch_bounds__(HID_THREADS) k_edge_hidden(const __grid_consta
   }
 }
 
-void launch_edge_hidden(DdkCtx* c, int layer, cudaStream_t st, bool lig_only) {
+void launch_edge_hidden(DdkCtx* c, int layer, cudaStream_t st, int mode) {
+  const bool lig_only = mode == CONV_LIG;
   HidArgs a;
   a.NL = c->NL;
   a.glist = ptr<int4>(c->b_glist);
   a.goff[0] = 0; a.goff[1] = c->NL; a.goff[2] = 2 * c->NL; a.goff[3] = 2 * c->NL + c->NR;
+  for (int g = 0; g < 4; ++g) a.gci[g] = g;
+  if (mode == CONV_NEEDED) { a.goff[2] = 2 * c->NL + 2 * c->NR; a.gci[2] = 4; }
   a.gcnt = ptr<int>(c->b_gcnt);
   a.seg_list = ptr<int2>(c->b_seg_list);
   a.ea_pool = ptr<float>(c->b_ea_pool);

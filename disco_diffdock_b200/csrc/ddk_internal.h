@@ -169,8 +169,11 @@ cudaError_t conv3_configure();
 bool build_lane_table(int lv, LaneTab* tab32);
 void build_con_split(const LayerInfo& li, ConSplit& sp);
 void launch_build_group_lists(DdkCtx* c, cudaStream_t st);
-void launch_conv_fused(DdkCtx* c, int layer, const float* x_in, float* x_out, cudaStream_t st, bool lig_only);
-void launch_edge_hidden(DdkCtx* c, int layer, cudaStream_t st, bool lig_only);
+// which segments a conv layer processes: all; ligand nodes + the residues with a cross edge (whose features the next,
+// ligand-only layer reads); ligand nodes only (the last layer before the score heads)
+enum ConvMode { CONV_ALL = 0, CONV_NEEDED = 1, CONV_LIG = 2 };
+void launch_conv_fused(DdkCtx* c, int layer, const float* x_in, float* x_out, cudaStream_t st, int mode);
+void launch_edge_hidden(DdkCtx* c, int layer, cudaStream_t st, int mode);
 cudaError_t heads_configure();
 void host_kabsch(const float* A, const float* Bp, int N, float* R9, float* t3);   // host build of the device routine (tests)
 void host_axis_angle(const float* aa, float* R9);   // opt-in dynamic shared memory sizes (once per process / device)
@@ -182,7 +185,7 @@ void launch_build_lists(DdkCtx* c, const float* lig_pos, const float* cutoff, cu
 void launch_edge_features(DdkCtx* c, const float* lig_pos, cudaStream_t st);
 void launch_build_worklist(DdkCtx* c, cudaStream_t st);
 void launch_node_proj(DdkCtx* c, int layer, const float* x_in, float* x0_out, cudaStream_t st);
-void launch_conv_layer(DdkCtx* c, int layer, const float* x_in, float* x_out, cudaStream_t st, bool lig_only = false);
+void launch_conv_layer(DdkCtx* c, int layer, const float* x_in, float* x_out, cudaStream_t st, int mode = 0);
 void launch_head_trrot(DdkCtx* c, const float* lig_pos, const float* x, const DdkStepInputs* in, float* tr, float* rot,
                        cudaStream_t st);
 void launch_head_tor(DdkCtx* c, const float* lig_pos, const float* x, const DdkStepInputs* in, float* tor, cudaStream_t st);

@@ -373,8 +373,9 @@ class Engine:
         return int(self.lib.ddk_segment_total(self.ctx))
 
     def group_totals(self):
-        """Cumulative (edges[4], segments[4]) per edge group (0 lig-lig, 1 lig<-rec, 2 rec-rec, 3 rec<-lig)."""
-        e, s = np.zeros(4, np.int64), np.zeros(4, np.int64)
+        """Cumulative (edges[5], segments[5]) per work list: groups 0 lig-lig, 1 lig<-rec, 2 rec-rec, 3 rec<-lig, and 4 = group 2
+        restricted to residues with a cross edge."""
+        e, s = np.zeros(5, np.int64), np.zeros(5, np.int64)
         self._check(self.lib.ddk_group_totals(self.ctx, _np_ptr(e), _np_ptr(s)), 'ddk_group_totals')
         return e, s
 

@@ -186,8 +186,9 @@ int64_t ddk_edge_total(DdkCtx* ctx);                   /* cumulative *dynamic* (
                                                           the static bond / receptor-contact edges are not included */
 int64_t ddk_segment_total(DdkCtx* ctx);                /* cumulative non-empty (node, edge group) segments since ddk_create (sync): the
                                                           second radial-MLP layer runs once per segment and conv layer */
-int ddk_group_totals(DdkCtx* ctx, int64_t* edges4, int64_t* segments4);   /* cumulative listed edges / non-empty segments per edge
-                                                          group (0 lig-lig, 1 lig<-rec, 2 rec-rec, 3 rec<-lig), all steps (sync) */
+int ddk_group_totals(DdkCtx* ctx, int64_t* edges5, int64_t* segments5);   /* cumulative listed edges / non-empty segments per work
+                                                          list: edge groups 0 lig-lig, 1 lig<-rec, 2 rec-rec, 3 rec<-lig, and 4 = group 2
+                                                          restricted to residues with a cross edge; all steps (sync) */
 int ddk_debug_read(DdkCtx* ctx, const char* name, void* dst_h, size_t max_bytes, size_t* n_bytes);
 
 /* Optional per-launch timing with CUDA events on the launching stream (used by bench.py for the roofline line).

@@ -241,6 +241,32 @@ __global__ void __launch_bounds__(256) k_edge_features(EdgeArgs p) {
   int base = p.seg_base[seg], cnt = p.seg_cnt[seg], nstatic = p.seg_static[seg];
   const float* tbv = p.tb + ((size_t)g * TB_COUNT + (GROUP == 0 ? TB_LIG_EDGE : (GROUP == 1 ? TB_CROSS_EDGE : TB_REC_EDGE))) * NS;
   float un = (p.uncond != nullptr) ? p.uncond[node] : 0.f;
+  if (GROUP == 2) {
+    // receptor contacts: the first layer is step-invariant (k_setup_rr_edges) up to the sigma-embedding bias, so only the
+    // 24 x 24 second layer is left; the hidden activations are consumed as they are formed (no pre[] array: with it this
+    // instantiation spilled 2 KB per thread to local memory)
+    for (int e = lane; e < cnt; e += 32) {
+      const int2 ent = p.seg_list[base + e];
+      const float4* rp4 = reinterpret_cast<const float4*>(p.rr_pre + (size_t)(ent.x - p.slot_rr) * EA);
+      float out[EA];
+#pragma unroll
+      for (int o = 0; o < EA; ++o) out[o] = sb2[o] + un * p.uncond_emb[o];
+#pragma unroll
+      for (int q = 0; q < EA / 4; ++q) {
+        const float4 v = __ldg(rp4 + q);
+        const float r4[4] = {fmaxf(v.x + tbv[4 * q], 0.f), fmaxf(v.y + tbv[4 * q + 1], 0.f), fmaxf(v.z + tbv[4 * q + 2], 0.f),
+                             fmaxf(v.w + tbv[4 * q + 3], 0.f)};
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int o = 0; o < EA; ++o) out[o] = fmaf(sW2[(4 * q + c) * EA + o], r4[c], out[o]);
+      }
+      float4* dst = reinterpret_cast<float4*>(p.ea_pool + (size_t)ent.x * EA);
+#pragma unroll
+      for (int q = 0; q < EA / 4; ++q) dst[q] = make_float4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
+    }
+    return;
+  }
   for (int e = lane; e < cnt; e += 32) {
     int2 ent = p.seg_list[base + e];
     float pre[EA];

@@ -24,6 +24,7 @@
 #include <cuda_pipeline_primitives.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "ddk_conv.cuh"
@@ -112,7 +113,7 @@ struct F3Args {
   int goff[4];
   int gci[4];                        // index of each group's count in gcnt (group 2 may use the filtered list)
   const int* gcnt;                   // [4]
-  int* counters;                     // [4 * NSLV] next block of each combo
+  int* counters;                     // [4 * NSLV] segment cursor of each combo
   const int2* seg_list;
   const float* x;                    // [N][84] layer input
   const float* hs;                   // [NSLV][LT][J] hidden units of every listed edge (k_edge_hidden)
@@ -685,12 +686,15 @@ __global__ void __launch_bounds__(F3_THREADS, 1) k_conv_fused(const __grid_const
       for (int tries = 0; tries < NCOMBO && !found; ++tries) {
         const int g = combo / NSLV;
         const int gn = ((p.gmask >> g) & 1) ? p.gcnt[p.gci[g]] : 0;
-        const int nblk = (gn + p.nb_segs - 1) / p.nb_segs;
-        if (nblk > 0) {
-          const int blk = atomicAdd(p.counters + combo, 1);
-          if (blk < nblk) {
-            S.task[0] = g; S.task[1] = combo % NSLV; S.task[2] = blk * p.nb_segs;
-            S.task[3] = min(p.nb_segs, gn - blk * p.nb_segs);
+        // guided self-scheduling on the combo's segment cursor: blocks shrink as the combo runs out, so the CTAs of a
+        // launch finish within a few segments of each other
+        const int rem = gn - *reinterpret_cast<volatile int*>(p.counters + combo);
+        if (rem > 0) {
+          const int size = max(F3_ACC, min(p.nb_segs, (rem / 8) / F3_ACC * F3_ACC));
+          const int start = atomicAdd(p.counters + combo, size);
+          if (start < gn) {
+            S.task[0] = g; S.task[1] = combo % NSLV; S.task[2] = start;
+            S.task[3] = min(size, gn - start);
             S.task[4] = (combo != S.task[6]);
             S.task[5] = combo; S.task[6] = combo;
             found = 1;
@@ -931,7 +935,8 @@ void launch_conv_fused(DdkCtx* c, int layer, const float* x_in, float* x_out, cu
   a.gmask = lig_only ? 0x3 : 0xf;
   const int nsegs = 2 * (lig_only ? c->NL : c->N);
   const int J = f3_J(li.lv), nsl = f3_nsl(li.lv);
-  int nb = (int)((int64_t)nsegs * nsl / (c->sm_count * 6)) / F3_ACC * F3_ACC;
+  static const int tasks_per_cta = getenv("DDK_TASKS_PER_CTA") ? atoi(getenv("DDK_TASKS_PER_CTA")) : 12;
+  int nb = (int)((int64_t)nsegs * nsl / (c->sm_count * tasks_per_cta)) / F3_ACC * F3_ACC;
   a.nb_segs = std::min(128, std::max(F3_ACC, nb));
   a.glist = ptr<int4>(c->b_glist);
   a.goff[0] = 0; a.goff[1] = c->NL; a.goff[2] = 2 * c->NL; a.goff[3] = 2 * c->NL + c->NR;

@@ -22,21 +22,29 @@ struct TrRotArgs {
 };
 
 constexpr int HEAD_THREADS = 128;
+constexpr int HEAD_ATOMS = 64;     // atoms per pass (two threads per atom)
 
+// One CTA per graph; atoms in passes of 64, two threads per atom: each computes half of the outputs of the three small
+// dense layers (hidden activations exchanged through shared memory) and half of the 72 (path, u) blocks of the tensor
+// product, whose second-layer rows are formed on the fly from the atom's hidden vector in shared memory.
 __global__ void __launch_bounds__(HEAD_THREADS) k_head_trrot(TrRotArgs p) {
-  __shared__ float sWc1[DE][EA];        // [k][o]
-  __shared__ float sWc2[EA][EA];        // [k][o]
-  __shared__ float sWf1[48][48];        // [k][o]
-  __shared__ float sWf2[48][144];       // [k][r]
-  __shared__ float sbf2[144];
+  extern __shared__ __align__(16) float hsm[];
+  float (*sWc1)[EA] = reinterpret_cast<float (*)[EA]>(hsm);                       // [32 k][24 o]
+  float (*sWc2)[EA] = reinterpret_cast<float (*)[EA]>(hsm + DE * EA);             // [24 k][24 o]
+  float (*sWf1)[48] = reinterpret_cast<float (*)[48]>(hsm + DE * EA + EA * EA);   // [48 k][48 o]
+  float (*sWf2)[144] = reinterpret_cast<float (*)[144]>(hsm + DE * EA + EA * EA + 48 * 48);   // [48 k][144 r]
+  float* sbf2 = hsm + DE * EA + EA * EA + 48 * 48 + 48 * 144;                     // [144]
+  float (*sPre)[EA + 1] = reinterpret_cast<float (*)[EA + 1]>(sbf2 + 144);        // [64][25]
+  float (*sFeat)[49] = reinterpret_cast<float (*)[49]>(sbf2 + 144 + HEAD_ATOMS * (EA + 1));
+  float (*sHid)[49] = reinterpret_cast<float (*)[49]>(sbf2 + 144 + HEAD_ATOMS * (EA + 1) + HEAD_ATOMS * 49);
   __shared__ float sred[HEAD_THREADS / 32][16];
   __shared__ float scen[3];
   const int g = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int l0 = p.lig_ptr[g], l1 = p.lig_ptr[g + 1], nl = l1 - l0;
   for (int i = tid; i < DE * EA; i += HEAD_THREADS) sWc1[i / EA][i % EA] = p.Wc1[(i % EA) * (DE + SE) + i / EA];
-  for (int i = tid; i < EA * EA; i += HEAD_THREADS) sWc2[i / EA][i % EA] = p.Wc2[(i % EA) * EA + i / EA];
-  for (int i = tid; i < 48 * 48; i += HEAD_THREADS) sWf1[i / 48][i % 48] = p.Wf1[(i % 48) * 48 + i / 48];
-  for (int i = tid; i < 48 * 144; i += HEAD_THREADS) sWf2[i / 144][i % 144] = p.Wf2[(i % 144) * 48 + i / 144];
+  for (int i = tid; i < EA * EA; i += HEAD_THREADS) { const int o = i / EA, k = i % EA; sWc2[k][o] = p.Wc2[i]; }
+  for (int i = tid; i < 48 * 48; i += HEAD_THREADS) { const int o = i / 48, k = i % 48; sWf1[k][o] = p.Wf1[i]; }
+  for (int i = tid; i < 48 * 144; i += HEAD_THREADS) { const int r = i / 48, k = i % 48; sWf2[k][r] = p.Wf2[i]; }
   for (int i = tid; i < 144; i += HEAD_THREADS) sbf2[i] = p.bf2[i];
   // centroid (build_center_conv_graph, score_model.py:414-416)
   float cx = 0.f, cy = 0.f, cz = 0.f;
@@ -51,80 +59,95 @@ __global__ void __launch_bounds__(HEAD_THREADS) k_head_trrot(TrRotArgs p) {
   }
   __syncthreads();
   const float* tbc = p.tb + ((size_t)g * TB_COUNT + TB_CENTER) * NS;
+  const float pw = sqrtf(3.f / (float)(NS + 2 * NV));
+  const float k1 = pw * 0.5773502691896258f, k2 = pw * 0.4082482904638631f;   // 1/sqrt3, 1/sqrt6
 
   float o12[12];
 #pragma unroll
   for (int i = 0; i < 12; ++i) o12[i] = 0.f;
-  for (int n = l0 + tid; n < l1; n += HEAD_THREADS) {
-    const float* xn = p.x + (size_t)n * D;
-    float nrm;
-    float4 sh = sh_l01(p.lig_pos[n * 3] - scen[0], p.lig_pos[n * 3 + 1] - scen[1], p.lig_pos[n * 3 + 2] - scen[2], &nrm);
-    float s[3] = {sh.y, sh.z, sh.w};
-    // center_edge_embedding
-    float pre[EA];
+  const int al = tid >> 1, half = tid & 1;
+  for (int n0 = l0; n0 < l1; n0 += HEAD_ATOMS) {
+    const int n = n0 + al;
+    const bool on = n < l1;
+    const float* xn = p.x + (size_t)(on ? n : l0) * D;
+    float nrm = 0.f;
+    float4 sh = make_float4(1.f, 0.f, 0.f, 0.f);
+    if (on) sh = sh_l01(p.lig_pos[n * 3] - scen[0], p.lig_pos[n * 3 + 1] - scen[1], p.lig_pos[n * 3 + 2] - scen[2], &nrm);
+    const float s[3] = {sh.y, sh.z, sh.w};
+    __syncthreads();                          // previous pass consumed
+    if (on) {                                 // center_edge_embedding, first layer: 12 outputs per thread
+      float pre[12];
 #pragma unroll
-    for (int o = 0; o < EA; ++o) pre[o] = tbc[o];
-    for (int k = 0; k < DE; ++k) {
-      float gk = smear1(p.sm, nrm, k);
+      for (int i = 0; i < 12; ++i) pre[i] = tbc[12 * half + i];
+      for (int k = 0; k < DE; ++k) {
+        const float gk = smear1(p.sm, nrm, k);
 #pragma unroll
-      for (int o = 0; o < EA; ++o) pre[o] += sWc1[k][o] * gk;
+        for (int i = 0; i < 12; ++i) pre[i] += sWc1[k][12 * half + i] * gk;
+      }
+#pragma unroll
+      for (int i = 0; i < 12; ++i) sPre[al][12 * half + i] = fmaxf(pre[i], 0.f);
     }
-    float feat[48];
+    __syncthreads();
+    if (on) {                                 // second layer + concatenation with the atom's scalars
+      float ft[12];
 #pragma unroll
-    for (int o = 0; o < EA; ++o) feat[o] = p.bc2[o];
+      for (int i = 0; i < 12; ++i) ft[i] = p.bc2[12 * half + i];
 #pragma unroll
-    for (int k = 0; k < EA; ++k) {
-      float r = fmaxf(pre[k], 0.f);
+      for (int k = 0; k < EA; ++k) {
+        const float r = sPre[al][k];
 #pragma unroll
-      for (int o = 0; o < EA; ++o) feat[o] += sWc2[k][o] * r;
+        for (int i = 0; i < 12; ++i) ft[i] += sWc2[k][12 * half + i] * r;
+      }
+#pragma unroll
+      for (int i = 0; i < 12; ++i) { sFeat[al][12 * half + i] = ft[i]; sFeat[al][EA + 12 * half + i] = xn[12 * half + i]; }
     }
+    __syncthreads();
+    if (on) {                                 // final_conv.fc first layer: 24 outputs per thread
+      float h[24];
 #pragma unroll
-    for (int o = 0; o < NS; ++o) feat[EA + o] = xn[o];
-    // final_conv.fc first layer
-    float h[48];
+      for (int i = 0; i < 24; ++i) h[i] = p.bf1[24 * half + i];
+      for (int k = 0; k < 48; ++k) {
+        const float v = sFeat[al][k];
 #pragma unroll
-    for (int o = 0; o < 48; ++o) h[o] = p.bf1[o];
+        for (int i = 0; i < 24; ++i) h[i] += sWf1[k][24 * half + i] * v;
+      }
 #pragma unroll
-    for (int k = 0; k < 48; ++k) {
-      float v = feat[k];
-#pragma unroll
-      for (int o = 0; o < 48; ++o) h[o] += sWf1[k][o] * v;
+      for (int i = 0; i < 24; ++i) sHid[al][24 * half + i] = fmaxf(h[i], 0.f);
     }
+    __syncthreads();
+    if (on) {
+      // second layer rows consumed on the fly by the tensor product; blocks (path, u) of two rows (wv = 0, 1) in the order of
+      // the e3nn instruction list: [0e x 1o -> 1o: 24 | 1o x 0e -> 1o: 6 | 1o x 1o -> 1e: 6 | 1e x 0e -> 1e: 6 | 1e x 1o -> 1o: 6 |
+      // 0o x 1o -> 1e: 24]; this thread takes the blocks of its parity
+      const float* hv = &sHid[al][0];
+      float e1o[2][3] = {{0, 0, 0}, {0, 0, 0}}, e1e[2][3] = {{0, 0, 0}, {0, 0, 0}};
+      for (int blk = half; blk < 72; blk += 2) {
+        float a0 = sbf2[2 * blk], a1 = sbf2[2 * blk + 1];
+#pragma unroll 8
+        for (int k = 0; k < 48; ++k) { const float hk = hv[k]; a0 += sWf2[k][2 * blk] * hk; a1 += sWf2[k][2 * blk + 1] * hk; }
+        float b3[3];
+        bool to1o;
+        if (blk < 24) { const float c = xn[blk] * k1; b3[0] = c * s[0]; b3[1] = c * s[1]; b3[2] = c * s[2]; to1o = true; }
+        else if (blk < 30) { const float* v = xn + 24 + 3 * (blk - 24); const float c = sh.x * k1; b3[0] = c * v[0]; b3[1] = c * v[1]; b3[2] = c * v[2]; to1o = true; }
+        else if (blk < 36) { const float* v = xn + 24 + 3 * (blk - 30);
+          b3[0] = (v[1] * s[2] - v[2] * s[1]) * k2; b3[1] = (v[2] * s[0] - v[0] * s[2]) * k2; b3[2] = (v[0] * s[1] - v[1] * s[0]) * k2; to1o = false; }
+        else if (blk < 42) { const float* v = xn + 42 + 3 * (blk - 36); const float c = sh.x * k1; b3[0] = c * v[0]; b3[1] = c * v[1]; b3[2] = c * v[2]; to1o = false; }
+        else if (blk < 48) { const float* v = xn + 42 + 3 * (blk - 42);
+          b3[0] = (v[1] * s[2] - v[2] * s[1]) * k2; b3[1] = (v[2] * s[0] - v[0] * s[2]) * k2; b3[2] = (v[0] * s[1] - v[1] * s[0]) * k2; to1o = true; }
+        else { const float c = xn[60 + (blk - 48)] * k1; b3[0] = c * s[0]; b3[1] = c * s[1]; b3[2] = c * s[2]; to1o = false; }
+        if (to1o) {
 #pragma unroll
-    for (int o = 0; o < 48; ++o) h[o] = fmaxf(h[o], 0.f);
-    // second layer rows consumed on the fly by the tensor product
-    auto wrow = [&](int r) {
-      float a = sbf2[r];
+          for (int c = 0; c < 3; ++c) { e1o[0][c] += a0 * b3[c]; e1o[1][c] += a1 * b3[c]; }
+        } else {
 #pragma unroll
-      for (int k = 0; k < 48; ++k) a += sWf2[k][r] * h[k];
-      return a;
-    };
-    const float pw = sqrtf(3.f / (float)(NS + 2 * NV));
-    const float k1 = pw * 0.5773502691896258f, k2 = pw * 0.4082482904638631f;   // 1/sqrt3, 1/sqrt6
-    float e1o[2][3] = {{0, 0, 0}, {0, 0, 0}}, e1e[2][3] = {{0, 0, 0}, {0, 0, 0}};
-    int r = 0;
-    for (int u = 0; u < NS; ++u)            // 0e (x) 1o -> 1o
-      for (int wv = 0; wv < 2; ++wv, ++r) { float a = wrow(r) * xn[u] * k1; e1o[wv][0] += a * s[0]; e1o[wv][1] += a * s[1]; e1o[wv][2] += a * s[2]; }
-    for (int u = 0; u < NV; ++u)            // 1o (x) 0e -> 1o
-      for (int wv = 0; wv < 2; ++wv, ++r) { float a = wrow(r) * sh.x * k1; for (int c = 0; c < 3; ++c) e1o[wv][c] += a * xn[24 + 3 * u + c]; }
-    for (int u = 0; u < NV; ++u) {          // 1o (x) 1o -> 1e
-      const float* v = xn + 24 + 3 * u;
-      float cr[3] = {v[1] * s[2] - v[2] * s[1], v[2] * s[0] - v[0] * s[2], v[0] * s[1] - v[1] * s[0]};
-      for (int wv = 0; wv < 2; ++wv, ++r) { float a = wrow(r) * k2; for (int c = 0; c < 3; ++c) e1e[wv][c] += a * cr[c]; }
+          for (int c = 0; c < 3; ++c) { e1e[0][c] += a0 * b3[c]; e1e[1][c] += a1 * b3[c]; }
+        }
+      }
+#pragma unroll
+      for (int wv = 0; wv < 2; ++wv)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { o12[wv * 3 + c] += e1o[wv][c]; o12[6 + wv * 3 + c] += e1e[wv][c]; }
     }
-    for (int u = 0; u < NV; ++u)            // 1e (x) 0e -> 1e
-      for (int wv = 0; wv < 2; ++wv, ++r) { float a = wrow(r) * sh.x * k1; for (int c = 0; c < 3; ++c) e1e[wv][c] += a * xn[42 + 3 * u + c]; }
-    for (int u = 0; u < NV; ++u) {          // 1e (x) 1o -> 1o
-      const float* v = xn + 42 + 3 * u;
-      float cr[3] = {v[1] * s[2] - v[2] * s[1], v[2] * s[0] - v[0] * s[2], v[0] * s[1] - v[1] * s[0]};
-      for (int wv = 0; wv < 2; ++wv, ++r) { float a = wrow(r) * k2; for (int c = 0; c < 3; ++c) e1o[wv][c] += a * cr[c]; }
-    }
-    for (int u = 0; u < NS; ++u)            // 0o (x) 1o -> 1e
-      for (int wv = 0; wv < 2; ++wv, ++r) { float a = wrow(r) * xn[60 + u] * k1; e1e[wv][0] += a * s[0]; e1e[wv][1] += a * s[1]; e1e[wv][2] += a * s[2]; }
-#pragma unroll
-    for (int wv = 0; wv < 2; ++wv)
-#pragma unroll
-      for (int c = 0; c < 3; ++c) { o12[wv * 3 + c] += e1o[wv][c]; o12[6 + wv * 3 + c] += e1e[wv][c]; }
   }
 #pragma unroll
   for (int i = 0; i < 12; ++i) o12[i] = warp_sum(o12[i]);
@@ -171,58 +194,79 @@ struct TorArgs {
   float* tor;
 };
 
-constexpr int TOR_THREADS = 128;   // 4 warps; each warp takes rotatable bonds round-robin, one lane per edge
+constexpr int TOR_THREADS = 128;
+constexpr int TOR_E = 32;          // torch_cluster.radius max_num_neighbors of the bond graph (score_model.py:430)
+constexpr int TOR_FS = HID + 1;    // padded row of the per-edge feature / hidden tiles
 
+// One CTA per graph, its rotatable bonds one after the other, every phase spread over the 128 threads:
+//   1. warp 0 lists the <= 32 atoms within 5 A of the bond midpoint (index order, as torch_cluster.radius does)
+//   2. edge embedding + concatenated features feat[e][72], tensor-product coefficients d[e][blk,u] (4 threads per edge)
+//   3. first layer of tor_bond_conv.fc: H = relu(feat W1^T + b1)                       (thread = edge x 18 columns)
+//   4. re-association (same algebra as the conv layers): A[q][k] = sum_e d[e][q] H[e][k], Dsum[q] = sum_e d[e][q], so the
+//      72 -> 288 second layer runs once per BOND instead of once per edge:
+//      out[w] = sum_u ( W2[r(blk,u,w)] . A[blk,u] + b2[r] Dsum[blk,u] )
+//   5. mean over the edges, batch-norm affine, tor_final_layer.
 __global__ void __launch_bounds__(TOR_THREADS) k_head_tor(TorArgs p) {
   extern __shared__ __align__(16) float tsm[];
-  float* sW1 = tsm;                    // [72 k][72 o]
-  float* sW2 = sW1 + HID * HID;        // [72 k][288 r]
-  float* sWe1 = sW2 + HID * 288;       // [32 k][24 o]
-  float* sWe2 = sWe1 + DE * EA;        // [24 k][24 o]
-  float* sfeat = sWe2 + EA * EA;       // [4 warps][48]
+  float* sW1 = tsm;                         // [72 k][72 o]
+  float* sWe1 = sW1 + HID * HID;            // [32 k][24 o]
+  float* sWe2 = sWe1 + DE * EA;             // [24 k][24 o]
+  float* sFeat = sWe2 + EA * EA;            // [32 e][73]
+  float* sH = sFeat + TOR_E * TOR_FS;       // [32 e][73]
+  float* sPre = sH + TOR_E * TOR_FS;        // [32 e][25]
+  float* sD = sPre + TOR_E * (EA + 1);      // [32 e][12]
+  float* sA = sD + TOR_E * 12;              // [12 q][72 k]
+  float* sDsum = sA + 12 * HID;             // [12]
+  float* sRow = sDsum + 12;                 // [288]
+  float* sOut = sRow + 288;                 // [48]
+  __shared__ int sIdx[TOR_E];
+  __shared__ int sCnt[2];
   const int g = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int b0 = p.rot_ptr[g], b1 = p.rot_ptr[g + 1];
   if (b0 == b1) return;
   const int l0 = p.lig_ptr[g], l1 = p.lig_ptr[g + 1];
-  for (int i = tid; i < HID * HID; i += TOR_THREADS) sW1[i] = p.W1[(i % HID) * HID + i / HID];
-  for (int i = tid; i < HID * 288; i += TOR_THREADS) sW2[i] = p.W2[(i % 288) * HID + i / 288];
-  for (int i = tid; i < DE * EA; i += TOR_THREADS) sWe1[i] = p.We1[(i % EA) * DE + i / EA];
-  for (int i = tid; i < EA * EA; i += TOR_THREADS) sWe2[i] = p.We2[(i % EA) * EA + i / EA];
-  __syncthreads();
+  for (int i = tid; i < HID * HID; i += TOR_THREADS) { const int o = i / HID, k = i % HID; sW1[k * HID + o] = p.W1[i]; }
+  for (int i = tid; i < DE * EA; i += TOR_THREADS) { const int o = i / DE, k = i % DE; sWe1[k * EA + o] = p.We1[i]; }
+  for (int i = tid; i < EA * EA; i += TOR_THREADS) { const int o = i / EA, k = i % EA; sWe2[k * EA + o] = p.We2[i]; }
   const float kpw = sqrtf(1.f / (float)NV) * 0.5773502691896258f;   // path weight sqrt(1/nv) * C(1,1,0) = 1/sqrt3
-  for (int b = b0 + w; b < b1; b += TOR_THREADS / 32) {
+  for (int b = b0; b < b1; ++b) {
     const int u = p.rot_u[b], v = p.rot_v[b];
     const float ux = p.lig_pos[u * 3], uy = p.lig_pos[u * 3 + 1], uz = p.lig_pos[u * 3 + 2];
     const float vx = p.lig_pos[v * 3], vy = p.lig_pos[v * 3 + 1], vz = p.lig_pos[v * 3 + 2];
     const float mx = (ux + vx) / 2.f, my = (uy + vy) / 2.f, mz = (uz + vz) / 2.f;   // bond midpoint (:428)
-    // Y2 of the bond direction (e3nn 'component' normalisation)
-    float bx = vx - ux, by = vy - uy, bz = vz - uz;
-    float bn = fmaxf(sqrtf(bx * bx + by * by + bz * bz), 1e-12f);
-    bx /= bn; by /= bn; bz /= bn;
-    const float s3 = 1.7320508075688772f, s5 = 2.23606797749979f;
-    const float y2[5] = {s5 * s3 * bx * bz, s5 * s3 * bx * by, s5 * (by * by - 0.5f * (bx * bx + bz * bz)), s5 * s3 * by * bz,
-                         s5 * (s3 / 2.f) * (bz * bz - bx * bx)};
-    float acc[48];
-#pragma unroll
-    for (int i = 0; i < 48; ++i) acc[i] = 0.f;
-    int cnt = 0;
-    for (int ab = l0; ab < l1 && cnt < 32; ab += 32) {
-      int a = ab + lane;
-      bool hit = false;
-      float ax = 0, ay = 0, az = 0;
-      if (a < l1) {
-        ax = p.lig_pos[a * 3]; ay = p.lig_pos[a * 3 + 1]; az = p.lig_pos[a * 3 + 2];
-        hit = dist2_unfused(mx, my, mz, ax, ay, az) < p.r2_lig;
+    __syncthreads();                           // weights staged / previous bond finished
+    // ---- 1. neighbour list
+    if (w == 0) {
+      int cnt = 0;
+      for (int ab = l0; ab < l1; ab += 32) {
+        const int a = ab + lane;
+        bool hit = false;
+        if (a < l1) hit = dist2_unfused(mx, my, mz, p.lig_pos[a * 3], p.lig_pos[a * 3 + 1], p.lig_pos[a * 3 + 2]) < p.r2_lig;
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        const int pos = cnt + __popc(m & ((1u << lane) - 1));
+        if (hit && pos < TOR_E) sIdx[pos] = a;
+        cnt += __popc(m);
       }
-      unsigned m = __ballot_sync(0xffffffffu, hit);
-      bool keep = hit && (cnt + __popc(m & ((1u << lane) - 1)) < 32);   // torch_cluster.radius max_num_neighbors=32
-      cnt += __popc(m);
-      if (keep) {
-        const float* xa = p.x + (size_t)a * D;
-        const float* xu = p.x + (size_t)u * D;
-        const float* xv = p.x + (size_t)v * D;
-        float nrm;
-        float4 sh = sh_l01(ax - mx, ay - my, az - mz, &nrm);
+      if (lane == 0) sCnt[0] = min(cnt, TOR_E);
+    }
+    __syncthreads();
+    const int ne = sCnt[0];
+    // ---- 2. per edge: harmonics / filter / coefficients (sub-thread 0), first embedding layer (6 outputs per sub-thread)
+    const int e = tid >> 2, sub = tid & 3;
+    float nrm = 0.f;
+    int a = 0;
+    if (e < ne) {
+      a = sIdx[e];
+      const float ax = p.lig_pos[a * 3], ay = p.lig_pos[a * 3 + 1], az = p.lig_pos[a * 3 + 2];
+      const float4 sh = sh_l01(ax - mx, ay - my, az - mz, &nrm);
+      if (sub == 0) {
+        // Y2 of the bond direction (e3nn 'component' normalisation)
+        float bx = vx - ux, by = vy - uy, bz = vz - uz;
+        const float bn = fmaxf(sqrtf(bx * bx + by * by + bz * bz), 1e-12f);
+        bx /= bn; by /= bn; bz /= bn;
+        const float s3 = 1.7320508075688772f, s5 = 2.23606797749979f;
+        const float y2[5] = {s5 * s3 * bx * bz, s5 * s3 * bx * by, s5 * (by * by - 0.5f * (bx * bx + bz * bz)), s5 * s3 * by * bz,
+                             s5 * (s3 / 2.f) * (bz * bz - bx * bx)};
         const float s[3] = {sh.y, sh.z, sh.w};
         // filter = 1o block of FullTensorProduct(sh, Y2): sqrt3 * C121[i][j][k] s_i Y2_j   (score_model.py:296)
         const float ca = 0.31622776601683794f, cb = 0.18257418583505536f;   // 1/sqrt10, 1/sqrt30
@@ -230,73 +274,121 @@ __global__ void __launch_bounds__(TOR_THREADS) k_head_tor(TorArgs p) {
         f[0] = s3 * (ca * (s[1] * y2[1] + s[2] * y2[0]) - ca * s[0] * y2[4] - cb * s[0] * y2[2]);
         f[1] = s3 * (ca * (s[0] * y2[1] + s[2] * y2[3]) + 2.f * cb * s[1] * y2[2]);
         f[2] = s3 * (ca * (s[0] * y2[0] + s[1] * y2[3] + s[2] * y2[4]) - cb * s[2] * y2[2]);
-        // final_edge_embedding on the smeared distance
-        float pre[EA];
+        const float* xa = p.x + (size_t)a * D;
 #pragma unroll
-        for (int o = 0; o < EA; ++o) pre[o] = p.be1[o];
-        for (int k = 0; k < DE; ++k) {
-          float gk = smear1(p.sm, nrm, k);
-#pragma unroll
-          for (int o = 0; o < EA; ++o) pre[o] += sWe1[k * EA + o] * gk;
-        }
-        float feat[HID];
-#pragma unroll
-        for (int o = 0; o < EA; ++o) feat[o] = p.be2[o];
-#pragma unroll
-        for (int k = 0; k < EA; ++k) {
-          float r = fmaxf(pre[k], 0.f);
-#pragma unroll
-          for (int o = 0; o < EA; ++o) feat[o] += sWe2[k * EA + o] * r;
-        }
-#pragma unroll
-        for (int o = 0; o < NS; ++o) { feat[EA + o] = xa[o]; feat[EA + NS + o] = xu[o] + xv[o]; }
-        float h[HID];
-#pragma unroll
-        for (int o = 0; o < HID; ++o) h[o] = p.b1[o];
-        for (int k = 0; k < HID; ++k) {
-          float fv = feat[k];
-#pragma unroll
-          for (int o = 0; o < HID; ++o) h[o] += sW1[k * HID + o] * fv;
-        }
-#pragma unroll
-        for (int o = 0; o < HID; ++o) h[o] = fmaxf(h[o], 0.f);
-        // tensor product: out0e[w] = k * sum_u W[u*24+w] (x1o[u].f);  out0o[w] = k * sum_u W[144+u*24+w] (x1e[u].f)
-        for (int blk = 0; blk < 2; ++blk) {
-          for (int uu = 0; uu < NV; ++uu) {
-            const float* xv3 = xa + (blk == 0 ? 24 : 42) + 3 * uu;
-            float d = (xv3[0] * f[0] + xv3[1] * f[1] + xv3[2] * f[2]) * kpw;
-            for (int wv = 0; wv < NS; ++wv) {
-              int r = blk * (NV * NS) + uu * NS + wv;
-              float a = p.b2[r];
-              for (int k = 0; k < HID; ++k) a += sW2[k * 288 + r] * h[k];
-              acc[(blk == 0 ? NS : 0) + wv] += a * d;    // output order: 24 x 0o then 24 x 0e (score_model.py:156)
-            }
-          }
+        for (int q = 0; q < 12; ++q) {         // q = blk * 6 + u: x1o[u] . f (blk 0), x1e[u] . f (blk 1)
+          const float* x3 = xa + 24 + 3 * q;   // x1o at 24..41, x1e at 42..59
+          sD[e * 12 + q] = (x3[0] * f[0] + x3[1] * f[1] + x3[2] * f[2]) * kpw;
         }
       }
-    }
-    cnt = min(cnt, 32);
+      float pre[6];
 #pragma unroll
-    for (int i = 0; i < 48; ++i) acc[i] = warp_sum(acc[i]);
-    if (lane == 0)
-      for (int i = 0; i < 48; ++i) sfeat[w * 48 + i] = (acc[i] / (float)max(cnt, 1)) * p.bn_scale[i] + p.bn_shift[i];
-    __syncwarp();
-    // tor_final_layer: Linear(48->24, no bias) . tanh . Linear(24->1, no bias)
-    float part = 0.f;
-    if (lane < NS) {
-      float a = 0.f;
-      for (int k = 0; k < 48; ++k) a += p.Wt1[lane * 48 + k] * sfeat[w * 48 + k];
-      part = p.Wt2[lane] * tanhf(a);
+      for (int i = 0; i < 6; ++i) pre[i] = p.be1[6 * sub + i];
+      for (int k = 0; k < DE; ++k) {
+        const float gk = smear1(p.sm, nrm, k);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) pre[i] += sWe1[k * EA + 6 * sub + i] * gk;
+      }
+#pragma unroll
+      for (int i = 0; i < 6; ++i) sPre[e * (EA + 1) + 6 * sub + i] = fmaxf(pre[i], 0.f);
     }
-    part = warp_sum(part);
-    if (lane == 0) p.tor[b] = part * p.tor_scale[g];
-    __syncwarp();
+    __syncthreads();
+    if (e < ne) {
+      float ft[6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) ft[i] = p.be2[6 * sub + i];
+#pragma unroll
+      for (int k = 0; k < EA; ++k) {
+        const float r = sPre[e * (EA + 1) + k];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) ft[i] += sWe2[k * EA + 6 * sub + i] * r;
+      }
+      const float* xa = p.x + (size_t)a * D;
+      const float* xu = p.x + (size_t)u * D;
+      const float* xv = p.x + (size_t)v * D;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const int o = 6 * sub + i;
+        sFeat[e * TOR_FS + o] = ft[i];
+        sFeat[e * TOR_FS + EA + o] = xa[o];
+        sFeat[e * TOR_FS + EA + NS + o] = xu[o] + xv[o];
+      }
+    }
+    __syncthreads();
+    // ---- 3. H = relu(feat W1^T + b1): thread = (edge, 18 of the 72 columns)
+    if (e < ne) {
+      float h[18];
+#pragma unroll
+      for (int i = 0; i < 18; ++i) h[i] = p.b1[18 * sub + i];
+      for (int k = 0; k < HID; ++k) {
+        const float fv = sFeat[e * TOR_FS + k];
+        const float* wr = sW1 + k * HID + 18 * sub;
+#pragma unroll
+        for (int i = 0; i < 18; ++i) h[i] += wr[i] * fv;
+      }
+#pragma unroll
+      for (int i = 0; i < 18; ++i) sH[e * TOR_FS + 18 * sub + i] = fmaxf(h[i], 0.f);
+    }
+    __syncthreads();
+    // ---- 4. A[q][k] = sum_e d[e][q] H[e][k], Dsum[q]; then the 288 second-layer rows against A
+    for (int idx = tid; idx < 12 * HID; idx += TOR_THREADS) {
+      const int q = idx / HID, k = idx % HID;
+      float acc = 0.f;
+      for (int ee = 0; ee < ne; ++ee) acc += sD[ee * 12 + q] * sH[ee * TOR_FS + k];
+      sA[idx] = acc;
+    }
+    if (tid < 12) {
+      float acc = 0.f;
+      for (int ee = 0; ee < ne; ++ee) acc += sD[ee * 12 + tid];
+      sDsum[tid] = acc;
+    }
+    __syncthreads();
+    for (int r = tid; r < 288; r += TOR_THREADS) {   // r = blk * 144 + u * 24 + w
+      const int q = r / NS;
+      const float4* wr = reinterpret_cast<const float4*>(p.W2 + (size_t)r * HID);
+      const float* ar = sA + q * HID;
+      float acc = p.b2[r] * sDsum[q];
+#pragma unroll
+      for (int k4 = 0; k4 < HID / 4; ++k4) {
+        const float4 wv = __ldg(wr + k4);
+        acc += wv.x * ar[4 * k4] + wv.y * ar[4 * k4 + 1] + wv.z * ar[4 * k4 + 2] + wv.w * ar[4 * k4 + 3];
+      }
+      sRow[r] = acc;
+    }
+    __syncthreads();
+    // ---- 5. sum over u in a fixed order, mean over edges, batch norm; output order: 24 x 0o then 24 x 0e (score_model.py:156)
+    if (tid < 48) {
+      const int blk = tid < NS ? 1 : 0, wv = tid % NS;
+      float acc = 0.f;
+      for (int uu = 0; uu < NV; ++uu) acc += sRow[blk * 144 + uu * NS + wv];
+      sOut[tid] = (acc / (float)max(ne, 1)) * p.bn_scale[tid] + p.bn_shift[tid];
+    }
+    __syncthreads();
+    // tor_final_layer: Linear(48->24, no bias) . tanh . Linear(24->1, no bias)
+    if (w == 0) {
+      float part = 0.f;
+      if (lane < NS) {
+        float acc = 0.f;
+        for (int k = 0; k < 48; ++k) acc += p.Wt1[lane * 48 + k] * sOut[k];
+        part = p.Wt2[lane] * tanhf(acc);
+      }
+      part = warp_sum(part);
+      if (lane == 0) p.tor[b] = part * p.tor_scale[g];
+    }
   }
 }
 
-size_t tor_smem_bytes() { return (size_t)(HID * HID + HID * 288 + DE * EA + EA * EA + 4 * 48) * sizeof(float); }
+size_t tor_smem_bytes() {
+  return (size_t)(HID * HID + DE * EA + EA * EA + 2 * TOR_E * TOR_FS + TOR_E * (EA + 1) + TOR_E * 12 + 12 * HID + 12 + 288 + 48) * sizeof(float);
+}
+
+size_t trrot_smem_bytes() {
+  return (size_t)(DE * EA + EA * EA + 48 * 48 + 48 * 144 + 144 + HEAD_ATOMS * (EA + 1) + 2 * HEAD_ATOMS * 49) * sizeof(float);
+}
 
 cudaError_t heads_configure() {
+  cudaError_t e = cudaFuncSetAttribute(k_head_trrot, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trrot_smem_bytes());
+  if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(k_head_tor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tor_smem_bytes());
 }
 
@@ -315,7 +407,7 @@ void launch_head_trrot(DdkCtx* c, const float* lig_pos, const float* x, const Dd
   p.tr_sigma = in->tr_sigma; p.rot_scale = in->rot_scale;
   p.tr = tr; p.rot = rot;
   LaunchScope ls(c, PC_HEADS, st);
-  k_head_trrot<<<c->B, HEAD_THREADS, 0, st>>>(p);
+  k_head_trrot<<<c->B, HEAD_THREADS, trrot_smem_bytes(), st>>>(p);
 }
 
 void launch_head_tor(DdkCtx* c, const float* lig_pos, const float* x, const DdkStepInputs* in, float* tor, cudaStream_t st) {

@@ -9,6 +9,8 @@
 //   k_node_proj    : per node, the x_src / x_dst parts of the first MLP layer (W1[:,24:48] x_s + b1, W1[:,48:72] x_d)
 //   k_conv_accum   : one CTA per (node, group) segment: h_e, basis_e, rank-1 updates of A in registers -> scratch
 //   k_conv_contract: per tile of 32 nodes: A (*) W2p for both groups, mean, batch-norm affine, residual
+#include <algorithm>
+
 #include "ddk_conv.cuh"
 
 namespace ddk {
@@ -35,47 +37,56 @@ __global__ void __launch_bounds__(288) k_node_proj(ProjArgs p) {
   __shared__ float sW[4][NS][HID];     // [slot][k][j]
   __shared__ float sB[2][HID];
   __shared__ float sx[PROJ_NODES][NS];
-  int nblk_l = (p.NL + PROJ_NODES - 1) / PROJ_NODES;
-  bool lig = (int)blockIdx.x < nblk_l;
-  int n0 = lig ? blockIdx.x * PROJ_NODES : (blockIdx.x - nblk_l) * PROJ_NODES;
-  int nn = min(PROJ_NODES, (lig ? p.NL : p.NR) - n0);
+  // persistent blocks: the first gridDim.x / 2 (rounded by node share) walk the ligand tiles, the others the receptor tiles,
+  // so the 27 KB of weights are staged once per block instead of once per 16 nodes
+  const int nblk_l = (p.NL + PROJ_NODES - 1) / PROJ_NODES, nblk_r = (p.NR + PROJ_NODES - 1) / PROJ_NODES;
+  int gl = (int)(((long long)gridDim.x * nblk_l + nblk_l + nblk_r - 1) / (nblk_l + nblk_r));
+  gl = max(1, min(gl, (int)gridDim.x - 1));
+  const bool lig = (int)blockIdx.x < gl;
+  const int tile0 = lig ? blockIdx.x : blockIdx.x - gl, tstep = lig ? gl : (int)gridDim.x - gl, ntile = lig ? nblk_l : nblk_r;
   const int gs[2][4] = {{0, 1, 0, 3}, {2, 3, 2, 1}};
   const int* g4 = gs[lig ? 0 : 1];
   for (int i = threadIdx.x; i < 4 * NS * HID; i += blockDim.x) {
-    int s = i / (NS * HID), k = (i / HID) % NS, j = i % HID;
+    // coalesced over the weight rows: i -> (slot s, hidden unit j, input k)
+    int s = i / (NS * HID), j = (i / NS) % HID, k = i % NS;
     int col = (s < 2 ? NS : 2 * NS) + k;
     sW[s][k][j] = p.W1[g4[s]][j * HID + col];
   }
   for (int i = threadIdx.x; i < 2 * HID; i += blockDim.x) sB[i / HID][i % HID] = p.b1[g4[i / HID]][i % HID];
-  for (int i = threadIdx.x; i < nn * NS; i += blockDim.x) {
-    int q = i / NS, k = i % NS, n = n0 + q;
-    float v;
+  for (int tile = tile0; tile < ntile; tile += tstep) {
+    const int n0 = tile * PROJ_NODES;
+    const int nn = min(PROJ_NODES, (lig ? p.NL : p.NR) - n0);
+    __syncthreads();                      // weights staged / previous tile consumed
+    for (int i = threadIdx.x; i < nn * NS; i += blockDim.x) {
+      int q = i / NS, k = i % NS, n = n0 + q;
+      float v;
+      if (FIRST) {
+        int g = lig ? p.lig_graph[n] : p.rec_graph[n];
+        const float* st = lig ? p.lig_static : p.rec_static;
+        const float* un = lig ? p.lig_uncond : p.rec_uncond;
+        v = st[n * NS + k] + p.tb[((size_t)g * TB_COUNT + (lig ? TB_LIG_NODE : TB_REC_NODE)) * NS + k];
+        if (un != nullptr) v += un[n] * p.uncond_emb[(lig ? 0 : 1) * NS + k];
+      } else {
+        v = p.x_in[(size_t)((lig ? 0 : p.NL) + n) * D + k];
+      }
+      sx[q][k] = v;
+    }
+    __syncthreads();
     if (FIRST) {
-      int g = lig ? p.lig_graph[n] : p.rec_graph[n];
-      const float* st = lig ? p.lig_static : p.rec_static;
-      const float* un = lig ? p.lig_uncond : p.rec_uncond;
-      v = st[n * NS + k] + p.tb[((size_t)g * TB_COUNT + (lig ? TB_LIG_NODE : TB_REC_NODE)) * NS + k];
-      if (un != nullptr) v += un[n] * p.uncond_emb[(lig ? 0 : 1) * NS + k];
-    } else {
-      v = p.x_in[(size_t)((lig ? 0 : p.NL) + n) * D + k];
+      for (int i = threadIdx.x; i < nn * D; i += blockDim.x) {
+        int q = i / D, f = i % D;
+        p.x0_out[(size_t)((lig ? 0 : p.NL) + n0 + q) * D + f] = f < NS ? sx[q][f] : 0.f;
+      }
     }
-    sx[q][k] = v;
-  }
-  __syncthreads();
-  if (FIRST) {
-    for (int i = threadIdx.x; i < nn * D; i += blockDim.x) {
-      int q = i / D, f = i % D;
-      p.x0_out[(size_t)((lig ? 0 : p.NL) + n0 + q) * D + f] = f < NS ? sx[q][f] : 0.f;
-    }
-  }
-  int s = threadIdx.x / HID, j = threadIdx.x % HID;   // 288 threads = 4 slots x 72
-  for (int q = 0; q < nn; ++q) {
-    float acc = s < 2 ? sB[s][j] : 0.f;
+    int s = threadIdx.x / HID, j = threadIdx.x % HID;   // 288 threads = 4 slots x 72
+    for (int q = 0; q < nn; ++q) {
+      float acc = s < 2 ? sB[s][j] : 0.f;
 #pragma unroll
-    for (int k = 0; k < NS; ++k) acc += sW[s][k][j] * sx[q][k];
-    const size_t node = (size_t)((lig ? 0 : p.NL) + n0 + q);
-    if (p.sliced) p.proj[(((size_t)(j / p.sliced) * p.N + node) * 4 + s) * p.sliced + (j % p.sliced)] = acc;
-    else p.proj[(node * 4 + s) * HID + j] = acc;
+      for (int k = 0; k < NS; ++k) acc += sW[s][k][j] * sx[q][k];
+      const size_t node = (size_t)((lig ? 0 : p.NL) + n0 + q);
+      if (p.sliced) p.proj[(((size_t)(j / p.sliced) * p.N + node) * 4 + s) * p.sliced + (j % p.sliced)] = acc;
+      else p.proj[(node * 4 + s) * HID + j] = acc;
+    }
   }
 }
 
@@ -385,6 +396,7 @@ void launch_node_proj(DdkCtx* c, int layer, const float* x_in, float* x0_out, cu
   p.proj = ptr<float>(c->b_proj);
   p.sliced = 0; p.N = c->N;
   int blocks = (c->NL + PROJ_NODES - 1) / PROJ_NODES + (c->NR + PROJ_NODES - 1) / PROJ_NODES;
+  blocks = std::max(2, std::min(blocks, 4 * c->sm_count));   // persistent blocks, see k_node_proj
   LaunchScope ls(c, PC_PROJ, st);
   if (x0_out != nullptr) k_node_proj<true><<<blocks, 288, 0, st>>>(p);
   else k_node_proj<false><<<blocks, 288, 0, st>>>(p);

@@ -75,6 +75,7 @@ struct F3Cfg {
   static constexpr int J = f3_J(LV);
   static constexpr int NSLV = HID / J;
   static constexpr int AST = J + 1;          // row stride of an A slot: J hidden units + the sum-of-basis (bias) column
+  static constexpr int KC = 8;               // edges per gather chunk of a warp pair (16 was measured slower at every level)
   static constexpr bool G0_VEC = LV == 1 || LV == 2;     // the first mixed group has vector lanes
   static constexpr bool HAS_M = LV == 3;                 // second mixed group
   static constexpr bool HAS_V0 = LV >= 1, HAS_G = LV == 2;
@@ -95,9 +96,9 @@ struct F3Smem {
   alignas(16) float Wb[F3Cfg<LV>::W];                        // packed second-layer bias (used by slice 0 only)
   alignas(16) float As[F3_ACC][F3Cfg<LV>::U * F3Cfg<LV>::AST];   // one slot per accumulate warp pair: [u][jj | bsum]
   struct Stage {
-    alignas(16) float X[2][KC3][F3Cfg<LV>::DINP];
-    alignas(16) float SH[2][KC3][4];
-    alignas(16) float H[2][KC3][F3Cfg<LV>::J];
+    alignas(16) float X[2][F3Cfg<LV>::KC][F3Cfg<LV>::DINP];
+    alignas(16) float SH[2][F3Cfg<LV>::KC][4];
+    alignas(16) float H[2][F3Cfg<LV>::KC][F3Cfg<LV>::J];
   } st[F3_ACC];
   alignas(16) float tile[F3_CON][F3_ACC][D];                 // per contraction warp partial outputs of a batch
   alignas(8) unsigned long long bar_full, bar_empty;         // mbarriers, see f3_mbar_*
@@ -292,13 +293,14 @@ __device__ __forceinline__ void f3_acc_task(const F3Args& p, F3Smem<LV>& S, cons
                                             const int idx0, const int nseg, const int pr, const int lane, int& nflush) {
   using Cfg = F3Cfg<LV>;
   constexpr int NSLOT = Cfg::NSLOT, DINP = Cfg::DINP, J = Cfg::J, AST = Cfg::AST, XQ = Cfg::XQ;
-  constexpr int XBUF = KC3 * DINP, SBUF = KC3 * 4, HBUF = KC3 * J;
+  constexpr int KC = Cfg::KC, GSUBS = 64 / KC;      // edges per chunk; 16-byte sub-pieces copied side by side per edge
+  constexpr int XBUF = KC * DINP, SBUF = KC * 4, HBUF = KC * J;
   typename F3Smem<LV>::Stage& T = S.st[pr];
   const int nb = (nseg + F3_ACC - 1) / F3_ACC;
   const int4* wl = p.glist + p.goff[g] + idx0;
   const float* hsr = p.hs + (size_t)r * p.LT * J;   // slice r of the hidden units, list order
   const int pl = HALF * 32 + lane;                  // thread of the pair
-  const int ge = pl & 7, gsub = pl >> 3;            // gather role: edge, 16-byte sub-piece (0..7)
+  const int ge = pl % KC, gsub = pl / KC;           // gather role: edge, 16-byte sub-piece (0..GSUBS-1)
 
   f32x2 acc[NSLOT][J / 2];
   float bs[NSLOT];
@@ -328,7 +330,7 @@ __device__ __forceinline__ void f3_acc_task(const F3Args& p, F3Smem<LV>& S, cons
       pre = (sn < nseg) ? wl[sn] : make_int4(-1, 0, 0, 0);
     }
     d.pos = sbase + c0;
-    d.kc = min(KC3, n - c0);
+    d.kc = min(KC, n - c0);
     d.seg = seg;
     c0 += d.kc;
     d.flags = CD_VALID | (bi > 0 ? CD_NOT_FIRST_BATCH : 0);
@@ -340,7 +342,7 @@ __device__ __forceinline__ void f3_acc_task(const F3Args& p, F3Smem<LV>& S, cons
     if (lane < d.kc) e = p.seg_list[d.pos + lane];
     return e;
   };
-  // the 64 threads of the pair copy fixed 16-byte pieces (q = gsub + 8 i) of the destination features of edge ge; the
+  // the 64 threads of the pair copy fixed 16-byte pieces (q = gsub + GSUBS i) of the destination features of edge ge; the
   // chunk's hidden-unit slice is one contiguous block of kc * J floats (copied by the second warp)
   auto gather = [&](const ChunkD& d, const int2 ent, const int buf) {
     if (d.kc > 0) {
@@ -350,13 +352,13 @@ __device__ __forceinline__ void f3_acc_task(const F3Args& p, F3Smem<LV>& S, cons
         const float* xs = p.x + (size_t)dst * D + 4 * gsub;
         float* xd = &T.X[buf][ge][4 * gsub];
 #pragma unroll
-        for (int i = 0; i < (XQ + 7) / 8; ++i)
-          if (gsub + 8 * i < XQ) f3_cp16(xd + 32 * i, xs + 32 * i);
+        for (int i = 0; i < (XQ + GSUBS - 1) / GSUBS; ++i)
+          if (gsub + GSUBS * i < XQ) f3_cp16(xd + 4 * GSUBS * i, xs + 4 * GSUBS * i);
         if (gsub == 0) f3_cp16(&T.SH[buf][ge][0], p.sh_pool + slot);
       }
       if (HALF == 1) {
 #pragma unroll
-        for (int i = 0; i < (KC3 * J / 4 + 31) / 32; ++i)
+        for (int i = 0; i < (KC * J / 4 + 31) / 32; ++i)
           if (lane + 32 * i < d.kc * (J / 4))
             f3_cp16(&T.H[buf][0][0] + 4 * (lane + 32 * i), hsr + (size_t)d.pos * J + 4 * (lane + 32 * i));
       }
@@ -385,9 +387,12 @@ __device__ __forceinline__ void f3_acc_task(const F3Args& p, F3Smem<LV>& S, cons
       const float* hb = &T.H[0][0][0] + buf * HBUF;
       const float* sb = &T.SH[0][0][0] + buf * SBUF;
       const float* xb = &T.X[0][0][0] + buf * XBUF;
-      if (cd0.kc == KC3) {
+      if (cd0.kc == KC) {
 #pragma unroll
-        for (int e = 0; e < KC3; ++e) f3_edge<LV, BIAS, HALF>(acc, bs, LB, hb + e * J, sb + e * 4, xb + e * DINP);
+        for (int e = 0; e < KC; ++e) f3_edge<LV, BIAS, HALF>(acc, bs, LB, hb + e * J, sb + e * 4, xb + e * DINP);
+      } else if (KC > 8 && cd0.kc == 8) {           // the 8-edge tail of the 24-edge receptor-contact segments
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f3_edge<LV, BIAS, HALF>(acc, bs, LB, hb + e * J, sb + e * 4, xb + e * DINP);
       } else {
 #pragma unroll 1
         for (int e = 0; e < cd0.kc; ++e) f3_edge<LV, BIAS, HALF>(acc, bs, LB, hb + e * J, sb + e * 4, xb + e * DINP);

@@ -123,9 +123,10 @@ int ddk_create(const DdkConfig* cfg, const float* weights_h, size_t n_floats, co
   if ((e = cudaMalloc(&c->w, n_floats * sizeof(float))) != cudaSuccess) return bail("cudaMalloc(weights)", e);
   if ((e = cudaMemcpy(c->w, weights_h, n_floats * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess)
     return bail("cudaMemcpy(weights)", e);
-  if ((e = cudaMalloc(&c->b_edge_total.p, 96)) != cudaSuccess) return bail("cudaMalloc(counter)", e);
-  c->b_edge_total.bytes = 96;   // cumulative: [0] dynamic edges, [1] non-empty segments, [2..6] edges / [7..11] segments per work list
-  if ((e = cudaMemset(c->b_edge_total.p, 0, 96)) != cudaSuccess) return bail("cudaMemset(counter)", e);
+  const size_t ncounter = (2 + 2 * F3_NLIST) * sizeof(unsigned long long);
+  if ((e = cudaMalloc(&c->b_edge_total.p, ncounter)) != cudaSuccess) return bail("cudaMalloc(counter)", e);
+  c->b_edge_total.bytes = ncounter;   // cumulative: [0] dynamic edges, [1] non-empty segments, then edges / segments per work list
+  if ((e = cudaMemset(c->b_edge_total.p, 0, ncounter)) != cudaSuccess) return bail("cudaMemset(counter)", e);
   if ((e = conv_configure()) != cudaSuccess) return bail("cudaFuncSetAttribute(conv)", e);
   if ((e = heads_configure()) != cudaSuccess) return bail("cudaFuncSetAttribute(heads)", e);
   if ((e = conv2_configure()) != cudaSuccess) return bail("cudaFuncSetAttribute(conv2)", e);
@@ -187,7 +188,7 @@ int ddk_destroy(DdkCtx* c) {
                 &c->b_lr_off, &c->b_seg_base, &c->b_seg_static, &c->b_seg_cnt, &c->b_seg_list, &c->b_seg_order,
                 &c->b_seg_sidx, &c->b_lig_static, &c->b_rec_static, &c->b_rr_pre, &c->b_ea_pool, &c->b_sh_pool, &c->b_tb,
                 &c->b_xa, &c->b_xb, &c->b_proj, &c->b_A, &c->b_Bsum, &c->b_tr, &c->b_rot, &c->b_tor, &c->b_pos, &c->b_step, &c->b_edge_total, &c->b_work, &c->b_nwork,
-                &c->b_glist, &c->b_gcnt, &c->b_counters, &c->b_part, &c->b_hs};
+                &c->b_glist, &c->b_gcnt, &c->b_counters, &c->b_part, &c->b_hs, &c->b_need};
   for (Buf* b : all) free_buf(*b);
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   if (c->w) cudaFree(c->w);
@@ -342,7 +343,9 @@ int ddk_set_batch(DdkCtx* c, const DdkBatch* b, void* stream) {
     EN(c->b_A, (size_t)max_chunk_segs * seg_bytes); EN(c->b_Bsum, (size_t)max_chunk_segs * Umax * 4);
     EN(c->b_work, (size_t)nsegs * 16); EN(c->b_nwork, (size_t)c->chunks.size() * 4);
   } else {
-    EN(c->b_glist, ((size_t)nsegs + NR) * 16); EN(c->b_gcnt, 5 * 4); EN(c->b_counters, 4 * NSL_MAX * 4);
+    c->nhop = std::min(F3_MAXHOP, c->cfg.num_conv_layers - 1);
+    EN(c->b_glist, ((size_t)nsegs + (size_t)c->nhop * NR) * 16); EN(c->b_gcnt, F3_NLIST * 4);
+    EN(c->b_need, (size_t)std::max(1, c->nhop) * NR); EN(c->b_counters, 4 * NSL_MAX * 4);
     EN(c->b_part, (size_t)nsegs * NSL_MAX * D * 4);
     EN(c->b_hs, (size_t)std::max<int64_t>(total, 1) * HID * 4);
   }
@@ -364,14 +367,14 @@ static int run_embed(DdkCtx* c, const float* lig_pos, const DdkStepInputs* in, c
   launch_build_lists(c, lig_pos, in->cross_cutoff, st);
   launch_edge_features(c, lig_pos, st);
   if (c->conv_v2) launch_build_worklist(c, st);
-  else if (!c->conv_v1) launch_build_group_lists(c, st);
+  else if (!c->conv_v1) launch_build_group_lists(c, st, heads_only);
   float* xa = ptr<float>(c->b_xa);
   float* xb = ptr<float>(c->b_xb);
   launch_node_proj(c, 0, nullptr, xa, st);
   float* xin = xa; float* xout = xb;
   for (int l = 0; l < c->cfg.num_conv_layers; ++l) {
     const int L = c->cfg.num_conv_layers;
-    launch_conv_layer(c, l, xin, xout, st, !heads_only ? CONV_ALL : (l == L - 1 ? CONV_LIG : (l == L - 2 ? CONV_NEEDED : CONV_ALL)));
+    launch_conv_layer(c, l, xin, xout, st, !heads_only ? CONV_ALL : (l == L - 1 ? CONV_LIG : CONV_NEEDED + (L - 2 - l)));
     if (l + 1 < c->cfg.num_conv_layers) launch_node_proj(c, l + 1, xout, nullptr, st);
     std::swap(xin, xout);
   }
@@ -531,13 +534,14 @@ int64_t ddk_segment_total(DdkCtx* c) {
   return (int64_t)v;
 }
 
-int ddk_group_totals(DdkCtx* c, int64_t* edges5, int64_t* segments5) {
-  if (!c || !edges5 || !segments5) return DDK_ERR_INVALID;
+int ddk_group_totals(DdkCtx* c, int64_t* edges, int64_t* segments) {
+  if (!c || !edges || !segments) return DDK_ERR_INVALID;
   cudaSetDevice(c->device);
-  unsigned long long v[12];
+  unsigned long long v[2 + 2 * F3_NLIST];
   DDK_CUDA_TRY(c, cudaDeviceSynchronize());
   DDK_CUDA_TRY(c, cudaMemcpy(v, c->b_edge_total.p, sizeof(v), cudaMemcpyDeviceToHost));
-  for (int g = 0; g < 5; ++g) { edges5[g] = (int64_t)v[2 + g]; segments5[g] = (int64_t)v[7 + g]; }
+  static_assert(F3_NLIST == DDK_WORK_LISTS, "work list count");
+  for (int g = 0; g < F3_NLIST; ++g) { edges[g] = (int64_t)v[2 + g]; segments[g] = (int64_t)v[2 + F3_NLIST + g]; }
   return DDK_OK;
 }
 

@@ -136,17 +136,31 @@ struct F3Args {
 // segments are claimed first.  The order inside a bucket is whatever the shared-memory cursors hand out; no result
 // depends on it (every (segment, slice) partial is produced by one warp pair in a fixed order).
 constexpr int GL_BUCKETS = 64;
+
+// need[0][r] = residue r has a cross edge;  need[h][r] = need[h-1][r] or r is a receptor-contact neighbour of such a residue
+__global__ void k_need_hop0(int NL, int NR, const int* __restrict__ seg_cnt, unsigned char* __restrict__ need) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < NR) need[r] = seg_cnt[2 * (NL + r) + 1] > 0;
+}
+__global__ void k_need_expand(int ER, const int* __restrict__ rr_src, const int* __restrict__ rr_dst,
+                              const unsigned char* __restrict__ prev, unsigned char* __restrict__ next) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < ER && prev[rr_src[e]]) { next[rr_src[e]] = 1; next[rr_dst[e]] = 1; }   // every write stores 1: no race that matters
+}
+
+// blocks 0..3: the four edge groups; block 4 + h: group 2 restricted to the residues of need[h]
 __global__ void __launch_bounds__(1024) k_build_group_lists(int NL, int NR, const int* __restrict__ seg_cnt,
                                                             const int* __restrict__ seg_base, int4* __restrict__ glist,
-                                                            int* __restrict__ gcnt, unsigned long long* __restrict__ seg_total) {
+                                                            int* __restrict__ gcnt, unsigned long long* __restrict__ counters,
+                                                            const unsigned char* __restrict__ need) {
   __shared__ int hist[GL_BUCKETS], cursor[GL_BUCKETS];
   __shared__ int nedge;
-  // block 4 = group 2 restricted to the residues that have at least one cross edge (non-empty group-3 segment): the only
-  // receptor nodes whose features the last conv layer before the score heads reads
-  const bool filt = blockIdx.x == 4;
-  const int g = filt ? 2 : blockIdx.x;
+  const int li = blockIdx.x;                       // work list
+  const bool filt = li >= 4;
+  const int g = filt ? 2 : li;
   const int nn = g < 2 ? NL : NR;
-  const int off = blockIdx.x == 0 ? 0 : (blockIdx.x == 1 ? NL : (blockIdx.x == 2 ? 2 * NL : (blockIdx.x == 3 ? 2 * NL + NR : 2 * NL + 2 * NR)));
+  const int off = li == 0 ? 0 : (li == 1 ? NL : (li == 2 ? 2 * NL : (li == 3 ? 2 * NL + NR : 2 * NL + 2 * NR + (li - 4) * NR)));
+  const unsigned char* nd = filt ? need + (size_t)(li - 4) * NR : nullptr;
   const int tid = threadIdx.x;
   if (tid < GL_BUCKETS) hist[tid] = 0;
   if (tid == 0) nedge = 0;
@@ -154,23 +168,23 @@ __global__ void __launch_bounds__(1024) k_build_group_lists(int NL, int NR, cons
   for (int i = tid; i < nn; i += 1024) {
     const int seg = g < 2 ? 2 * i + g : 2 * (NL + i) + (g - 2);
     int n = seg_cnt[seg];
-    if (filt && seg_cnt[seg + 1] == 0) n = 0;
+    if (filt && !nd[i]) n = 0;
     if (n > 0) { atomicAdd(&hist[min(GL_BUCKETS - 1, (n + KC3 - 1) / KC3)], 1); atomicAdd(&nedge, n); }
   }
   __syncthreads();
   if (tid == 0) {
     int run = 0;
     for (int bkt = GL_BUCKETS - 1; bkt >= 0; --bkt) { cursor[bkt] = run; run += hist[bkt]; }
-    gcnt[blockIdx.x] = run;
-    if (!filt) atomicAdd(seg_total, (unsigned long long)run);      // seg_total = &counters[1]
-    atomicAdd(seg_total + 1 + blockIdx.x, (unsigned long long)nedge);   // counters[2..6]: edges per list
-    atomicAdd(seg_total + 6 + blockIdx.x, (unsigned long long)run);     // counters[7..11]: segments per list
+    gcnt[li] = run;
+    if (!filt) atomicAdd(counters + 1, (unsigned long long)run);            // all non-empty segments
+    atomicAdd(counters + 2 + li, (unsigned long long)nedge);                // edges per work list
+    atomicAdd(counters + 2 + F3_NLIST + li, (unsigned long long)run);       // segments per work list
   }
   __syncthreads();
   for (int i = tid; i < nn; i += 1024) {
     const int seg = g < 2 ? 2 * i + g : 2 * (NL + i) + (g - 2);
     int n = seg_cnt[seg];
-    if (filt && seg_cnt[seg + 1] == 0) n = 0;
+    if (filt && !nd[i]) n = 0;
     if (n > 0) {
       const int o = atomicAdd(&cursor[min(GL_BUCKETS - 1, (n + KC3 - 1) / KC3)], 1);
       glist[off + o] = make_int4(seg, n, seg_base[seg], 0);
@@ -925,11 +939,23 @@ cudaError_t conv3_configure() {
   return cudaFuncSetAttribute(k_conv_fused<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(F3Smem<3>));
 }
 
-void launch_build_group_lists(DdkCtx* c, cudaStream_t st) {
+void launch_build_group_lists(DdkCtx* c, cudaStream_t st, bool with_needed) {
+  unsigned char* need = ptr<unsigned char>(c->b_need);
+  const int nhop = with_needed ? c->nhop : 0;
+  if (nhop > 0) {
+    LaunchScope ls(c, PC_GRAPH, st);
+    k_need_hop0<<<(c->NR + 255) / 256, 256, 0, st>>>(c->NL, c->NR, ptr<int>(c->b_seg_cnt), need);
+  }
+  for (int h = 1; h < nhop; ++h) {
+    cudaMemsetAsync(need + (size_t)h * c->NR, 0, c->NR, st);
+    LaunchScope ls(c, PC_GRAPH, st);
+    k_need_expand<<<(c->ER + 255) / 256, 256, 0, st>>>(c->ER, ptr<int>(c->b_rr_src), ptr<int>(c->b_rr_dst),
+                                                      need + (size_t)(h - 1) * c->NR, need + (size_t)h * c->NR);
+  }
   LaunchScope ls(c, PC_GRAPH, st);
-  k_build_group_lists<<<5, 1024, 0, st>>>(c->NL, c->NR, ptr<int>(c->b_seg_cnt), ptr<int>(c->b_seg_base),
-                                          ptr<int4>(c->b_glist), ptr<int>(c->b_gcnt),
-                                          ptr<unsigned long long>(c->b_edge_total) + 1);
+  k_build_group_lists<<<4 + nhop, 1024, 0, st>>>(c->NL, c->NR, ptr<int>(c->b_seg_cnt), ptr<int>(c->b_seg_base),
+                                                 ptr<int4>(c->b_glist), ptr<int>(c->b_gcnt),
+                                                 ptr<unsigned long long>(c->b_edge_total), need);
 }
 
 void launch_conv_fused(DdkCtx* c, int layer, const float* x_in, float* x_out, cudaStream_t st, int mode) {
@@ -946,7 +972,7 @@ void launch_conv_fused(DdkCtx* c, int layer, const float* x_in, float* x_out, cu
   a.glist = ptr<int4>(c->b_glist);
   a.goff[0] = 0; a.goff[1] = c->NL; a.goff[2] = 2 * c->NL; a.goff[3] = 2 * c->NL + c->NR;
   for (int g = 0; g < 4; ++g) a.gci[g] = g;
-  if (mode == CONV_NEEDED) { a.goff[2] = 2 * c->NL + 2 * c->NR; a.gci[2] = 4; }
+  if (mode >= CONV_NEEDED) { const int h = mode - CONV_NEEDED; a.goff[2] = 2 * c->NL + 2 * c->NR + h * c->NR; a.gci[2] = 4 + h; }
   a.gcnt = ptr<int>(c->b_gcnt);
   a.counters = ptr<int>(c->b_counters);
   a.seg_list = ptr<int2>(c->b_seg_list);

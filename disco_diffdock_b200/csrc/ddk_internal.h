@@ -129,6 +129,8 @@ struct DdkCtx {
   ddk::LaneTab* ltab = nullptr;       // [4 basis levels][32 lanes]: lane -> basis rows / sources of the fused conv kernel
   std::vector<ddk::ConSplit> con_split;   // per layer
   ddk::Buf b_glist, b_gcnt, b_counters, b_part;
+  ddk::Buf b_need;                    // [hops][NR] uint8: receptor nodes whose features are read downstream (see ConvMode)
+  int nhop = 0;                       // hops computed per step = num_conv_layers - 1
   ddk::Buf b_hs;                      // [72 / J][list_total][J]: hidden units of every listed edge of the current layer
 
   // optional profiling (off by default)
@@ -168,10 +170,14 @@ cudaError_t conv_configure();
 cudaError_t conv3_configure();
 bool build_lane_table(int lv, LaneTab* tab32);
 void build_con_split(const LayerInfo& li, ConSplit& sp);
-void launch_build_group_lists(DdkCtx* c, cudaStream_t st);
-// which segments a conv layer processes: all; ligand nodes + the residues with a cross edge (whose features the next,
-// ligand-only layer reads); ligand nodes only (the last layer before the score heads)
-enum ConvMode { CONV_ALL = 0, CONV_NEEDED = 1, CONV_LIG = 2 };
+void launch_build_group_lists(DdkCtx* c, cudaStream_t st, bool with_needed);
+// Which segments a conv layer processes.  Before the score heads only ligand features are read, so working backwards from
+// the last layer the set of receptor nodes whose features matter shrinks: the last layer needs ligand nodes only
+// (CONV_LIG); the layer before it additionally the residues with a cross edge (hop 0); each earlier layer the previous set
+// plus its receptor-contact neighbours (hop h).  CONV_NEEDED + h selects work list 4 + h for edge group 2.
+enum ConvMode { CONV_LIG = -1, CONV_ALL = 0, CONV_NEEDED = 1 };
+constexpr int F3_MAXHOP = 7;        // conv layers 0 .. L-2 <-> hops L-2 .. 0 (num_conv_layers <= 8)
+constexpr int F3_NLIST = 4 + F3_MAXHOP;
 void launch_conv_fused(DdkCtx* c, int layer, const float* x_in, float* x_out, cudaStream_t st, int mode);
 void launch_edge_hidden(DdkCtx* c, int layer, cudaStream_t st, int mode);
 cudaError_t heads_configure();

@@ -373,9 +373,9 @@ class Engine:
         return int(self.lib.ddk_segment_total(self.ctx))
 
     def group_totals(self):
-        """Cumulative (edges[5], segments[5]) per work list: groups 0 lig-lig, 1 lig<-rec, 2 rec-rec, 3 rec<-lig, and 4 = group 2
-        restricted to residues with a cross edge."""
-        e, s = np.zeros(5, np.int64), np.zeros(5, np.int64)
+        """Cumulative (edges[11], segments[11]) per work list: groups 0 lig-lig, 1 lig<-rec, 2 rec-rec, 3 rec<-lig, and 4 + h =
+        group 2 restricted to residues within h receptor-contact hops of a residue with a cross edge."""
+        e, s = np.zeros(11, np.int64), np.zeros(11, np.int64)
         self._check(self.lib.ddk_group_totals(self.ctx, _np_ptr(e), _np_ptr(s)), 'ddk_group_totals')
         return e, s
 

@@ -186,9 +186,11 @@ int64_t ddk_edge_total(DdkCtx* ctx);                   /* cumulative *dynamic* (
                                                           the static bond / receptor-contact edges are not included */
 int64_t ddk_segment_total(DdkCtx* ctx);                /* cumulative non-empty (node, edge group) segments since ddk_create (sync): the
                                                           second radial-MLP layer runs once per segment and conv layer */
-int ddk_group_totals(DdkCtx* ctx, int64_t* edges5, int64_t* segments5);   /* cumulative listed edges / non-empty segments per work
-                                                          list: edge groups 0 lig-lig, 1 lig<-rec, 2 rec-rec, 3 rec<-lig, and 4 = group 2
-                                                          restricted to residues with a cross edge; all steps (sync) */
+#define DDK_WORK_LISTS 11
+int ddk_group_totals(DdkCtx* ctx, int64_t* edges, int64_t* segments);   /* cumulative listed edges / non-empty segments per work
+                                                          list ([DDK_WORK_LISTS] each): edge groups 0 lig-lig, 1 lig<-rec, 2 rec-rec,
+                                                          3 rec<-lig, and 4 + h = group 2 restricted to the residues within h
+                                                          receptor-contact hops of a residue with a cross edge; all steps (sync) */
 int ddk_debug_read(DdkCtx* ctx, const char* name, void* dst_h, size_t max_bytes, size_t* n_bytes);
 
 /* Optional per-launch timing with CUDA events on the launching stream (used by bench.py for the roofline line).

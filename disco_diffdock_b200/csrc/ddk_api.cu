@@ -188,7 +188,7 @@ int ddk_destroy(DdkCtx* c) {
                 &c->b_lr_off, &c->b_seg_base, &c->b_seg_static, &c->b_seg_cnt, &c->b_seg_list, &c->b_seg_order,
                 &c->b_seg_sidx, &c->b_lig_static, &c->b_rec_static, &c->b_rr_pre, &c->b_ea_pool, &c->b_sh_pool, &c->b_tb,
                 &c->b_xa, &c->b_xb, &c->b_proj, &c->b_A, &c->b_Bsum, &c->b_tr, &c->b_rot, &c->b_tor, &c->b_pos, &c->b_step, &c->b_edge_total, &c->b_work, &c->b_nwork,
-                &c->b_glist, &c->b_gcnt, &c->b_counters, &c->b_part, &c->b_hs, &c->b_need};
+                &c->b_glist, &c->b_gcnt, &c->b_counters, &c->b_part, &c->b_hs, &c->b_need, &c->b_static_pos};
   for (Buf* b : all) free_buf(*b);
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   if (c->w) cudaFree(c->w);
@@ -279,14 +279,13 @@ int ddk_set_batch(DdkCtx* c, const DdkBatch* b, void* stream) {
   for (int s = 0; s < nsegs; ++s) { seg_base[s] = (int)total; total += seg_cap[s]; }
   if (total >= ((int64_t)1 << 31)) return fail(c, DDK_ERR_INVALID, "batch too large for 32-bit list offsets");
   c->list_total = total;
-  std::vector<int2> seg_list((size_t)std::max<int64_t>(total, 1), make_int2(0, 0));
+  // static list entries (covalent bonds, receptor contacts) sit at the head of their segment, in edge order; only their
+  // positions travel to the device (k_fill_static_lists writes them), not the whole capacity-sized list
+  std::vector<int> static_pos((size_t)EB + ER);
   {
     std::vector<int> fill(nsegs, 0);
-    for (int e = 0; e < EB; ++e) { int s = 2 * bond_src[e]; seg_list[seg_base[s] + fill[s]++] = make_int2(e, bond_dst[e]); }
-    for (int e = 0; e < ER; ++e) {
-      int s = 2 * (NL + rr_src[e]);
-      seg_list[seg_base[s] + fill[s]++] = make_int2((int)(c->slot_rr + e), NL + rr_dst[e]);
-    }
+    for (int e = 0; e < EB; ++e) { int s = 2 * bond_src[e]; static_pos[e] = seg_base[s] + fill[s]++; }
+    for (int e = 0; e < ER; ++e) { int s = 2 * (NL + rr_src[e]); static_pos[(size_t)EB + e] = seg_base[s] + fill[s]++; }
   }
   // chunks of graphs bounded by the outer-product scratch; LPT-ish order inside a chunk (largest groups first)
   int Umax = 0;
@@ -331,7 +330,8 @@ int ddk_set_batch(DdkCtx* c, const DdkBatch* b, void* stream) {
   UP(c->b_rot_u, rot_u); UP(c->b_rot_v, rot_v); UP(c->b_rot_ptr, rot_ptr); UP(c->b_mr_off, mr_off);
   UP(c->b_ll_off, ll_off); UP(c->b_lr_off, lr_off);
   seg_base.resize(nsegs);
-  UP(c->b_seg_base, seg_base); UP(c->b_seg_static, seg_static); UP(c->b_seg_cnt, seg_static); UP(c->b_seg_list, seg_list);
+  UP(c->b_seg_base, seg_base); UP(c->b_seg_static, seg_static); UP(c->b_seg_cnt, seg_static); UP(c->b_static_pos, static_pos);
+  if ((rc = ensure(c, c->b_seg_list, (size_t)std::max<int64_t>(total, 1) * sizeof(int2))) != DDK_OK) return rc;
   UP(c->b_seg_order, seg_order); UP(c->b_seg_sidx, seg_sidx);
 #undef UP
 #define EN(buf, bytes) if ((rc = ensure(c, buf, (size_t)(bytes))) != DDK_OK) return rc

@@ -91,6 +91,14 @@ __global__ void k_setup_rr_edges(int ER, const int* __restrict__ rr_src, const i
   for (int o = 0; o < EA; ++o) rr_pre[(size_t)e * EA + o] = pre[o];
 }
 
+// Static entries of the segment lists: bond e -> (slot e, dst atom), receptor contact e -> (slot_rr + e, NL + dst residue)
+__global__ void k_fill_static_lists(int EB, int ER, int NL, int slot_rr, const int* __restrict__ static_pos,
+                                    const int* __restrict__ bond_dst, const int* __restrict__ rr_dst, int2* __restrict__ seg_list) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < EB) seg_list[static_pos[e]] = make_int2(e, bond_dst[e]);
+  else if (e < EB + ER) seg_list[static_pos[e]] = make_int2(slot_rr + (e - EB), NL + rr_dst[e - EB]);
+}
+
 // ------------------------------------------------------------------------------------------------ per step
 struct TbArgs {
   const float* Wsrc[TB_COUNT];
@@ -323,6 +331,12 @@ __global__ void __launch_bounds__(256) k_edge_features(EdgeArgs p) {
 // ------------------------------------------------------------------------------------------------ launchers
 void launch_setup(DdkCtx* c, const DdkBatch* b, const int32_t* lig_x, const float* rec_x, cudaStream_t st) {
   int L = c->cfg.latent_dim;
+  if (c->EB + c->ER > 0) {
+    LaunchScope ls(c, PC_SETUP, st);
+    k_fill_static_lists<<<(c->EB + c->ER + 255) / 256, 256, 0, st>>>(c->EB, c->ER, c->NL, (int)c->slot_rr, ptr<int>(c->b_static_pos),
+                                                                   ptr<int>(c->b_bond_dst), ptr<int>(c->b_rr_dst),
+                                                                   ptr<int2>(c->b_seg_list));
+  }
   {
     dim3 blk(NS, 8);
     LaunchScope ls(c, PC_SETUP, st);

@@ -110,7 +110,7 @@ struct DdkCtx {
   // device arrays owned by the context (grow-only)
   ddk::Buf b_lig_ptr, b_rec_ptr, b_lig_graph, b_rec_graph, b_bond_src, b_bond_dst, b_rr_src, b_rr_dst;
   ddk::Buf b_rot_u, b_rot_v, b_rot_ptr, b_rot_graph, b_mr_off, b_ll_off, b_lr_off;
-  ddk::Buf b_seg_base, b_seg_static, b_seg_cnt, b_seg_list, b_seg_order, b_seg_sidx;
+  ddk::Buf b_seg_base, b_seg_static, b_seg_cnt, b_seg_list, b_seg_order, b_seg_sidx, b_static_pos;
   ddk::Buf b_lig_static, b_rec_static, b_rr_pre, b_ea_pool, b_sh_pool, b_tb;
   ddk::Buf b_xa, b_xb, b_proj, b_A, b_Bsum;
   ddk::Buf b_tr, b_rot, b_tor, b_pos;

@@ -85,10 +85,36 @@ def torsion_update_host(pos, edge_index, mask_rotate, torsion_updates):
     return torch.from_numpy(p.astype(np.float32))
 
 
+_STEP_TABLE_CACHE = {}
+
+
 def build_step_tables(score_model, model_args, t_to_sigma, tr_schedule, rot_schedule, tor_schedule, inference_steps, B,
                       temp_sampling, temp_psi, temp_sigma_data, ode=False) -> StepTables:
     """Host arithmetic of sampling.py:106-113, 137-192 and of the sigma-dependent parts of
-    TensorProductScoreModel.forward (score_model.py:187, 203, 276, 284-286, 303-307) for every step."""
+    TensorProductScoreModel.forward (score_model.py:187, 203, 276, 284-286, 303-307) for every step.  The tables depend only
+    on the schedule, the noise-level hyper-parameters, the temperatures and the batch size, so evaluate.py's loop over
+    complexes reuses them (a small keyed cache)."""
+    try:
+        key = (id(score_model), inference_steps, B, bool(ode), tuple(np.asarray(tr_schedule, dtype=np.float64).tolist()),
+               tuple(np.asarray(rot_schedule, dtype=np.float64).tolist()), tuple(np.asarray(tor_schedule, dtype=np.float64).tolist()),
+               tuple(_three(temp_sampling)), tuple(_three(temp_psi)), tuple(_three(temp_sigma_data)),
+               tuple(float(getattr(model_args, k)) for k in ('tr_sigma_min', 'tr_sigma_max', 'rot_sigma_min', 'rot_sigma_max',
+                                                              'tor_sigma_min', 'tor_sigma_max')))
+    except Exception:
+        key = None
+    if key is not None and key in _STEP_TABLE_CACHE:
+        return _STEP_TABLE_CACHE[key]
+    tab = _build_step_tables(score_model, model_args, t_to_sigma, tr_schedule, rot_schedule, tor_schedule, inference_steps, B,
+                             temp_sampling, temp_psi, temp_sigma_data, ode)
+    if key is not None:
+        if len(_STEP_TABLE_CACHE) > 64:
+            _STEP_TABLE_CACHE.clear()
+        _STEP_TABLE_CACHE[key] = tab
+    return tab
+
+
+def _build_step_tables(score_model, model_args, t_to_sigma, tr_schedule, rot_schedule, tor_schedule, inference_steps, B,
+                       temp_sampling, temp_psi, temp_sigma_data, ode=False) -> StepTables:
     ts, tp, td = _three(temp_sampling), _three(temp_psi), _three(temp_sigma_data)
     emb_fn = score_model.timestep_emb_func
     rng = [(model_args.tr_sigma_min, model_args.tr_sigma_max), (model_args.rot_sigma_min, model_args.rot_sigma_max),

@@ -239,12 +239,12 @@ int ddk_set_batch(DdkCtx* c, const DdkBatch* b, void* stream) {
   // bonds, rotatable bonds
   std::vector<int> bond_src(b->bond_index_h, b->bond_index_h + EB), bond_dst(b->bond_index_h + EB, b->bond_index_h + 2 * EB);
   std::vector<int> rr_src(b->rec_index_h, b->rec_index_h + ER), rr_dst(b->rec_index_h + ER, b->rec_index_h + 2 * ER);
-  std::vector<int> rot_u, rot_v, rot_ptr(B + 1, 0);
+  std::vector<int> rot_u, rot_v, rot_graph, rot_ptr(B + 1, 0);
   for (int g = 0; g < B; ++g) {
     for (int e = b->bond_ptr_h[g]; e < b->bond_ptr_h[g + 1]; ++e) {
       if (bond_src[e] < lig_ptr[g] || bond_src[e] >= lig_ptr[g + 1] || bond_dst[e] < lig_ptr[g] || bond_dst[e] >= lig_ptr[g + 1])
         return fail(c, DDK_ERR_INVALID, "bond crosses a graph boundary");
-      if (b->edge_mask_h[e]) { rot_u.push_back(bond_src[e]); rot_v.push_back(bond_dst[e]); }
+      if (b->edge_mask_h[e]) { rot_u.push_back(bond_src[e]); rot_v.push_back(bond_dst[e]); rot_graph.push_back(g); }
     }
     rot_ptr[g + 1] = (int)rot_u.size();
   }
@@ -327,7 +327,7 @@ int ddk_set_batch(DdkCtx* c, const DdkBatch* b, void* stream) {
 #define UP(buf, vec) if ((rc = upload(c, buf, vec, st)) != DDK_OK) return rc
   UP(c->b_lig_ptr, lig_ptr); UP(c->b_rec_ptr, rec_ptr); UP(c->b_lig_graph, lig_graph); UP(c->b_rec_graph, rec_graph);
   UP(c->b_bond_src, bond_src); UP(c->b_bond_dst, bond_dst); UP(c->b_rr_src, rr_src); UP(c->b_rr_dst, rr_dst);
-  UP(c->b_rot_u, rot_u); UP(c->b_rot_v, rot_v); UP(c->b_rot_ptr, rot_ptr); UP(c->b_mr_off, mr_off);
+  UP(c->b_rot_u, rot_u); UP(c->b_rot_v, rot_v); UP(c->b_rot_ptr, rot_ptr); UP(c->b_rot_graph, rot_graph); UP(c->b_mr_off, mr_off);
   UP(c->b_ll_off, ll_off); UP(c->b_lr_off, lr_off);
   seg_base.resize(nsegs);
   UP(c->b_seg_base, seg_base); UP(c->b_seg_static, seg_static); UP(c->b_seg_cnt, seg_static); UP(c->b_static_pos, static_pos);

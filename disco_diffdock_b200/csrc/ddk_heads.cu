@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(HEAD_THREADS) k_head_trrot(TrRotArgs p) {
 
 // ------------------------------------------------------------------------------------------------ torsion head
 struct TorArgs {
-  const int* lig_ptr; const int* rot_ptr; const int* rot_u; const int* rot_v;
+  const int* lig_ptr; const int* rot_graph; const int* rot_u; const int* rot_v;
   const float* lig_pos; const float* x;
   const float* sm;                         // ligand smearing (reused for bond edges, score_model.py:433)
   const float* We1; const float* be1; const float* We2; const float* be2;   // final_edge_embedding [24][32],[24][24]
@@ -198,7 +198,7 @@ constexpr int TOR_THREADS = 128;
 constexpr int TOR_E = 32;          // torch_cluster.radius max_num_neighbors of the bond graph (score_model.py:430)
 constexpr int TOR_FS = HID + 1;    // padded row of the per-edge feature / hidden tiles
 
-// One CTA per graph, its rotatable bonds one after the other, every phase spread over the 128 threads:
+// One CTA per rotatable bond, every phase spread over the 128 threads:
 //   1. warp 0 lists the <= 32 atoms within 5 A of the bond midpoint (index order, as torch_cluster.radius does)
 //   2. edge embedding + concatenated features feat[e][72], tensor-product coefficients d[e][blk,u] (4 threads per edge)
 //   3. first layer of tor_bond_conv.fc: H = relu(feat W1^T + b1)                       (thread = edge x 18 columns)
@@ -221,20 +221,18 @@ __global__ void __launch_bounds__(TOR_THREADS) k_head_tor(TorArgs p) {
   float* sOut = sRow + 288;                 // [48]
   __shared__ int sIdx[TOR_E];
   __shared__ int sCnt[2];
-  const int g = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const int b0 = p.rot_ptr[g], b1 = p.rot_ptr[g + 1];
-  if (b0 == b1) return;
+  const int b = blockIdx.x, g = p.rot_graph[b], tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int l0 = p.lig_ptr[g], l1 = p.lig_ptr[g + 1];
   for (int i = tid; i < HID * HID; i += TOR_THREADS) { const int o = i / HID, k = i % HID; sW1[k * HID + o] = p.W1[i]; }
   for (int i = tid; i < DE * EA; i += TOR_THREADS) { const int o = i / DE, k = i % DE; sWe1[k * EA + o] = p.We1[i]; }
   for (int i = tid; i < EA * EA; i += TOR_THREADS) { const int o = i / EA, k = i % EA; sWe2[k * EA + o] = p.We2[i]; }
   const float kpw = sqrtf(1.f / (float)NV) * 0.5773502691896258f;   // path weight sqrt(1/nv) * C(1,1,0) = 1/sqrt3
-  for (int b = b0; b < b1; ++b) {
+  {
     const int u = p.rot_u[b], v = p.rot_v[b];
     const float ux = p.lig_pos[u * 3], uy = p.lig_pos[u * 3 + 1], uz = p.lig_pos[u * 3 + 2];
     const float vx = p.lig_pos[v * 3], vy = p.lig_pos[v * 3 + 1], vz = p.lig_pos[v * 3 + 2];
     const float mx = (ux + vx) / 2.f, my = (uy + vy) / 2.f, mz = (uz + vz) / 2.f;   // bond midpoint (:428)
-    __syncthreads();                           // weights staged / previous bond finished
+    __syncthreads();                           // weights staged
     // ---- 1. neighbour list
     if (w == 0) {
       int cnt = 0;
@@ -413,7 +411,7 @@ void launch_head_trrot(DdkCtx* c, const float* lig_pos, const float* x, const Dd
 void launch_head_tor(DdkCtx* c, const float* lig_pos, const float* x, const DdkStepInputs* in, float* tor, cudaStream_t st) {
   if (c->RB == 0 || c->cfg.no_torsion) return;
   TorArgs p;
-  p.lig_ptr = ptr<int>(c->b_lig_ptr); p.rot_ptr = ptr<int>(c->b_rot_ptr);
+  p.lig_ptr = ptr<int>(c->b_lig_ptr); p.rot_graph = ptr<int>(c->b_rot_graph);
   p.rot_u = ptr<int>(c->b_rot_u); p.rot_v = ptr<int>(c->b_rot_v);
   p.lig_pos = lig_pos; p.x = x;
   p.sm = W(c, DDK_W_SMEAR);
@@ -427,7 +425,7 @@ void launch_head_tor(DdkCtx* c, const float* lig_pos, const float* x, const DdkS
   p.r2_lig = c->r2_lig;
   p.tor = tor;
   LaunchScope ls(c, PC_HEADS, st);
-  k_head_tor<<<c->B, TOR_THREADS, tor_smem_bytes(), st>>>(p);
+  k_head_tor<<<c->RB, TOR_THREADS, tor_smem_bytes(), st>>>(p);
 }
 
 }  // namespace ddk

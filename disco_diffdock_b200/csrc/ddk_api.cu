@@ -102,7 +102,6 @@ int ddk_create(const DdkConfig* cfg, const float* weights_h, size_t n_floats, co
   if (device < 0 || device >= ndev) return fail(nullptr, DDK_ERR_INVALID, "device index out of range");
   DdkCtx* c = new DdkCtx();
   c->cfg = *cfg;
-  if (c->cfg.scratch_bytes <= 0) c->cfg.scratch_bytes = (int64_t)4 << 30;
   c->device = device;
   c->off.assign(offsets_h, offsets_h + n_offsets);
   for (int64_t o : c->off)
@@ -127,15 +126,9 @@ int ddk_create(const DdkConfig* cfg, const float* weights_h, size_t n_floats, co
   if ((e = cudaMalloc(&c->b_edge_total.p, ncounter)) != cudaSuccess) return bail("cudaMalloc(counter)", e);
   c->b_edge_total.bytes = ncounter;   // cumulative: [0] dynamic edges, [1] non-empty segments, then edges / segments per work list
   if ((e = cudaMemset(c->b_edge_total.p, 0, ncounter)) != cudaSuccess) return bail("cudaMemset(counter)", e);
-  if ((e = conv_configure()) != cudaSuccess) return bail("cudaFuncSetAttribute(conv)", e);
   if ((e = heads_configure()) != cudaSuccess) return bail("cudaFuncSetAttribute(heads)", e);
-  if ((e = conv2_configure()) != cudaSuccess) return bail("cudaFuncSetAttribute(conv2)", e);
-  if ((e = contract2_configure()) != cudaSuccess) return bail("cudaFuncSetAttribute(contract2)", e);
   if ((e = conv3_configure()) != cudaSuccess) return bail("cudaFuncSetAttribute(conv3)", e);
   {
-    const char* v = getenv("DDK_CONV");
-    c->conv_v1 = v && std::string(v) == "v1";
-    c->conv_v2 = v && std::string(v) == "v2";
     cudaDeviceProp prop;
     if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
     c->sm_count = prop.multiProcessorCount;
@@ -185,9 +178,9 @@ int ddk_destroy(DdkCtx* c) {
   cudaSetDevice(c->device);
   Buf* all[] = {&c->b_lig_ptr, &c->b_rec_ptr, &c->b_lig_graph, &c->b_rec_graph, &c->b_bond_src, &c->b_bond_dst, &c->b_rr_src,
                 &c->b_rr_dst, &c->b_rot_u, &c->b_rot_v, &c->b_rot_ptr, &c->b_rot_graph, &c->b_mr_off, &c->b_ll_off,
-                &c->b_lr_off, &c->b_seg_base, &c->b_seg_static, &c->b_seg_cnt, &c->b_seg_list, &c->b_seg_order,
-                &c->b_seg_sidx, &c->b_lig_static, &c->b_rec_static, &c->b_rr_pre, &c->b_ea_pool, &c->b_sh_pool, &c->b_tb,
-                &c->b_xa, &c->b_xb, &c->b_proj, &c->b_A, &c->b_Bsum, &c->b_tr, &c->b_rot, &c->b_tor, &c->b_pos, &c->b_step, &c->b_edge_total, &c->b_work, &c->b_nwork,
+                &c->b_lr_off, &c->b_seg_base, &c->b_seg_static, &c->b_seg_cnt, &c->b_seg_list,
+                &c->b_lig_static, &c->b_rec_static, &c->b_rr_pre, &c->b_ea_pool, &c->b_sh_pool, &c->b_tb,
+                &c->b_xa, &c->b_xb, &c->b_proj, &c->b_tr, &c->b_rot, &c->b_tor, &c->b_pos, &c->b_step, &c->b_edge_total,
                 &c->b_glist, &c->b_gcnt, &c->b_counters, &c->b_part, &c->b_hs, &c->b_need, &c->b_static_pos};
   for (Buf* b : all) free_buf(*b);
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
@@ -287,42 +280,6 @@ int ddk_set_batch(DdkCtx* c, const DdkBatch* b, void* stream) {
     for (int e = 0; e < EB; ++e) { int s = 2 * bond_src[e]; static_pos[e] = seg_base[s] + fill[s]++; }
     for (int e = 0; e < ER; ++e) { int s = 2 * (NL + rr_src[e]); static_pos[(size_t)EB + e] = seg_base[s] + fill[s]++; }
   }
-  // chunks of graphs bounded by the outer-product scratch; LPT-ish order inside a chunk (largest groups first)
-  int Umax = 0;
-  for (const LayerInfo& li : c->layers) Umax = std::max(Umax, li.U);
-  const int64_t seg_bytes = (int64_t)Umax * HID * sizeof(float);
-  const int64_t max_segs = std::max<int64_t>(c->cfg.scratch_bytes / seg_bytes, 2 * (c->maxNl + c->maxNr));
-  c->chunks.clear();
-  std::vector<int> seg_order, seg_sidx(nsegs, 0);
-  int64_t max_chunk_segs = 0;
-  for (int g = 0; g < B;) {
-    Chunk ch{};
-    ch.g0 = g;
-    int64_t segs = 0;
-    while (g < B) {
-      int64_t add = 2 * ((lig_ptr[g + 1] - lig_ptr[g]) + (rec_ptr[g + 1] - rec_ptr[g]));
-      if (segs > 0 && segs + add > max_segs) break;
-      segs += add;
-      ++g;
-    }
-    ch.g1 = g;
-    ch.lig0 = lig_ptr[ch.g0]; ch.lig1 = lig_ptr[ch.g1]; ch.rec0 = rec_ptr[ch.g0]; ch.rec1 = rec_ptr[ch.g1];
-    ch.nseg = (int)segs;
-    ch.order_off = (int)seg_order.size();
-    const int nlc = ch.lig1 - ch.lig0;
-    for (int n = ch.lig0; n < ch.lig1; ++n) seg_order.push_back(2 * n + 1);                  // group 1 (largest)
-    for (int r = ch.rec0; r < ch.rec1; ++r) seg_order.push_back(2 * (NL + r) + 1);           // group 3
-    for (int r = ch.rec0; r < ch.rec1; ++r) seg_order.push_back(2 * (NL + r));               // group 2
-    for (int n = ch.lig0; n < ch.lig1; ++n) seg_order.push_back(2 * n);                      // group 0
-    for (int n = ch.lig0; n < ch.lig1; ++n) { seg_sidx[2 * n] = 2 * (n - ch.lig0); seg_sidx[2 * n + 1] = 2 * (n - ch.lig0) + 1; }
-    for (int r = ch.rec0; r < ch.rec1; ++r) {
-      seg_sidx[2 * (NL + r)] = 2 * nlc + 2 * (r - ch.rec0);
-      seg_sidx[2 * (NL + r) + 1] = 2 * nlc + 2 * (r - ch.rec0) + 1;
-    }
-    max_chunk_segs = std::max<int64_t>(max_chunk_segs, segs);
-    c->chunks.push_back(ch);
-  }
-
   int rc;
 #define UP(buf, vec) if ((rc = upload(c, buf, vec, st)) != DDK_OK) return rc
   UP(c->b_lig_ptr, lig_ptr); UP(c->b_rec_ptr, rec_ptr); UP(c->b_lig_graph, lig_graph); UP(c->b_rec_graph, rec_graph);
@@ -332,23 +289,17 @@ int ddk_set_batch(DdkCtx* c, const DdkBatch* b, void* stream) {
   seg_base.resize(nsegs);
   UP(c->b_seg_base, seg_base); UP(c->b_seg_static, seg_static); UP(c->b_seg_cnt, seg_static); UP(c->b_static_pos, static_pos);
   if ((rc = ensure(c, c->b_seg_list, (size_t)std::max<int64_t>(total, 1) * sizeof(int2))) != DDK_OK) return rc;
-  UP(c->b_seg_order, seg_order); UP(c->b_seg_sidx, seg_sidx);
 #undef UP
 #define EN(buf, bytes) if ((rc = ensure(c, buf, (size_t)(bytes))) != DDK_OK) return rc
   EN(c->b_lig_static, (size_t)NL * NS * 4); EN(c->b_rec_static, (size_t)NR * NS * 4); EN(c->b_rr_pre, (size_t)ER * EA * 4);
   EN(c->b_ea_pool, (size_t)c->P * EA * 4); EN(c->b_sh_pool, (size_t)c->P * 16);
   EN(c->b_tb, (size_t)B * TB_COUNT * NS * 4);
   EN(c->b_xa, (size_t)c->N * D * 4); EN(c->b_xb, (size_t)c->N * D * 4); EN(c->b_proj, (size_t)c->N * 4 * HID * 4);
-  if (c->conv_v1 || c->conv_v2) {
-    EN(c->b_A, (size_t)max_chunk_segs * seg_bytes); EN(c->b_Bsum, (size_t)max_chunk_segs * Umax * 4);
-    EN(c->b_work, (size_t)nsegs * 16); EN(c->b_nwork, (size_t)c->chunks.size() * 4);
-  } else {
-    c->nhop = std::min(F3_MAXHOP, c->cfg.num_conv_layers - 1);
-    EN(c->b_glist, ((size_t)nsegs + (size_t)c->nhop * NR) * 16); EN(c->b_gcnt, F3_NLIST * 4);
-    EN(c->b_need, (size_t)std::max(1, c->nhop) * NR); EN(c->b_counters, 4 * NSL_MAX * 4);
-    EN(c->b_part, (size_t)nsegs * NSL_MAX * D * 4);
-    EN(c->b_hs, (size_t)std::max<int64_t>(total, 1) * HID * 4);
-  }
+  c->nhop = std::min(F3_MAXHOP, c->cfg.num_conv_layers - 1);
+  EN(c->b_glist, ((size_t)nsegs + (size_t)c->nhop * NR) * 16); EN(c->b_gcnt, F3_NLIST * 4); EN(c->b_counters, 4 * NSL_MAX * 4);
+  EN(c->b_need, (size_t)std::max(1, c->nhop) * NR);
+  EN(c->b_part, (size_t)nsegs * NSL_MAX * D * 4);
+  EN(c->b_hs, (size_t)std::max<int64_t>(total, 1) * HID * 4);
   EN(c->b_tr, (size_t)B * 3 * 4); EN(c->b_rot, (size_t)B * 3 * 4); EN(c->b_tor, (size_t)std::max(c->RB, 1) * 4);
 #undef EN
   launch_setup(c, b, b->lig_x, b->rec_x, st);
@@ -366,8 +317,7 @@ static int run_embed(DdkCtx* c, const float* lig_pos, const DdkStepInputs* in, c
   launch_step_consts(c, in->sigma_emb, st);
   launch_build_lists(c, lig_pos, in->cross_cutoff, st);
   launch_edge_features(c, lig_pos, st);
-  if (c->conv_v2) launch_build_worklist(c, st);
-  else if (!c->conv_v1) launch_build_group_lists(c, st, heads_only);
+  launch_build_group_lists(c, st, heads_only);
   float* xa = ptr<float>(c->b_xa);
   float* xb = ptr<float>(c->b_xb);
   launch_node_proj(c, 0, nullptr, xa, st);

@@ -39,13 +39,6 @@ struct LayerInfo {
   int ncls;
 };
 
-struct Chunk {       // a contiguous range of graphs processed through one accumulate / contract pass
-  int g0, g1;
-  int lig0, lig1, rec0, rec1;
-  int nseg;
-  int order_off;     // offset into seg_order
-};
-
 struct Buf {
   void* p = nullptr;
   size_t bytes = 0;
@@ -100,7 +93,6 @@ struct DdkCtx {
   int maxNl = 0, maxNr = 0, maxRot = 0;
   int64_t LLtot = 0, LRtot = 0, P = 0, list_total = 0;
   int64_t slot_ll = 0, slot_lr = 0, slot_rr = 0;
-  std::vector<ddk::Chunk> chunks;
   const float* rec_pos = nullptr;     // caller memory (must stay alive while the batch is current)
   const uint8_t* mask_rotate = nullptr;
   const float* lig_latent = nullptr; const float* rec_latent = nullptr;
@@ -110,19 +102,15 @@ struct DdkCtx {
   // device arrays owned by the context (grow-only)
   ddk::Buf b_lig_ptr, b_rec_ptr, b_lig_graph, b_rec_graph, b_bond_src, b_bond_dst, b_rr_src, b_rr_dst;
   ddk::Buf b_rot_u, b_rot_v, b_rot_ptr, b_rot_graph, b_mr_off, b_ll_off, b_lr_off;
-  ddk::Buf b_seg_base, b_seg_static, b_seg_cnt, b_seg_list, b_seg_order, b_seg_sidx, b_static_pos;
+  ddk::Buf b_seg_base, b_seg_static, b_seg_cnt, b_seg_list, b_static_pos;
   ddk::Buf b_lig_static, b_rec_static, b_rr_pre, b_ea_pool, b_sh_pool, b_tb;
-  ddk::Buf b_xa, b_xb, b_proj, b_A, b_Bsum;
+  ddk::Buf b_xa, b_xb, b_proj;
   ddk::Buf b_tr, b_rot, b_tor, b_pos;
   ddk::Buf b_step;                    // staging for ddk_sample_host
-  ddk::Buf b_work, b_nwork;           // compacted per-chunk segment work lists (rebuilt every step)
   ddk::Buf b_edge_total;              // device uint64: edges of every combined graph built so far
   float* x_final = nullptr;           // points into xa or xb after the last conv layer
   bool x_final_all = false;           // receptor rows of x_final are valid (ddk_embed); ddk_score / ddk_sample skip them
 
-  bool conv_v1 = false;               // DDK_CONV=v1: the simple one-CTA-per-segment accumulate kernel + scratch
-  bool conv_v2 = false;               // DDK_CONV=v2: persistent accumulate + tensor-pipe contract over the scratch
-                                      // default: fused, hidden-unit-sliced kernel (ddk_conv3.cu), no scratch
   int sm_count = 148;
   float* w2s = nullptr;               // second-layer weights re-sliced per hidden-unit slice: [layer][group][72 / J][W * J]
   std::vector<int64_t> w2s_off;       // [layer * 4 + group] (floats)
@@ -166,7 +154,6 @@ struct LaunchScope {
   ~LaunchScope() { if (idx >= 0) cudaEventRecord(c->prof_recs[idx].b, st); }
 };
 
-cudaError_t conv_configure();
 cudaError_t conv3_configure();
 bool build_lane_table(int lv, LaneTab* tab32);
 void build_con_split(const LayerInfo& li, ConSplit& sp);
@@ -189,7 +176,6 @@ void launch_setup(DdkCtx* c, const DdkBatch* b, const int32_t* lig_x, const floa
 void launch_step_consts(DdkCtx* c, const float* sigma_emb, cudaStream_t st);
 void launch_build_lists(DdkCtx* c, const float* lig_pos, const float* cutoff, cudaStream_t st);
 void launch_edge_features(DdkCtx* c, const float* lig_pos, cudaStream_t st);
-void launch_build_worklist(DdkCtx* c, cudaStream_t st);
 void launch_node_proj(DdkCtx* c, int layer, const float* x_in, float* x0_out, cudaStream_t st);
 void launch_conv_layer(DdkCtx* c, int layer, const float* x_in, float* x_out, cudaStream_t st, int mode = 0);
 void launch_head_trrot(DdkCtx* c, const float* lig_pos, const float* x, const DdkStepInputs* in, float* tr, float* rot,

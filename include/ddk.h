@@ -61,7 +61,7 @@ typedef struct DdkConfig {
   int32_t scale_by_sigma;
   int32_t no_torsion;
   float lig_max_radius, rec_max_radius, cross_max_distance, center_max_distance;
-  int64_t scratch_bytes;      /* cap for the per-layer outer-product scratch (0 = default 4 GiB) */
+  int64_t scratch_bytes;      /* reserved (was: cap of an outer-product scratch; the fused conv kernel has none), pass 0 */
 } DdkConfig;
 
 /* Offsets (in floats) of each packed tensor inside the weight blob; layout documented in

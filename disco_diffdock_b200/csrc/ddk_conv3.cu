@@ -47,14 +47,18 @@ __device__ __forceinline__ void f3_mbar_init(unsigned long long* bar, int count)
 __device__ __forceinline__ void f3_mbar_arrive(unsigned long long* bar) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared.b64 st, [%0];\n\t}" ::"r"(f3_smem_addr(bar)) : "memory");
 }
-__device__ __forceinline__ void f3_mbar_wait(unsigned long long* bar, int parity) {
+__device__ __forceinline__ bool f3_mbar_try(unsigned long long* bar, int parity) {
+  unsigned ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared.b64 p, [%0], %1;\n\t"
-      "@p bra.uni DONE_%=;\n\t"
-      "bra.uni WAIT_%=;\n\t"
-      "DONE_%=:\n\t}" ::"r"(f3_smem_addr(bar)), "r"(parity) : "memory");
+      "mbarrier.try_wait.parity.shared.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(f3_smem_addr(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// waiting warps back off between probes so they do not take issue slots from the warps they are waiting for
+__device__ __forceinline__ void f3_mbar_wait(unsigned long long* bar, int parity) {
+  if (f3_mbar_try(bar, parity)) return;
+  while (!f3_mbar_try(bar, parity)) __nanosleep(128);
 }
 
 // Basis rows are laid out over (slot, lane) by SOURCE feature so that a few shared-memory loads feed many rows and every

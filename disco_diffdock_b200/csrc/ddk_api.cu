@@ -1,5 +1,6 @@
 // C ABI of libddk (include/ddk.h): context / batch management and the step drivers.
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
@@ -206,6 +207,12 @@ int ddk_set_batch(DdkCtx* c, const DdkBatch* b, void* stream) {
       b->rec_edge_ptr_h[b->B] != b->ER)
     return fail(c, DDK_ERR_INVALID, "ptr arrays do not match the totals");
   const int B = b->B, NL = b->NL, NR = b->NR, EB = b->EB, ER = b->ER;
+  static const bool timing = getenv("DDK_TIMING") != nullptr;   // host phases of this call on stderr
+  const auto tm0 = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (timing) fprintf(stderr, "[ddk_set_batch] %-10s %8.3f ms\n", what,
+                        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tm0).count());
+  };
   c->B = B; c->NL = NL; c->NR = NR; c->EB = EB; c->ER = ER; c->N = NL + NR;
   c->rec_pos = b->rec_pos; c->mask_rotate = b->mask_rotate; c->bond_attr = b->bond_attr;
   c->lig_latent = b->lig_latent; c->rec_latent = b->rec_latent;
@@ -280,6 +287,7 @@ int ddk_set_batch(DdkCtx* c, const DdkBatch* b, void* stream) {
     for (int e = 0; e < EB; ++e) { int s = 2 * bond_src[e]; static_pos[e] = seg_base[s] + fill[s]++; }
     for (int e = 0; e < ER; ++e) { int s = 2 * (NL + rr_src[e]); static_pos[(size_t)EB + e] = seg_base[s] + fill[s]++; }
   }
+  lap("host lists");
   int rc;
 #define UP(buf, vec) if ((rc = upload(c, buf, vec, st)) != DDK_OK) return rc
   UP(c->b_lig_ptr, lig_ptr); UP(c->b_rec_ptr, rec_ptr); UP(c->b_lig_graph, lig_graph); UP(c->b_rec_graph, rec_graph);
@@ -302,9 +310,11 @@ int ddk_set_batch(DdkCtx* c, const DdkBatch* b, void* stream) {
   EN(c->b_hs, (size_t)std::max<int64_t>(total, 1) * HID * 4);
   EN(c->b_tr, (size_t)B * 3 * 4); EN(c->b_rot, (size_t)B * 3 * 4); EN(c->b_tor, (size_t)std::max(c->RB, 1) * 4);
 #undef EN
+  lap("uploads");
   launch_setup(c, b, b->lig_x, b->rec_x, st);
   DDK_CUDA_TRY(c, cudaGetLastError());
   DDK_CUDA_TRY(c, cudaStreamSynchronize(st));   // host vectors above go out of scope
+  lap("setup+sync");
   c->has_batch = true;
   c->x_final = nullptr;
   return DDK_OK;

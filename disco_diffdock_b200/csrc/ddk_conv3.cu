@@ -24,6 +24,7 @@
 #include <cuda_pipeline_primitives.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <vector>
 
@@ -132,7 +133,14 @@ struct F3Args {
   ClassInfo cls[4];
   int w8off[4];                      // offset of each class inside a weight slice (floats)
   int ncls;
+  unsigned long long* trace;         // DDK_CONV_TRACE: per CTA (start, end, tasks, weight reloads, reload ns, work ns, claim ns); else null
 };
+
+__device__ __forceinline__ unsigned long long f3_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 
 // ---------------------------------------------------------------------------------------------- group work lists
 // Non-empty segments of each edge group (block g = group g), bucketed by their number of 8-edge chunks, longest first:
@@ -702,8 +710,17 @@ __global__ void __launch_bounds__(F3_THREADS, 1) k_conv_fused(const __grid_const
   }
   __syncthreads();
   int nbat = 0;                      // batches handed over so far (same count on both sides of the mbarriers)
+#if DDK_CONV_TRACE     // build with DDK_NVCC_EXTRA=-DDDK_CONV_TRACE=1 (tools/conv_trace.sh); the counters cost registers
+  unsigned long long tr_t0 = 0, tr_a = 0, tr_reload = 0, tr_work = 0, tr_claim = 0, tr_tasks = 0, tr_nrel = 0;
+  const bool tracing = p.trace != nullptr && tid == 0;
+  if (tracing) tr_t0 = f3_now();
+#define F3_TRACE(...) if (tracing) { __VA_ARGS__ }
+#else
+#define F3_TRACE(...)
+#endif
 
   for (;;) {
+    F3_TRACE(tr_a = f3_now();)
     if (tid == 0) {
       int combo = S.task[5], found = 0;
       for (int tries = 0; tries < NCOMBO && !found; ++tries) {
@@ -732,6 +749,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1) k_conv_fused(const __grid_const
     const int g = S.task[0];
     if (g < 0) break;
     const int r = S.task[1], idx0 = S.task[2], nseg = S.task[3];
+    F3_TRACE(const unsigned long long t = f3_now(); tr_claim += t - tr_a; tr_a = t; ++tr_tasks;)
     if (S.task[4]) {
       const float4* src = reinterpret_cast<const float4*>(p.W2S[g] + (size_t)r * Cfg::W * J);
       float4* dst = reinterpret_cast<float4*>(S.Wsl);
@@ -740,6 +758,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1) k_conv_fused(const __grid_const
         for (int i = tid; i < Cfg::W / 4; i += F3_THREADS)
           reinterpret_cast<float4*>(S.Wb)[i] = reinterpret_cast<const float4*>(p.b2p[g])[i];
       __syncthreads();
+      F3_TRACE(const unsigned long long t = f3_now(); tr_reload += t - tr_a; tr_a = t; ++tr_nrel;)
     }
     if (is_acc) {
       if (half == 0) {
@@ -754,7 +773,11 @@ __global__ void __launch_bounds__(F3_THREADS, 1) k_conv_fused(const __grid_const
       else f3_con_task<LV, false>(p, S, r, nseg, w - 2 * F3_ACC, lane, nbat);
     }
     __syncthreads();
+    F3_TRACE(tr_work += f3_now() - tr_a;)
   }
+  F3_TRACE(unsigned long long* o = p.trace + 8 * blockIdx.x;
+           o[0] = tr_t0; o[1] = f3_now(); o[2] = tr_tasks; o[3] = tr_nrel; o[4] = tr_reload; o[5] = tr_work; o[6] = tr_claim;)
+#undef F3_TRACE
 }
 
 // ---------------------------------------------------------------------------------------------- finalize
@@ -998,6 +1021,14 @@ void launch_conv_fused(DdkCtx* c, int layer, const float* x_in, float* x_out, cu
   }
   cudaMemsetAsync(c->b_counters.p, 0, F3_NCOMBO_MAX * sizeof(int), st);
   const int grid = c->sm_count;
+#if DDK_CONV_TRACE
+  static const bool trace_on = getenv("DDK_CONV_TRACE") != nullptr;     // per-CTA timeline summary on stderr (synchronises)
+#else
+  static const bool trace_on = false;
+#endif
+  static unsigned long long* trace_buf = nullptr;
+  if (trace_on && !trace_buf) cudaMalloc(&trace_buf, (size_t)grid * 8 * sizeof(unsigned long long));
+  a.trace = trace_on ? trace_buf : nullptr;
   {
     LaunchScope ls(c, PC_ACC0 + li.lv, st);
     switch (li.lv) {
@@ -1006,6 +1037,23 @@ void launch_conv_fused(DdkCtx* c, int layer, const float* x_in, float* x_out, cu
       case 2: k_conv_fused<2><<<grid, F3_THREADS, sizeof(F3Smem<2>), st>>>(a); break;
       default: k_conv_fused<3><<<grid, F3_THREADS, sizeof(F3Smem<3>), st>>>(a); break;
     }
+  }
+  if (trace_on && trace_buf) {
+    std::vector<unsigned long long> h((size_t)grid * 8);
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h.data(), trace_buf, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    unsigned long long t0 = ~0ull, t1 = 0, first_end = ~0ull;
+    double busy = 0, tasks = 0, nrel = 0, rel = 0, work = 0, claim = 0;
+    for (int b = 0; b < grid; ++b) {
+      const unsigned long long* o = &h[(size_t)b * 8];
+      t0 = std::min(t0, o[0]); t1 = std::max(t1, o[1]); first_end = std::min(first_end, o[1]);
+      busy += (double)(o[1] - o[0]); tasks += (double)o[2]; nrel += (double)o[3]; rel += (double)o[4]; work += (double)o[5]; claim += (double)o[6];
+    }
+    const double span = (double)(t1 - t0);
+    fprintf(stderr, "[conv_trace] layer %d lv %d mode %2d B %4d span %8.1f us  resident %5.1f%%  first CTA done at %5.1f%%  per CTA: tasks %5.1f "
+                    "reloads %4.1f  work %5.1f%%  reload %4.1f%%  claim %4.1f%% of span\n",
+            layer, li.lv, mode, c->B, span / 1e3, 100.0 * busy / grid / span, 100.0 * (double)(first_end - t0) / span, tasks / grid,
+            nrel / grid, 100.0 * work / grid / span, 100.0 * rel / grid / span, 100.0 * claim / grid / span);
   }
   FinArgs f;
   f.N = lig_only ? c->NL : c->N; f.dout = li.dout; f.nsl = nsl;   // ligand nodes come first

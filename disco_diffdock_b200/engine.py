@@ -113,6 +113,98 @@ def _unwrap_mask(m):
     return np.ascontiguousarray(np.asarray(m), dtype=np.uint8)
 
 
+def batch_index_arrays(data, no_torsion: bool):
+    """Host index arrays of a PyG-style batch (utils/sampling.py:56-67): per-graph node / edge offsets, int32 edge lists,
+    the rotatable-bond mask and the flattened ``mask_rotate`` blocks (identical blocks stored once)."""
+    lig, rec = data['ligand'], data['receptor']
+    B = int(data.num_graphs)
+    lb = lig.batch.cpu().long() if 'batch' in lig else torch.zeros(lig.num_nodes, dtype=torch.long)
+    rb = rec.batch.cpu().long() if 'batch' in rec else torch.zeros(rec.num_nodes, dtype=torch.long)
+    lig_ptr = np.concatenate([[0], np.cumsum(np.bincount(lb.numpy(), minlength=B))]).astype(np.int32)
+    rec_ptr = np.concatenate([[0], np.cumsum(np.bincount(rb.numpy(), minlength=B))]).astype(np.int32)
+    bei = data['ligand', 'ligand'].edge_index.cpu().long()
+    rei = data['receptor', 'receptor'].edge_index.cpu().long()
+    bond_index = np.ascontiguousarray(bei.numpy().astype(np.int32))
+    rec_index = np.ascontiguousarray(rei.numpy().astype(np.int32))
+    bond_ptr = np.concatenate([[0], np.cumsum(np.bincount(lb[bei[0]].numpy(), minlength=B))]).astype(np.int32)
+    rec_eptr = np.concatenate([[0], np.cumsum(np.bincount(rb[rei[0]].numpy(), minlength=B))]).astype(np.int32)
+    edge_mask = np.ascontiguousarray(lig.edge_mask.cpu().numpy().astype(np.uint8))
+    RB = int(edge_mask.sum())
+    # mask_rotate: list (one entry per graph, possibly nested) of [R, N] arrays; identical arrays are stored once
+    mr_off = np.zeros(B, dtype=np.int64)
+    mr_flat = None
+    if RB > 0 and not no_torsion:
+        mr = lig.mask_rotate if 'mask_rotate' in lig else None
+        if mr is None:
+            raise RuntimeError('batch has rotatable bonds but no mask_rotate')
+        per_graph = [mr[g] for g in range(B)] if isinstance(mr, (list, tuple)) and len(mr) == B and B > 1 else [mr] * B
+        chunks, off = [], 0
+        for g in range(B):
+            m = _unwrap_mask(per_graph[g])
+            nl = int(lig_ptr[g + 1] - lig_ptr[g])
+            rg = int(edge_mask[bond_ptr[g]:bond_ptr[g + 1]].sum())
+            if m.shape != (rg, nl):
+                raise RuntimeError(f'mask_rotate of graph {g} has shape {m.shape}, expected {(rg, nl)}')
+            found = None
+            for (o, mm) in chunks:      # dedupe equal content (deep copies of one complex)
+                if mm.shape == m.shape and np.array_equal(mm, m):
+                    found = o
+                    break
+            if found is None:
+                chunks.append((off, m))
+                found = off
+                off += m.size
+            mr_off[g] = found
+        mr_flat = np.concatenate([m.ravel() for _, m in chunks]) if chunks else np.zeros(1, np.uint8)
+    host = SimpleNamespace(lig_ptr=lig_ptr, rec_ptr=rec_ptr, bond_index=bond_index, bond_ptr=bond_ptr,
+                           edge_mask=edge_mask, rec_index=rec_index, rec_eptr=rec_eptr, mr_off=mr_off)
+    return host, mr_flat, RB
+
+
+def group_index_arrays(groups, no_torsion: bool):
+    """The same arrays as ``batch_index_arrays`` for a batch given as runs of copies ``[(complex, n_copies), ...]``, built
+    from one graph per run (no PyG collation of the copies); the big edge lists are written once, as int32."""
+    protos = []
+    for proto, n in groups:
+        lig, rec = proto['ligand'], proto['receptor']
+        bei = proto['ligand', 'ligand'].edge_index.cpu().numpy().astype(np.int32)
+        rei = proto['receptor', 'receptor'].edge_index.cpu().numpy().astype(np.int32)
+        em1 = lig.edge_mask.cpu().numpy().astype(np.uint8)
+        protos.append((int(n), int(lig.num_nodes), int(rec.num_nodes), bei, rei, em1, lig))
+    B = sum(p[0] for p in protos)
+    EB = sum(p[0] * p[3].shape[1] for p in protos)
+    ER = sum(p[0] * p[4].shape[1] for p in protos)
+    if max(sum(p[0] * p[1] for p in protos), sum(p[0] * p[2] for p in protos)) >= 2 ** 31:
+        raise RuntimeError('batch too large for 32-bit node indices')
+    bond_index, rec_index = np.empty((2, EB), np.int32), np.empty((2, ER), np.int32)
+    edge_mask, mr_off = np.empty(EB, np.uint8), np.zeros(B, np.int64)
+    counts = np.empty((4, B), np.int64)                       # ligand atoms, residues, bonds, contacts per graph
+    mr_chunks = []
+    lo = ro = mo = RB = g0 = e0 = r0 = 0
+    for n, nl, nr, bei, rei, em1, lig in protos:
+        eb, er = bei.shape[1], rei.shape[1]
+        counts[:, g0:g0 + n] = np.array([[nl], [nr], [eb], [er]])
+        ar = np.arange(n, dtype=np.int32)
+        np.add(bei[:, None, :], (lo + ar * nl)[None, :, None], out=bond_index[:, e0:e0 + n * eb].reshape(2, n, eb))
+        np.add(rei[:, None, :], (ro + ar * nr)[None, :, None], out=rec_index[:, r0:r0 + n * er].reshape(2, n, er))
+        edge_mask[e0:e0 + n * eb].reshape(n, eb)[:] = em1[None, :]
+        r1 = int(em1.sum())
+        RB += r1 * n
+        if r1 > 0 and not no_torsion:
+            m = _unwrap_mask(lig.mask_rotate).ravel()
+            if m.size != r1 * nl:
+                raise RuntimeError('mask_rotate does not match edge_mask / ligand size')
+            mr_chunks.append(m)
+            mr_off[g0:g0 + n] = mo
+            mo += m.size
+        lo += n * nl; ro += n * nr; g0 += n; e0 += n * eb; r0 += n * er
+    cum = lambda c: np.concatenate([[0], np.cumsum(c)]).astype(np.int32)
+    host = SimpleNamespace(lig_ptr=cum(counts[0]), rec_ptr=cum(counts[1]), bond_ptr=cum(counts[2]), rec_eptr=cum(counts[3]),
+                           bond_index=bond_index, rec_index=rec_index, edge_mask=edge_mask, mr_off=mr_off)
+    mr_flat = np.concatenate(mr_chunks) if mr_chunks else None
+    return host, mr_flat, RB
+
+
 class Engine:
     """One ``DdkCtx``: packed weights on one GPU plus the workspace of the current batch."""
 
@@ -163,50 +255,12 @@ class Engine:
         setup kernels.  Returns sizes / index info of the batch."""
         lig, rec = data['ligand'], data['receptor']
         B = int(data.num_graphs)
-        lb = lig.batch.cpu().long() if 'batch' in lig else torch.zeros(lig.num_nodes, dtype=torch.long)
-        rb = rec.batch.cpu().long() if 'batch' in rec else torch.zeros(rec.num_nodes, dtype=torch.long)
-        lig_ptr = np.concatenate([[0], np.cumsum(np.bincount(lb.numpy(), minlength=B))]).astype(np.int32)
-        rec_ptr = np.concatenate([[0], np.cumsum(np.bincount(rb.numpy(), minlength=B))]).astype(np.int32)
-        bei = data['ligand', 'ligand'].edge_index.cpu().long()
-        rei = data['receptor', 'receptor'].edge_index.cpu().long()
-        bond_index = np.ascontiguousarray(bei.numpy().astype(np.int32))
-        rec_index = np.ascontiguousarray(rei.numpy().astype(np.int32))
-        bond_ptr = np.concatenate([[0], np.cumsum(np.bincount(lb[bei[0]].numpy(), minlength=B))]).astype(np.int32)
-        rec_eptr = np.concatenate([[0], np.cumsum(np.bincount(rb[rei[0]].numpy(), minlength=B))]).astype(np.int32)
-        edge_mask = np.ascontiguousarray(lig.edge_mask.cpu().numpy().astype(np.uint8))
-        RB = int(edge_mask.sum())
-        # mask_rotate: list (one entry per graph, possibly nested) of [R, N] arrays; identical arrays are stored once
-        mr_off = np.zeros(B, dtype=np.int64)
-        mr_flat = None
-        if RB > 0 and not self.hyper.no_torsion:
-            mr = lig.mask_rotate if 'mask_rotate' in lig else None
-            if mr is None:
-                raise RuntimeError('batch has rotatable bonds but no mask_rotate')
-            per_graph = [mr[g] for g in range(B)] if isinstance(mr, (list, tuple)) and len(mr) == B and B > 1 else [mr] * B
-            chunks, off = [], 0
-            for g in range(B):
-                m = _unwrap_mask(per_graph[g])
-                nl = int(lig_ptr[g + 1] - lig_ptr[g])
-                rg = int(edge_mask[bond_ptr[g]:bond_ptr[g + 1]].sum())
-                if m.shape != (rg, nl):
-                    raise RuntimeError(f'mask_rotate of graph {g} has shape {m.shape}, expected {(rg, nl)}')
-                found = None
-                for (o, mm) in chunks:      # dedupe equal content (deep copies of one complex)
-                    if mm.shape == m.shape and np.array_equal(mm, m):
-                        found = o
-                        break
-                if found is None:
-                    chunks.append((off, m))
-                    found = off
-                    off += m.size
-                mr_off[g] = found
-            mr_flat = np.concatenate([m.ravel() for _, m in chunks]) if chunks else np.zeros(1, np.uint8)
+        host, mr_flat, RB = batch_index_arrays(data, self.hyper.no_torsion)
+        rec_ptr = host.rec_ptr
         L = self.hyper.latent_dim
         unc = self.hyper.latent_droprate > 0
         nr0 = int(rec_ptr[1])
         share_rec = assume_copies and B > 1 and rec.x.shape[0] == B * nr0
-        host = SimpleNamespace(lig_ptr=lig_ptr, rec_ptr=rec_ptr, bond_index=bond_index, bond_ptr=bond_ptr,
-                               edge_mask=edge_mask, rec_index=rec_index, rec_eptr=rec_eptr, mr_off=mr_off)
         return self._upload(B, RB, host, mr_flat, lig_x=lig.x, bond_attr=data['ligand', 'ligand'].edge_attr,
                             rec_x=rec.x[:nr0] if share_rec else rec.x, rec_pos=rec.pos[:nr0] if share_rec else rec.pos,
                             rec_repeat=B if share_rec else 1, lig_repeat=1,
@@ -217,38 +271,40 @@ class Engine:
     def set_batch_copies(self, proto, B: int) -> SimpleNamespace:
         """``B`` copies of one complex (what ``sampling()`` batches are, utils/sampling.py:57) without materialising the
         PyG batch on the host: the complex is shipped once and replicated on the device."""
-        lig, rec = proto['ligand'], proto['receptor']
-        nl, nr = int(lig.num_nodes), int(rec.num_nodes)
-        bei = proto['ligand', 'ligand'].edge_index.cpu().numpy().astype(np.int64)
-        rei = proto['receptor', 'receptor'].edge_index.cpu().numpy().astype(np.int64)
-        eb, er = bei.shape[1], rei.shape[1]
-        ar = np.arange(B, dtype=np.int64)
-        lig_ptr = (np.arange(B + 1) * nl).astype(np.int32)
-        rec_ptr = (np.arange(B + 1) * nr).astype(np.int32)
-        bond_index = np.ascontiguousarray((bei[:, None, :] + (ar * nl)[None, :, None]).reshape(2, B * eb).astype(np.int32))
-        rec_index = np.ascontiguousarray((rei[:, None, :] + (ar * nr)[None, :, None]).reshape(2, B * er).astype(np.int32))
-        bond_ptr = (np.arange(B + 1) * eb).astype(np.int32)
-        rec_eptr = (np.arange(B + 1) * er).astype(np.int32)
-        em1 = lig.edge_mask.cpu().numpy().astype(np.uint8)
-        edge_mask = np.ascontiguousarray(np.tile(em1, B))
-        RB = int(em1.sum()) * B
-        mr_flat = None
-        if RB > 0 and not self.hyper.no_torsion:
-            mr_flat = _unwrap_mask(lig.mask_rotate).ravel()
-            if mr_flat.size != int(em1.sum()) * nl:
-                raise RuntimeError('mask_rotate does not match edge_mask / ligand size')
-        host = SimpleNamespace(lig_ptr=lig_ptr, rec_ptr=rec_ptr, bond_index=bond_index, bond_ptr=bond_ptr,
-                               edge_mask=edge_mask, rec_index=rec_index, rec_eptr=rec_eptr, mr_off=np.zeros(B, dtype=np.int64))
+        return self.set_batch_groups([(proto, B)])
+
+    def set_batch_groups(self, groups) -> SimpleNamespace:
+        """A batch made of runs of copies: ``groups = [(complex, n_copies), ...]`` in batch order (several complexes of an
+        evaluate.py loop sampled together).  Every complex is shipped once -- its 1.5 MB receptor embedding included -- and
+        replicated on the device; the host only builds the index arrays."""
         if self.hyper.latent_dim > 0:
-            raise RuntimeError('set_batch_copies does not carry per-copy latents; use set_batch')
-        return self._upload(B, RB, host, mr_flat, lig_x=lig.x, bond_attr=proto['ligand', 'ligand'].edge_attr, rec_x=rec.x,
-                            rec_pos=rec.pos, rec_repeat=B, lig_repeat=B, lig_latent=None, rec_latent=None,
-                            lig_uncond=None, rec_uncond=None)
+            raise RuntimeError('set_batch_groups does not carry per-copy latents; use set_batch')
+        dev = self.device
+        host, mr_flat, RB = group_index_arrays(groups, self.hyper.no_torsion)
+        h2d = 0
+
+        def up(x, dtype, n):
+            nonlocal h2d
+            if not x.is_cuda:
+                h2d += x.numel() * torch.empty(0, dtype=dtype).element_size()
+            y = x.to(dev, dtype, non_blocking=True)
+            return y.repeat(n, 1) if n > 1 else y
+
+        cat = lambda parts: parts[0] if len(parts) == 1 else torch.cat(parts, dim=0)
+        lig_x = cat([up(g['ligand'].x, torch.int32, n) for g, n in groups])
+        bond_attr = cat([up(g['ligand', 'ligand'].edge_attr, torch.float32, n) for g, n in groups])
+        rec_x = cat([up(g['receptor'].x, torch.float32, n) for g, n in groups])
+        rec_pos = cat([up(g['receptor'].pos, torch.float32, n) for g, n in groups])
+        B = int(sum(n for _, n in groups))
+        return self._upload(B, RB, host, mr_flat, lig_x=lig_x, bond_attr=bond_attr, rec_x=rec_x, rec_pos=rec_pos,
+                            rec_repeat=1, lig_repeat=1, lig_latent=None, rec_latent=None, lig_uncond=None, rec_uncond=None,
+                            h2d0=h2d)
 
     def _upload(self, B, RB, host, mr_flat, lig_x, bond_attr, rec_x, rec_pos, rec_repeat, lig_repeat, lig_latent, rec_latent,
-                lig_uncond, rec_uncond) -> SimpleNamespace:
+                lig_uncond, rec_uncond, h2d0=0) -> SimpleNamespace:
         dev = self.device
-        h2d = 0
+        h2d = h2d0 + sum(getattr(host, k).nbytes for k in ('lig_ptr', 'rec_ptr', 'bond_index', 'bond_ptr', 'edge_mask',
+                                                           'rec_index', 'rec_eptr', 'mr_off'))
 
         def up(x, dtype, repeat=1, flat=False):
             nonlocal h2d

@@ -85,6 +85,33 @@ def torsion_update_host(pos, edge_index, mask_rotate, torsion_updates):
     return torch.from_numpy(p.astype(np.float32))
 
 
+def _same_complex(a, b):
+    """Is graph ``b`` a copy of complex ``a`` (evaluate.py:229 deep-copies one complex N times)?  Shared storage answers
+    without reading; otherwise every static tensor must have the same shape and the receptor positions, ligand atom
+    features and bonds the same content (every reference caller passes copies of ONE complex; two different complexes
+    with identical C-alpha coordinates, ligand atoms and bonds do not occur)."""
+    la, lb, ra, rb = a['ligand'], b['ligand'], a['receptor'], b['receptor']
+    if la.x.shape != lb.x.shape or ra.x.shape != rb.x.shape:
+        return False
+    ea, eb = a['ligand', 'ligand'].edge_index, b['ligand', 'ligand'].edge_index
+    if ra.x.data_ptr() == rb.x.data_ptr() and la.x.data_ptr() == lb.x.data_ptr() and ea.data_ptr() == eb.data_ptr():
+        return True
+    if ea.shape != eb.shape or a['receptor', 'receptor'].edge_index.shape != b['receptor', 'receptor'].edge_index.shape:
+        return False
+    return bool(torch.equal(ra.pos, rb.pos) and torch.equal(la.x, lb.x) and torch.equal(ea, eb))
+
+
+def group_copies(items):
+    """Runs of consecutive copies of one complex: [(first graph of the run, run length), ...]."""
+    groups = []
+    for g in items:
+        if groups and _same_complex(groups[-1][0], g):
+            groups[-1][1] += 1
+        else:
+            groups.append([g, 1])
+    return [(g, n) for g, n in groups]
+
+
 _STEP_TABLE_CACHE = {}
 
 
@@ -153,7 +180,7 @@ def _build_step_tables(score_model, model_args, t_to_sigma, tr_schedule, rot_sch
                       torch.stack(tors), coef)
 
 
-def _sample_with_guidance(sm, eng, batch, start_pos, steps, z, tr_schedule, weight, cfg_start, cfg_end, device):
+def _sample_with_guidance(sm, eng, batch, start_pos, steps, z, tr_schedule, weight, cfg_start, cfg_end, device, copies=True):
     """Classifier-free guidance (utils/sampling.py:119-135): inside [cfg_end, cfg_start] every reverse step evaluates the score
     model twice -- with the latents, and with ``unconditional = 1`` and zeroed latents -- and extrapolates
     ``s + w (s - s_uncond)``.  The two branches live in two libddk contexts over the same pose buffer (the latents enter the
@@ -166,7 +193,7 @@ def _sample_with_guidance(sm, eng, batch, start_pos, steps, z, tr_schedule, weig
     for nt in ('ligand', 'receptor'):
         ub[nt].unconditional = torch.ones(batch[nt].num_nodes, 1)
         ub[nt].latent_h = torch.zeros_like(batch[nt].latent_h)
-    eng_u.set_batch(ub, assume_copies=True)
+    eng_u.set_batch(ub, assume_copies=copies)
     pos = start_pos.to(device, torch.float32).contiguous().clone()
     dev = lambda t: None if t is None else t.to(device, torch.float32).contiguous()
     for i in range(steps.n_steps):
@@ -202,7 +229,8 @@ def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_s
     pose0 = 0
     with torch.no_grad():
         n_batches = (N + batch_size - 1) // batch_size
-        fast = not latent and confidence_model is None      # copies of one complex: no host-side PyG collation needed
+        fast = not latent and confidence_model is None      # runs of copies: no host-side PyG collation needed
+        tor0 = 0
         for batch_id in range(n_batches):
             items = data_list[batch_id * batch_size:(batch_id + 1) * batch_size]
             b = len(items)
@@ -210,7 +238,7 @@ def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_s
             if fast:
                 batch = None
                 start_pos = torch.cat([x['ligand'].pos for x in items], dim=0)
-                info = eng.set_batch_copies(items[0], b)
+                info = eng.set_batch_groups(group_copies(items))
             else:
                 batch = Batch.from_data_list(items)
                 if latent:
@@ -227,7 +255,8 @@ def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_s
                     batch['ligand'].unconditional = torch.zeros(batch['ligand'].num_nodes, 1)
                     batch['receptor'].unconditional = torch.zeros(batch['receptor'].num_nodes, 1)
                 start_pos = batch['ligand'].pos
-                info = eng.set_batch(batch, assume_copies=True)
+                copies = len(group_copies(items)) == 1
+                info = eng.set_batch(batch, assume_copies=copies)
             eng._batch_key = None
             steps = build_step_tables(sm, model_args, t_to_sigma, tr_schedule, rot_schedule, tor_schedule, inference_steps, b,
                                       temp_sampling, temp_psi, temp_sigma_data, ode)
@@ -235,9 +264,8 @@ def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_s
             if no_random or ode:
                 z = None
             elif noise is not None:
-                per = R // b if b else 0
                 z = {'tr': noise['tr'][:, pose0:pose0 + b], 'rot': noise['rot'][:, pose0:pose0 + b],
-                     'tor': noise['tor'][:, pose0 * per:(pose0 + b) * per] if R else None}
+                     'tor': noise['tor'][:, tor0:tor0 + R] if R else None}
             else:
                 zdev = torch.device('cpu') if host_buffers else device
                 z = {'tr': torch.randn(inference_steps, b, 3, device=zdev, generator=generator),
@@ -249,7 +277,7 @@ def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_s
                             v[-1] = 0
             if cfg_on:
                 pos = _sample_with_guidance(sm, eng, batch, start_pos, steps, z, tr_schedule, classifier_free_guidance_weight,
-                                            cfg_start, cfg_end, device)
+                                            cfg_start, cfg_end, device, copies)
             elif host_buffers:
                 pos = start_pos.detach().to('cpu', torch.float32).contiguous()
                 eng.sample_host(pos, steps, z)
@@ -258,14 +286,14 @@ def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_s
                 eng.sample(pos, steps, z)
             if batch is not None:
                 batch['ligand'].pos = pos
-            len_lig = pos.shape[0] // b
+            lp = info.lig_ptr
             for i in range(b):
-                data_list[batch_id * batch_size + i]['ligand'].pos = pos[i * len_lig:(i + 1) * len_lig]
+                data_list[batch_id * batch_size + i]['ligand'].pos = pos[int(lp[i]):int(lp[i + 1])]
                 if latent:                                                      # utils/sampling.py:205-222
                     item = data_list[batch_id * batch_size + i]
-                    len_rec = batch['receptor'].num_nodes // b
-                    lig_lat = batch['ligand'].latent_h[i * len_lig:(i + 1) * len_lig]
-                    rec_lat = batch['receptor'].latent_h[i * len_rec:(i + 1) * len_rec]
+                    rp = info.rec_ptr
+                    lig_lat = batch['ligand'].latent_h[int(lp[i]):int(lp[i + 1])]
+                    rec_lat = batch['receptor'].latent_h[int(rp[i]):int(rp[i + 1])]
                     item['ligand'].latent_h = lig_lat
                     centre = item.original_center.detach().cpu() if 'original_center' in item else torch.zeros(1, 3)
                     lat_str, lat_pos = '', []
@@ -281,6 +309,7 @@ def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_s
                     item.latent_str = lat_str
                     item.latent_pos = torch.cat(lat_pos, dim=0)
             pose0 += b
+            tor0 += R
             if visualization_list is not None:
                 for idx, vis in enumerate(visualization_list):
                     vis.add((data_list[idx]['ligand'].pos.detach().cpu() + data_list[idx].original_center.detach().cpu()),

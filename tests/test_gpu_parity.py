@@ -307,3 +307,60 @@ def test_forward_large_receptor_stress():
     dump('large_receptor', d)
     assert d['edges'] > 2 * 2 * 120 * 2000 * 0.95
     assert max(d['tr'], d['rot'], d['tor']) < 5e-5, d
+
+
+def test_batched_inference_matches_per_complex_calls():
+    """the evaluate.py-style driver sampling several complexes in one call (runs of copies, one ddk batch)
+    gives bit-identical poses to one sampling() call per complex, and those match the oracle."""
+    from functools import partial
+    from disco_diffdock_b200 import inference
+    m, sd, cfg = helpers.make_model(2, gain=5.0)
+    m = m.to('cuda')
+    N, steps = 4, 12
+    gs = [synthetic.make_complex(71, 18, 40), synthetic.make_complex(72, 26, 64), synthetic.make_complex(73, 9, 17)]
+    gs[2]['ligand'].edge_mask = torch.zeros_like(gs[2]['ligand'].edge_mask)
+    gs[2]['ligand'].mask_rotate = np.zeros((0, 9), dtype=bool)
+    for g in gs:
+        g['ligand'].orig_pos = g['ligand'].pos.numpy().copy()
+    complexes = [synthetic.as_loader_item(g) for g in gs]
+    Rs = [int(g['ligand'].edge_mask.sum()) for g in gs]
+    zs = [helpers.draw_noise(20 + i, steps, N, Rs[i]) for i in range(3)]
+
+    def noise_fn(first, flat):
+        sel = zs[first:first + len(flat) // N]
+        return {k: torch.cat([z[k] for z in sel], dim=1) for k in ('tr', 'rot', 'tor')}
+
+    t2s = partial(du.t_to_sigma, args=cfg)
+    res = {}
+    for per_call in (1, 3, 2):
+        np.random.seed(5); torch.manual_seed(5)
+        res[per_call] = inference.run_inference(complexes, m, cfg, torch.device('cuda'), t2s, samples_per_complex=N,
+                                                inference_steps=steps, complexes_per_call=per_call, noise_fn=noise_fn,
+                                                no_final_step_noise=True, **helpers.README_TEMPS)
+    diffs = {}
+    for per_call in (3, 2):
+        for i in range(3):
+            a = np.stack([g['ligand'].pos.cpu().numpy() for g in res[1]['data_lists'][i]])
+            b = np.stack([g['ligand'].pos.cpu().numpy() for g in res[per_call]['data_lists'][i]])
+            diffs[f'{per_call}_{i}'] = float(np.abs(a - b).max())
+        assert res[per_call]['names'] == ['synth_71', 'synth_72', 'synth_73']
+        assert np.array_equal(np.array(res[per_call]['rmsds']), np.array(res[1]['rmsds']))
+    # oracle on complex 1 from the same start poses
+    np.random.seed(5); torch.manual_seed(5)
+    start = []
+    for i in range(3):
+        dl = [copy.deepcopy(complexes[i]) for _ in range(N)]
+        dsampling.randomize_position(dl, False, False, cfg.tr_sigma_max)
+        start.append(dl)
+    lst = []
+    for k in range(N):
+        g = copy.deepcopy(gs[1]); g['ligand'].pos = start[1][k]['ligand'].pos.clone(); lst.append(g)
+    batch = ddata.Batch.from_data_list(lst)
+    sched = du.get_t_schedule(steps)
+    with torch.no_grad():
+        want = restate.sample(sd, cfg, batch, load_tables(), sched, zs[1], inference_steps=steps, **helpers.README_TEMPS)
+    got = torch.cat([g['ligand'].pos.cpu() for g in res[3]['data_lists'][1]])
+    rmsd = helpers.rmsd_per_pose(want, got, N)
+    dump('batched_inference', {'max_abs_diff_vs_per_complex': diffs, 'rmsd_vs_oracle': rmsd.tolist()})
+    assert max(diffs.values()) == 0.0, diffs
+    assert float(rmsd.max()) < 1e-3, rmsd

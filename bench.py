@@ -311,8 +311,17 @@ def main():
     sm_mhz = clocks.get('sm_mhz') or peaks_raw.get('sm_max_mhz', 1965.0)
     fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
     conv_ms = sum(prof[k][0] for k in ('conv_accum_lv0', 'conv_accum_lv1', 'conv_accum_lv2', 'conv_accum_lv3'))
+    # DRAM bytes per launch of this kernel from the committed ncu pass over this very command (tools/gpu_round.sh,
+    # tools/launch_summary.py); null when the capture is absent
+    traffic, traffic_src = None, None
+    tj = os.path.join(ROOT, 'profiles', 'conv_fused3_traffic.json')
+    if os.path.exists(tj) and n_complex == N_COMPLEX:
+        td = json.load(open(tj))
+        traffic, traffic_src = td['dram_bytes_per_launch'], 'profiles/conv_fused3_traffic.json (' + td['source'] + ')'
     roofline = {'kernel': 'k_conv_fused<3>', 'bound': 'hbm', 'achieved': bytes_launch / t_launch / 1e9, 'peak': hbm_peak,
-                'unit': 'GB/s', 'frac': bytes_launch / t_launch / 1e9 / hbm_peak, 'traffic': None, 'peak_source': peak_src,
+                'unit': 'GB/s', 'frac': bytes_launch / t_launch / 1e9 / hbm_peak, 'traffic': traffic,
+                'traffic_unit': 'bytes per launch', 'traffic_source': traffic_src, 'algorithmic_bytes_per_launch': bytes_launch,
+                'peak_source': peak_src,
                 'launch_ms': t_launch * 1000, 'launches': acc_n, 'share_of_step': acc_ms / max(total_prof_ms, 1e-9),
                 'conv_share_of_step': conv_ms / max(total_prof_ms, 1e-9),
                 'edges_per_launch': e_launch, 'segments_per_launch': s_launch,

@@ -236,15 +236,21 @@ int ddk_set_batch(DdkCtx* c, const DdkBatch* b, void* stream) {
   c->slot_ll = EB; c->slot_lr = EB + LL; c->slot_rr = EB + LL + LR; c->P = c->slot_rr + ER;
   if (c->P >= ((int64_t)1 << 31)) return fail(c, DDK_ERR_INVALID, "batch too large for 32-bit edge slots");
 
-  // bonds, rotatable bonds
-  std::vector<int> bond_src(b->bond_index_h, b->bond_index_h + EB), bond_dst(b->bond_index_h + EB, b->bond_index_h + 2 * EB);
-  std::vector<int> rr_src(b->rec_index_h, b->rec_index_h + ER), rr_dst(b->rec_index_h + ER, b->rec_index_h + 2 * ER);
+  // bonds, rotatable bonds.  The edge arrays of the caller are read in place (they are uploaded from there too): at 400
+  // poses the receptor contacts alone are 2.9 M edges, and copies / separate passes showed up in the end-to-end time.
+  const int* bond_src = b->bond_index_h; const int* bond_dst = b->bond_index_h + EB;
+  const int* rr_src = b->rec_index_h;    const int* rr_dst = b->rec_index_h + ER;
   std::vector<int> rot_u, rot_v, rot_graph, rot_ptr(B + 1, 0);
+  const int nsegs = 2 * (NL + NR);
+  std::vector<int> seg_static(nsegs, 0), seg_base(nsegs + 1, 0);
+  std::vector<int> static_pos((size_t)EB + ER);       // position of every static edge inside its segment (edge order)
   for (int g = 0; g < B; ++g) {
+    const int l0 = lig_ptr[g], l1 = lig_ptr[g + 1];
     for (int e = b->bond_ptr_h[g]; e < b->bond_ptr_h[g + 1]; ++e) {
-      if (bond_src[e] < lig_ptr[g] || bond_src[e] >= lig_ptr[g + 1] || bond_dst[e] < lig_ptr[g] || bond_dst[e] >= lig_ptr[g + 1])
-        return fail(c, DDK_ERR_INVALID, "bond crosses a graph boundary");
-      if (b->edge_mask_h[e]) { rot_u.push_back(bond_src[e]); rot_v.push_back(bond_dst[e]); rot_graph.push_back(g); }
+      const int u = bond_src[e], v = bond_dst[e];
+      if (u < l0 || u >= l1 || v < l0 || v >= l1) return fail(c, DDK_ERR_INVALID, "bond crosses a graph boundary");
+      if (b->edge_mask_h[e]) { rot_u.push_back(u); rot_v.push_back(v); rot_graph.push_back(g); }
+      static_pos[e] = seg_static[2 * u]++;
     }
     rot_ptr[g + 1] = (int)rot_u.size();
   }
@@ -254,44 +260,51 @@ int ddk_set_batch(DdkCtx* c, const DdkBatch* b, void* stream) {
     return fail(c, DDK_ERR_INVALID, "mask_rotate required");
   std::vector<int64_t> mr_off(B, 0);
   if (b->mask_rotate_off_h) mr_off.assign(b->mask_rotate_off_h, b->mask_rotate_off_h + B);
-  for (int e = 0; e < ER; ++e) {
-    int g = rec_graph[std::min(std::max(rr_src[e], 0), NR - 1)];
-    if (rr_src[e] < 0 || rr_src[e] >= NR || rr_dst[e] < rec_ptr[g] || rr_dst[e] >= rec_ptr[g + 1])
-      return fail(c, DDK_ERR_INVALID, "receptor edge crosses a graph boundary");
+  for (int g = 0; g < B; ++g) {
+    const int r0 = rec_ptr[g], r1 = rec_ptr[g + 1];
+    const int e0 = b->rec_edge_ptr_h[g], e1 = b->rec_edge_ptr_h[g + 1];
+    if (e0 < 0 || e1 < e0 || e1 > ER) return fail(c, DDK_ERR_INVALID, "bad receptor edge offsets");
+    for (int e = e0; e < e1; ++e) {
+      const int u = rr_src[e], v = rr_dst[e];
+      if (u < r0 || u >= r1 || v < r0 || v >= r1) return fail(c, DDK_ERR_INVALID, "receptor edge crosses a graph boundary");
+      static_pos[(size_t)EB + e] = seg_static[2 * (NL + u)]++;
+    }
   }
 
-  // segments: (node, group) -> list of (edge slot, destination node)
-  const int nsegs = 2 * (NL + NR);
-  std::vector<int> seg_static(nsegs, 0), seg_cap(nsegs, 0), seg_base(nsegs + 1, 0);
-  for (int e = 0; e < EB; ++e) seg_static[2 * bond_src[e]]++;
-  for (int e = 0; e < ER; ++e) seg_static[2 * (NL + rr_src[e])]++;
-  for (int n = 0; n < NL; ++n) {
-    int g = lig_graph[n], nl = lig_ptr[g + 1] - lig_ptr[g], nr = rec_ptr[g + 1] - rec_ptr[g];
-    seg_cap[2 * n] = seg_static[2 * n] + nl - 1;
-    seg_cap[2 * n + 1] = nr;
+  // segments: (node, group) -> list of (edge slot, destination node); capacity = static edges + every possible dynamic one
+  {
+    int64_t total = 0;
+    for (int g = 0; g < B; ++g) {
+      const int nl = lig_ptr[g + 1] - lig_ptr[g], nr = rec_ptr[g + 1] - rec_ptr[g];
+      for (int n = lig_ptr[g]; n < lig_ptr[g + 1]; ++n) {
+        seg_base[2 * n] = (int)total; total += seg_static[2 * n] + nl - 1;
+        seg_base[2 * n + 1] = (int)total; total += nr;
+      }
+    }
+    for (int g = 0; g < B; ++g) {
+      const int nl = lig_ptr[g + 1] - lig_ptr[g];
+      for (int r = rec_ptr[g]; r < rec_ptr[g + 1]; ++r) {
+        seg_base[2 * (NL + r)] = (int)total; total += seg_static[2 * (NL + r)];
+        seg_base[2 * (NL + r) + 1] = (int)total; total += nl;
+      }
+    }
+    if (total >= ((int64_t)1 << 31)) return fail(c, DDK_ERR_INVALID, "batch too large for 32-bit list offsets");
+    c->list_total = total;
   }
-  for (int r = 0; r < NR; ++r) {
-    int g = rec_graph[r], nl = lig_ptr[g + 1] - lig_ptr[g];
-    seg_cap[2 * (NL + r)] = seg_static[2 * (NL + r)];
-    seg_cap[2 * (NL + r) + 1] = nl;
-  }
-  int64_t total = 0;
-  for (int s = 0; s < nsegs; ++s) { seg_base[s] = (int)total; total += seg_cap[s]; }
-  if (total >= ((int64_t)1 << 31)) return fail(c, DDK_ERR_INVALID, "batch too large for 32-bit list offsets");
-  c->list_total = total;
   // static list entries (covalent bonds, receptor contacts) sit at the head of their segment, in edge order; only their
   // positions travel to the device (k_fill_static_lists writes them), not the whole capacity-sized list
-  std::vector<int> static_pos((size_t)EB + ER);
-  {
-    std::vector<int> fill(nsegs, 0);
-    for (int e = 0; e < EB; ++e) { int s = 2 * bond_src[e]; static_pos[e] = seg_base[s] + fill[s]++; }
-    for (int e = 0; e < ER; ++e) { int s = 2 * (NL + rr_src[e]); static_pos[(size_t)EB + e] = seg_base[s] + fill[s]++; }
-  }
+  for (int e = 0; e < EB; ++e) static_pos[e] += seg_base[2 * bond_src[e]];
+  for (int e = 0; e < ER; ++e) static_pos[(size_t)EB + e] += seg_base[2 * (NL + rr_src[e])];
+  const int64_t total = c->list_total;
   lap("host lists");
   int rc;
 #define UP(buf, vec) if ((rc = upload(c, buf, vec, st)) != DDK_OK) return rc
   UP(c->b_lig_ptr, lig_ptr); UP(c->b_rec_ptr, rec_ptr); UP(c->b_lig_graph, lig_graph); UP(c->b_rec_graph, rec_graph);
-  UP(c->b_bond_src, bond_src); UP(c->b_bond_dst, bond_dst); UP(c->b_rr_src, rr_src); UP(c->b_rr_dst, rr_dst);
+#define UPP(buf, p_, n_)                                                                                   \
+  if ((rc = ensure(c, buf, (size_t)(n_) * sizeof(int))) != DDK_OK) return rc;                              \
+  if ((n_) > 0) DDK_CUDA_TRY(c, cudaMemcpyAsync(buf.p, p_, (size_t)(n_) * sizeof(int), cudaMemcpyHostToDevice, st))
+  UPP(c->b_bond_src, bond_src, EB); UPP(c->b_bond_dst, bond_dst, EB); UPP(c->b_rr_src, rr_src, ER); UPP(c->b_rr_dst, rr_dst, ER);
+#undef UPP
   UP(c->b_rot_u, rot_u); UP(c->b_rot_v, rot_v); UP(c->b_rot_ptr, rot_ptr); UP(c->b_rot_graph, rot_graph); UP(c->b_mr_off, mr_off);
   UP(c->b_ll_off, ll_off); UP(c->b_lr_off, lr_off);
   seg_base.resize(nsegs);

@@ -56,6 +56,17 @@ __device__ __forceinline__ bool f3_mbar_try(unsigned long long* bar, int parity)
       "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(f3_smem_addr(bar)), "r"(parity) : "memory");
   return ok != 0;
 }
+// Bulk asynchronous copy global -> shared (TMA engine, SASS UBLKCP) that completes on an mbarrier: the resident weight
+// slice of a combo is one contiguous block of up to 69 KB, so a single elected thread moves it with one instruction
+// instead of a 640-thread float4 loop.  size: multiple of 16 bytes; dst / src 16-byte aligned.
+__device__ __forceinline__ void f3_bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(f3_smem_addr(dst)), "l"(src), "r"(bytes), "r"(f3_smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void f3_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}"
+               ::"r"(f3_smem_addr(bar)), "r"(bytes) : "memory");
+}
 // waiting warps back off between probes so they do not take issue slots from the warps they are waiting for
 __device__ __forceinline__ void f3_mbar_wait(unsigned long long* bar, int parity) {
   if (f3_mbar_try(bar, parity)) return;
@@ -107,8 +118,9 @@ struct F3Smem {
   } st[F3_ACC];
   alignas(16) float tile[F3_CON][F3_ACC][D];                 // per contraction warp partial outputs of a batch
   alignas(8) unsigned long long bar_full, bar_empty;         // mbarriers, see f3_mbar_*
+  alignas(8) unsigned long long bar_w;                       // completion of the weight-slice bulk copy
   int meta[F3_ACC];                                          // segment id of each slot of the batch in flight (-1: none)
-  int task[8];                                               // g, r, idx0, nseg, reload, combo cursor, resident combo
+  int task[8];                                               // g, r, idx0, nseg, reload, combo cursor, resident combo, reloads so far
 };
 
 struct F3Args {
@@ -704,9 +716,11 @@ __global__ void __launch_bounds__(F3_THREADS, 1) k_conv_fused(const __grid_const
     for (int k = 0; k < 3; ++k) { LB.gx[k] = lt.gi[k]; LB.gs[k] = lt.gm[k]; LB.gf[k] = lt.gf[k]; }
   }
   if (tid == 0) {
-    S.task[5] = blockIdx.x % NCOMBO; S.task[6] = -1;
+    S.task[5] = blockIdx.x % NCOMBO; S.task[6] = -1; S.task[7] = 0;
     f3_mbar_init(&S.bar_full, 2 * F3_ACC);
     f3_mbar_init(&S.bar_empty, F3_CON);
+    f3_mbar_init(&S.bar_w, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");   // the init is visible to the async proxy
   }
   __syncthreads();
   int nbat = 0;                      // batches handed over so far (same count on both sides of the mbarriers)
@@ -736,6 +750,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1) k_conv_fused(const __grid_const
             S.task[0] = g; S.task[1] = combo % NSLV; S.task[2] = start;
             S.task[3] = min(size, gn - start);
             S.task[4] = (combo != S.task[6]);
+            if (combo != S.task[6]) S.task[7] += 1;
             S.task[5] = combo; S.task[6] = combo;
             found = 1;
             break;
@@ -751,13 +766,17 @@ __global__ void __launch_bounds__(F3_THREADS, 1) k_conv_fused(const __grid_const
     const int r = S.task[1], idx0 = S.task[2], nseg = S.task[3];
     F3_TRACE(const unsigned long long t = f3_now(); tr_claim += t - tr_a; tr_a = t; ++tr_tasks;)
     if (S.task[4]) {
-      const float4* src = reinterpret_cast<const float4*>(p.W2S[g] + (size_t)r * Cfg::W * J);
-      float4* dst = reinterpret_cast<float4*>(S.Wsl);
-      for (int i = tid; i < Cfg::W * J / 4; i += F3_THREADS) dst[i] = src[i];
-      if (r == 0)
-        for (int i = tid; i < Cfg::W / 4; i += F3_THREADS)
-          reinterpret_cast<float4*>(S.Wb)[i] = reinterpret_cast<const float4*>(p.b2p[g])[i];
-      __syncthreads();
+      // every read of the previous slice happened before the __syncthreads that ended the previous task; the proxy fence
+      // orders those generic-proxy reads before the async-proxy writes of the copy
+      if (tid == 0) {
+        constexpr unsigned wbytes = Cfg::W * J * sizeof(float), bbytes = Cfg::W * sizeof(float);
+        static_assert(wbytes % 16 == 0 && bbytes % 16 == 0, "bulk copies move multiples of 16 bytes");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        f3_mbar_expect_tx(&S.bar_w, wbytes + (r == 0 ? bbytes : 0u));
+        f3_bulk_g2s(S.Wsl, p.W2S[g] + (size_t)r * Cfg::W * J, wbytes, &S.bar_w);
+        if (r == 0) f3_bulk_g2s(S.Wb, p.b2p[g], bbytes, &S.bar_w);
+      }
+      f3_mbar_wait(&S.bar_w, (S.task[7] - 1) & 1);
       F3_TRACE(const unsigned long long t = f3_now(); tr_reload += t - tr_a; tr_a = t; ++tr_nrel;)
     }
     if (is_acc) {

@@ -364,3 +364,39 @@ def test_batched_inference_matches_per_complex_calls():
     dump('batched_inference', {'max_abs_diff_vs_per_complex': diffs, 'rmsd_vs_oracle': rmsd.tolist()})
     assert max(diffs.values()) == 0.0, diffs
     assert float(rmsd.max()) < 1e-3, rmsd
+
+
+def test_radius_truncation_at_32_neighbours():
+    """torch_cluster's max_num_neighbors rule: a compact ligand in which atoms have more than 32 neighbours
+    within 5 A (radius_graph asks for 33 incl. the self loop, keeps the first by ascending index) and rotatable-bond
+    midpoints with more than 32 atoms in range (score_model.py:425-438).  Edge multiset bit-exact, scores vs oracle."""
+    from collections import Counter
+    m, sd, cfg = helpers.make_model(31)
+    m = m.to('cuda')
+    g = synthetic.make_complex(81, 48, 40)
+    c = g['ligand'].pos.mean(0, keepdim=True)
+    g['ligand'].pos = (g['ligand'].pos - c) * 0.3 + c                                  # 48 atoms inside a ~4 A ball
+    lst = []
+    gen = torch.Generator().manual_seed(5)
+    for k in range(3):
+        x = copy.deepcopy(g)
+        x['ligand'].pos = x['ligand'].pos + torch.randn(48, 3, generator=gen) * 0.3 + torch.randn(1, 3, generator=gen)
+        lst.append(x)
+    deg = max(int((torch.cdist(x['ligand'].pos, x['ligand'].pos) < 5.0).sum(1).max()) - 1 for x in lst)
+    assert deg > 32, deg                                                             # the rule is exercised
+    batch = ddata.Batch.from_data_list(lst)
+    restate.set_time(batch, 0.4, 0.4, 0.4, 3)
+    (tr_o, rot_o, tor_o), trc = oracle_forward(sd, cfg, batch)
+    tr, rot, tor = m(batch)
+    eng = m.engine()
+    groups = edge_sets_from_engine(eng, eng.batch_info)
+    got0 = Counter((s, d) for s, d, _ in groups[0])
+    want0 = Counter(zip(trc['ll_src'].tolist(), trc['ll_dst'].tolist()))
+    n_radius = len(trc['ll_src']) - batch['ligand', 'ligand'].edge_index.shape[1]
+    d = {'max_degree': deg, 'radius_edges': n_radius, 'untruncated': int(sum(int((torch.cdist(x['ligand'].pos, x['ligand'].pos) < 5.0).sum()) - 48 for x in lst)),
+         'tr': rel_err(tr, tr_o), 'rot': rel_err(rot, rot_o), 'tor': rel_err(tor, tor_o)}
+    dump('truncation', d)
+    assert d['radius_edges'] < d['untruncated']                                      # something was cut
+    assert got0 == want0, 'ligand-ligand edge multiset differs under truncation'
+    assert eng.last_edge_count() == trc['n_edges']
+    assert max(d['tr'], d['rot'], d['tor']) < 2e-5, d

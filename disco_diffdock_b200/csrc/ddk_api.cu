@@ -129,6 +129,14 @@ int ddk_create(const DdkConfig* cfg, const float* weights_h, size_t n_floats, co
   if ((e = cudaMemset(c->b_edge_total.p, 0, ncounter)) != cudaSuccess) return bail("cudaMemset(counter)", e);
   if ((e = heads_configure()) != cudaSuccess) return bail("cudaFuncSetAttribute(heads)", e);
   if ((e = conv3_configure()) != cudaSuccess) return bail("cudaFuncSetAttribute(conv3)", e);
+  if ((e = conv_tc_configure()) != cudaSuccess) return bail("cudaFuncSetAttribute(conv_tc)", e);
+  {
+    std::vector<TcRow> rows((size_t)4 * TC_MAXROWS);
+    for (int lv = 0; lv < 4; ++lv) build_tc_rows(lv, rows.data() + (size_t)lv * TC_MAXROWS);
+    if ((e = cudaMalloc(&c->tc_rows, rows.size() * sizeof(TcRow))) != cudaSuccess) return bail("cudaMalloc(tc_rows)", e);
+    if ((e = cudaMemcpy(c->tc_rows, rows.data(), rows.size() * sizeof(TcRow), cudaMemcpyHostToDevice)) != cudaSuccess)
+      return bail("cudaMemcpy(tc_rows)", e);
+  }
   {
     cudaDeviceProp prop;
     if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
@@ -182,12 +190,14 @@ int ddk_destroy(DdkCtx* c) {
                 &c->b_lr_off, &c->b_seg_base, &c->b_seg_static, &c->b_seg_cnt, &c->b_seg_list,
                 &c->b_lig_static, &c->b_rec_static, &c->b_rr_pre, &c->b_ea_pool, &c->b_sh_pool, &c->b_tb,
                 &c->b_xa, &c->b_xb, &c->b_proj, &c->b_tr, &c->b_rot, &c->b_tor, &c->b_pos, &c->b_step, &c->b_edge_total,
-                &c->b_glist, &c->b_gcnt, &c->b_counters, &c->b_part, &c->b_hs, &c->b_need, &c->b_static_pos};
+                &c->b_glist, &c->b_gcnt, &c->b_counters, &c->b_part, &c->b_hs, &c->b_need, &c->b_static_pos,
+                &c->b_tc_scratch};
   for (Buf* b : all) free_buf(*b);
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   if (c->w) cudaFree(c->w);
   if (c->w2s) cudaFree(c->w2s);
   if (c->ltab) cudaFree(c->ltab);
+  if (c->tc_rows) cudaFree(c->tc_rows);
   delete c;
   return DDK_OK;
 }
@@ -317,10 +327,16 @@ int ddk_set_batch(DdkCtx* c, const DdkBatch* b, void* stream) {
   EN(c->b_tb, (size_t)B * TB_COUNT * NS * 4);
   EN(c->b_xa, (size_t)c->N * D * 4); EN(c->b_xb, (size_t)c->N * D * 4); EN(c->b_proj, (size_t)c->N * 4 * HID * 4);
   c->nhop = std::min(F3_MAXHOP, c->cfg.num_conv_layers - 1);
-  EN(c->b_glist, ((size_t)nsegs + (size_t)c->nhop * NR) * 16); EN(c->b_gcnt, F3_NLIST * 4); EN(c->b_counters, 4 * NSL_MAX * 4);
+  EN(c->b_glist, ((size_t)nsegs + (size_t)c->nhop * NR) * 16); EN(c->b_gcnt, (F3_NLIST + 4) * 4); EN(c->b_counters, 4 * NSL_MAX * 4);
   EN(c->b_need, (size_t)std::max(1, c->nhop) * NR);
   EN(c->b_part, (size_t)nsegs * NSL_MAX * D * 4);
   EN(c->b_hs, (size_t)std::max<int64_t>(total, 1) * HID * 4);
+  c->tc_cap = 0;
+  if (tc_enabled()) {   // A_s scratch of the tensor-core path: one block per ligand atom, capped at 4 GB
+    const size_t per = tc_scratch_floats_per_segment() * sizeof(float);
+    c->tc_cap = (int)std::min<size_t>((size_t)NL, ((size_t)4 << 30) / per);
+    EN(c->b_tc_scratch, (size_t)c->tc_cap * per);
+  }
   EN(c->b_tr, (size_t)B * 3 * 4); EN(c->b_rot, (size_t)B * 3 * 4); EN(c->b_tor, (size_t)std::max(c->RB, 1) * 4);
 #undef EN
   lap("uploads");

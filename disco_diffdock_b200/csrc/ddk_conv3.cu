@@ -121,6 +121,7 @@ struct F3Smem {
   alignas(8) unsigned long long bar_w;                       // completion of the weight-slice bulk copy
   int meta[F3_ACC];                                          // segment id of each slot of the batch in flight (-1: none)
   int task[8];                                               // g, r, idx0, nseg, reload, combo cursor, resident combo, reloads so far
+  int ntc;                                                   // entries at the head of the task's work list whose A blocks come from k_acc_tc
 };
 
 struct F3Args {
@@ -145,6 +146,9 @@ struct F3Args {
   ClassInfo cls[4];
   int w8off[4];                      // offset of each class inside a weight slice (floats)
   int ncls;
+  const float* tc_scratch;           // A_s blocks of the long group-1 segments (k_acc_tc), or null
+  const int* tc_n_long;              // how many entries at the head of the group-1 list they cover
+  int tc_cap;
   unsigned long long* trace;         // DDK_CONV_TRACE: per CTA (start, end, tasks, weight reloads, reload ns, work ns, claim ns); else null
 };
 
@@ -200,6 +204,7 @@ __global__ void __launch_bounds__(1024) k_build_group_lists(int NL, int NR, cons
     int run = 0;
     for (int bkt = GL_BUCKETS - 1; bkt >= 0; --bkt) { cursor[bkt] = run; run += hist[bkt]; }
     gcnt[li] = run;
+    if (!filt) gcnt[F3_NLIST + li] = cursor[TC_MIN_CHUNKS - 1];             // segments with >= TC_MIN_CHUNKS chunks (list head)
     if (!filt) atomicAdd(counters + 1, (unsigned long long)run);            // all non-empty segments
     atomicAdd(counters + 2 + li, (unsigned long long)nedge);                // edges per work list
     atomicAdd(counters + 2 + F3_NLIST + li, (unsigned long long)run);       // segments per work list
@@ -227,7 +232,7 @@ struct LaneBasis {                   // the part of the LaneTab row a warp keeps
 struct ChunkD {                       // one gather chunk (<= KC3 consecutive list entries of a segment) of an accumulate warp
   int pos, kc, seg, flags;           // first list position, edges, segment id (valid when CD_LAST), CD_* flags
 };
-enum { CD_VALID = 1, CD_LAST = 2, CD_DONE = 4, CD_NOT_FIRST_BATCH = 8 };
+enum { CD_VALID = 1, CD_LAST = 2, CD_DONE = 4, CD_NOT_FIRST_BATCH = 8, CD_TC = 16 };
 
 __device__ __forceinline__ void f3_cp16(void* dst, const void* src) { __pipeline_memcpy_async(dst, src, 16); }
 
@@ -366,6 +371,12 @@ __device__ __forceinline__ void f3_acc_task(const F3Args& p, F3Smem<LV>& S, cons
       seg = pre.x; n = pre.y; sbase = pre.z; c0 = 0; in_seg = true;
       const int sn = si + F3_ACC;
       pre = (sn < nseg) ? wl[sn] : make_int4(-1, 0, 0, 0);
+      if (idx0 + si < S.ntc) {                      // accumulated on the tensor cores (k_acc_tc): one pseudo chunk, no edges
+        d.pos = idx0 + si; d.seg = seg;
+        d.flags = CD_VALID | CD_LAST | CD_TC | (bi > 0 ? CD_NOT_FIRST_BATCH : 0);
+        in_seg = false; ++bi;
+        return d;
+      }
     }
     d.pos = sbase + c0;
     d.kc = min(KC, n - c0);
@@ -439,7 +450,16 @@ __device__ __forceinline__ void f3_acc_task(const F3Args& p, F3Smem<LV>& S, cons
     if (cd0.flags & CD_LAST) {
       // ---- hand the finished U x J block to the contraction warps
       if (nflush > 0) f3_mbar_wait(&S.bar_empty, (nflush - 1) & 1);   // the contraction warps are done with the previous batch
-      if (cd0.flags & CD_VALID) {
+      if (cd0.flags & CD_TC) {
+        constexpr int NF = Cfg::U * AST, VW = NF % 4 == 0 ? 4 : 2;
+        const float* src = p.tc_scratch + ((size_t)cd0.pos * Cfg::NSLV + r) * ((NF + 3) & ~3);   // padded block stride
+        float* slot = &S.As[pr][0];
+        if (VW == 4) {
+          for (int i = pl; i < NF / 4; i += 64) reinterpret_cast<float4*>(slot)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
+        } else {
+          for (int i = pl; i < NF / 2; i += 64) reinterpret_cast<float2*>(slot)[i] = __ldg(reinterpret_cast<const float2*>(src) + i);
+        }
+      } else if (cd0.flags & CD_VALID) {
         float* slot = &S.As[pr][0];
 #pragma unroll
         for (int k = 0; k < NSLOT; ++k)
@@ -747,6 +767,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1) k_conv_fused(const __grid_const
           const int size = max(F3_ACC, min(p.nb_segs, (rem / 8) / F3_ACC * F3_ACC));
           const int start = atomicAdd(p.counters + combo, size);
           if (start < gn) {
+            S.ntc = (g == 1 && p.tc_scratch != nullptr) ? min(*p.tc_n_long, p.tc_cap) : 0;
             S.task[0] = g; S.task[1] = combo % NSLV; S.task[2] = start;
             S.task[3] = min(size, gn - start);
             S.task[4] = (combo != S.task[6]);
@@ -862,6 +883,20 @@ static void basis_desc_host(int lv, int u, int& type, int& i0, int& m) {
   }
   u -= 3 * F1e;
   if (u < 6) { type = 1; i0 = X1E + 3 * u; } else { type = 0; i0 = X0O + (u - 6); m = 0; }
+}
+
+// rows in PROCESSING order of k_acc_tc: plain products first, then dot products, then cross products; u = row of the A block
+// (kernel order), -1 = padding (evaluates x[0] * sh[0]; the result is never read)
+void build_tc_rows(int lv, TcRow* rows) {
+  const int U = lv == 0 ? 96 : (lv == 1 ? 138 : (lv == 2 ? 180 : 276));
+  int n = 0;
+  for (int pass = 0; pass < 3; ++pass)
+    for (int u = 0; u < U; ++u) {
+      int ty, i0, m;
+      basis_desc_host(lv, u, ty, i0, m);
+      if (ty == pass) rows[n++] = TcRow{(short)ty, (short)i0, (short)m, (short)u};
+    }
+  for (; n < TC_MAXROWS; ++n) rows[n] = TcRow{0, 0, 0, -1};
 }
 
 // lane -> (rows, sources) of a basis level, see F3Cfg.  Returns false unless every row is owned exactly once.
@@ -1038,6 +1073,11 @@ void launch_conv_fused(DdkCtx* c, int layer, const float* x_in, float* x_out, cu
     a.w8off[k] = w8;
     if (k < li.ncls) w8 += li.cls[k].F * J * li.cls[k].O;
   }
+  const bool tc = tc_enabled() && c->tc_cap > 0;
+  a.tc_scratch = tc ? ptr<float>(c->b_tc_scratch) : nullptr;
+  a.tc_n_long = ptr<int>(c->b_gcnt) + F3_NLIST + 1;
+  a.tc_cap = c->tc_cap;
+  if (tc) launch_acc_tc(c, layer, x_in, st);
   cudaMemsetAsync(c->b_counters.p, 0, F3_NCOMBO_MAX * sizeof(int), st);
   const int grid = c->sm_count;
 #if DDK_CONV_TRACE

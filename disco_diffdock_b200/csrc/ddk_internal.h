@@ -63,6 +63,11 @@ struct LaneTab {                    // what one lane of an accumulate warp evalu
   float gf[3];
 };
 
+// tensor-core accumulation of long lig<-rec segments (ddk_conv_tc.cu)
+struct TcRow { short type, i0, m, u; };   // basis row: 0 = x[i0] * sh[m]; 1 = x[i0..i0+2] . sh[1..3]; 2 = component m-1 of x[i0..i0+2] x sh[1..3]
+constexpr int TC_MAXROWS = 384;
+constexpr int TC_MIN_CHUNKS = 8;            // segments with at least this many 8-edge chunks take the tensor-core path
+
 struct ConSplit {                   // rows [f0, f1) of each irrep class handled by each contraction warp
   int f0[F3_CON][4], f1[F3_CON][4];
 };
@@ -120,6 +125,9 @@ struct DdkCtx {
   ddk::Buf b_need;                    // [hops][NR] uint8: receptor nodes whose features are read downstream (see ConvMode)
   int nhop = 0;                       // hops computed per step = num_conv_layers - 1
   ddk::Buf b_hs;                      // [72 / J][list_total][J]: hidden units of every listed edge of the current layer
+  ddk::TcRow* tc_rows = nullptr;      // [4 levels][TC_MAXROWS]
+  ddk::Buf b_tc_scratch;              // [segment][slice][U][J + 1]: A_s blocks of the tensor-core path
+  int tc_cap = 0;                     // segments the scratch holds (0: tensor-core path off)
 
   // optional profiling (off by default)
   bool prof = false;
@@ -168,6 +176,11 @@ constexpr int F3_NLIST = 4 + F3_MAXHOP;
 void launch_conv_fused(DdkCtx* c, int layer, const float* x_in, float* x_out, cudaStream_t st, int mode);
 void launch_edge_hidden(DdkCtx* c, int layer, cudaStream_t st, int mode);
 cudaError_t heads_configure();
+bool tc_enabled();                                   // DDK_TC=0 switches the tensor-core path off
+cudaError_t conv_tc_configure();
+size_t tc_scratch_floats_per_segment();
+void build_tc_rows(int lv, TcRow* rows);
+void launch_acc_tc(DdkCtx* c, int layer, const float* x_in, cudaStream_t st);
 void host_kabsch(const float* A, const float* Bp, int N, float* R9, float* t3);   // host build of the device routine (tests)
 void host_axis_angle(const float* aa, float* R9);   // opt-in dynamic shared memory sizes (once per process / device)
 

@@ -32,7 +32,7 @@
 
 namespace ddk {
 
-constexpr int F3_NCOMBO_MAX = 4 * NSL_MAX;
+constexpr int F3_NCOMBO_MAX = 5 * NSL_MAX;
 
 enum { F3_BAR_CON = 1, F3_BAR_CON2 = 2, F3_BAR_PAIR0 = 3 };   // named barriers; + one per warp pair
 
@@ -121,7 +121,7 @@ struct F3Smem {
   alignas(8) unsigned long long bar_w;                       // completion of the weight-slice bulk copy
   int meta[F3_ACC];                                          // segment id of each slot of the batch in flight (-1: none)
   int task[8];                                               // g, r, idx0, nseg, reload, combo cursor, resident combo, reloads so far
-  int ntc;                                                   // entries at the head of the task's work list whose A blocks come from k_acc_tc
+  int ntc;                                                   // the task's segments were accumulated by k_acc_tc: load their A blocks
 };
 
 struct F3Args {
@@ -132,7 +132,7 @@ struct F3Args {
   int goff[4];
   int gci[4];                        // index of each group's count in gcnt (group 2 may use the filtered list)
   const int* gcnt;                   // [4]
-  int* counters;                     // [4 * NSLV] segment cursor of each combo
+  int* counters;                     // [5 * NSLV] segment cursor of each combo
   const int2* seg_list;
   const float* x;                    // [N][84] layer input
   const float* hs;                   // [NSLV][LT][J] hidden units of every listed edge (k_edge_hidden)
@@ -232,7 +232,7 @@ struct LaneBasis {                   // the part of the LaneTab row a warp keeps
 struct ChunkD {                       // one gather chunk (<= KC3 consecutive list entries of a segment) of an accumulate warp
   int pos, kc, seg, flags;           // first list position, edges, segment id (valid when CD_LAST), CD_* flags
 };
-enum { CD_VALID = 1, CD_LAST = 2, CD_DONE = 4, CD_NOT_FIRST_BATCH = 8, CD_TC = 16 };
+enum { CD_VALID = 1, CD_LAST = 2, CD_DONE = 4, CD_NOT_FIRST_BATCH = 8 };
 
 __device__ __forceinline__ void f3_cp16(void* dst, const void* src) { __pipeline_memcpy_async(dst, src, 16); }
 
@@ -371,12 +371,6 @@ __device__ __forceinline__ void f3_acc_task(const F3Args& p, F3Smem<LV>& S, cons
       seg = pre.x; n = pre.y; sbase = pre.z; c0 = 0; in_seg = true;
       const int sn = si + F3_ACC;
       pre = (sn < nseg) ? wl[sn] : make_int4(-1, 0, 0, 0);
-      if (idx0 + si < S.ntc) {                      // accumulated on the tensor cores (k_acc_tc): one pseudo chunk, no edges
-        d.pos = idx0 + si; d.seg = seg;
-        d.flags = CD_VALID | CD_LAST | CD_TC | (bi > 0 ? CD_NOT_FIRST_BATCH : 0);
-        in_seg = false; ++bi;
-        return d;
-      }
     }
     d.pos = sbase + c0;
     d.kc = min(KC, n - c0);
@@ -450,16 +444,7 @@ __device__ __forceinline__ void f3_acc_task(const F3Args& p, F3Smem<LV>& S, cons
     if (cd0.flags & CD_LAST) {
       // ---- hand the finished U x J block to the contraction warps
       if (nflush > 0) f3_mbar_wait(&S.bar_empty, (nflush - 1) & 1);   // the contraction warps are done with the previous batch
-      if (cd0.flags & CD_TC) {
-        constexpr int NF = Cfg::U * AST, VW = NF % 4 == 0 ? 4 : 2;
-        const float* src = p.tc_scratch + ((size_t)cd0.pos * Cfg::NSLV + r) * ((NF + 3) & ~3);   // padded block stride
-        float* slot = &S.As[pr][0];
-        if (VW == 4) {
-          for (int i = pl; i < NF / 4; i += 64) reinterpret_cast<float4*>(slot)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
-        } else {
-          for (int i = pl; i < NF / 2; i += 64) reinterpret_cast<float2*>(slot)[i] = __ldg(reinterpret_cast<const float2*>(src) + i);
-        }
-      } else if (cd0.flags & CD_VALID) {
+      if (cd0.flags & CD_VALID) {
         float* slot = &S.As[pr][0];
 #pragma unroll
         for (int k = 0; k < NSLOT; ++k)
@@ -489,6 +474,35 @@ __device__ __forceinline__ void f3_acc_task(const F3Args& p, F3Smem<LV>& S, cons
     cd0 = cd1; cd1 = cd2; ent1 = ent2;
   }
   __pipeline_wait_prior(0);
+}
+
+// A task made only of segments that k_acc_tc accumulated on the tensor cores (the claim logic never mixes the two kinds): the
+// pair copies the segment's (U x (J | bsum)) block of this slice from the scratch into its slot and hands it to the
+// contraction warps with the same mbarrier protocol as f3_acc_task.  Kept apart so that the FFMA2 loop carries no extra state.
+template <int LV>
+__device__ __noinline__ void f3_tc_task(const F3Args& p, F3Smem<LV>& S, const int r, const int idx0, const int nseg, const int pr,
+                                        const int pl, int& nflush) {
+  using Cfg = F3Cfg<LV>;
+  constexpr int NF = Cfg::U * Cfg::AST, NFP = (NF + 3) & ~3, VW = NF % 4 == 0 ? 4 : 2;
+  const int nb = (nseg + F3_ACC - 1) / F3_ACC;
+  const int4* wl = p.glist + p.goff[1] + idx0;
+  for (int bi = 0; bi < nb; ++bi) {
+    const int si = F3_ACC * bi + pr;
+    if (nflush > 0) f3_mbar_wait(&S.bar_empty, (nflush - 1) & 1);
+    if (si < nseg) {
+      const float* src = p.tc_scratch + ((size_t)(idx0 + si) * Cfg::NSLV + r) * NFP;
+      float* slot = &S.As[pr][0];
+      if (VW == 4) {
+        for (int i = pl; i < NF / 4; i += 64) reinterpret_cast<float4*>(slot)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
+      } else {
+        for (int i = pl; i < NF / 2; i += 64) reinterpret_cast<float2*>(slot)[i] = __ldg(reinterpret_cast<const float2*>(src) + i);
+      }
+    }
+    if (pl == 0) S.meta[pr] = si < nseg ? wl[si].x : -1;
+    __syncwarp();
+    if ((pl & 31) == 0) f3_mbar_arrive(&S.bar_full);
+    ++nflush;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------- contraction warps
@@ -719,7 +733,7 @@ __device__ __forceinline__ void f3_con_task(const F3Args& p, F3Smem<LV>& S, cons
 template <int LV>
 __global__ void __launch_bounds__(F3_THREADS, 1) k_conv_fused(const __grid_constant__ F3Args p) {
   using Cfg = F3Cfg<LV>;
-  constexpr int J = Cfg::J, NSLV = Cfg::NSLV, NCOMBO = 4 * Cfg::NSLV;
+  constexpr int J = Cfg::J, NSLV = Cfg::NSLV, NCOMBO = 5 * Cfg::NSLV;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   F3Smem<LV>& S = *reinterpret_cast<F3Smem<LV>*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -756,10 +770,14 @@ __global__ void __launch_bounds__(F3_THREADS, 1) k_conv_fused(const __grid_const
   for (;;) {
     F3_TRACE(tr_a = f3_now();)
     if (tid == 0) {
+      // combos: (work range, slice).  Ranges 0..3 = the four edge groups; range 4 = the head of the group-1 list that k_acc_tc
+      // accumulated on the tensor cores (range 1 then starts behind it), so a task holds one kind of segment only
       int combo = S.task[5], found = 0;
       for (int tries = 0; tries < NCOMBO && !found; ++tries) {
-        const int g = combo / NSLV;
-        const int gn = ((p.gmask >> g) & 1) ? p.gcnt[p.gci[g]] : 0;
+        const int g5 = combo / NSLV, g = g5 == 4 ? 1 : g5;
+        const int gall = ((p.gmask >> g) & 1) ? p.gcnt[p.gci[g]] : 0;
+        const int ntc = (g == 1 && p.tc_scratch != nullptr) ? min(min(*p.tc_n_long, p.tc_cap), gall) : 0;
+        const int lo = g5 == 1 ? ntc : 0, gn = (g5 == 4 ? ntc : gall) - lo;
         // guided self-scheduling on the combo's segment cursor: blocks shrink as the combo runs out, so the CTAs of a
         // launch finish within a few segments of each other
         const int rem = gn - *reinterpret_cast<volatile int*>(p.counters + combo);
@@ -767,12 +785,13 @@ __global__ void __launch_bounds__(F3_THREADS, 1) k_conv_fused(const __grid_const
           const int size = max(F3_ACC, min(p.nb_segs, (rem / 8) / F3_ACC * F3_ACC));
           const int start = atomicAdd(p.counters + combo, size);
           if (start < gn) {
-            S.ntc = (g == 1 && p.tc_scratch != nullptr) ? min(*p.tc_n_long, p.tc_cap) : 0;
-            S.task[0] = g; S.task[1] = combo % NSLV; S.task[2] = start;
+            const int wcombo = g * NSLV + combo % NSLV;                  // which weight slice the task needs
+            S.ntc = g5 == 4;
+            S.task[0] = g; S.task[1] = combo % NSLV; S.task[2] = lo + start;
             S.task[3] = min(size, gn - start);
-            S.task[4] = (combo != S.task[6]);
-            if (combo != S.task[6]) S.task[7] += 1;
-            S.task[5] = combo; S.task[6] = combo;
+            S.task[4] = (wcombo != S.task[6]);
+            if (wcombo != S.task[6]) S.task[7] += 1;
+            S.task[5] = combo; S.task[6] = wcombo;
             found = 1;
             break;
           }
@@ -800,7 +819,9 @@ __global__ void __launch_bounds__(F3_THREADS, 1) k_conv_fused(const __grid_const
       f3_mbar_wait(&S.bar_w, (S.task[7] - 1) & 1);
       F3_TRACE(const unsigned long long t = f3_now(); tr_reload += t - tr_a; tr_a = t; ++tr_nrel;)
     }
-    if (is_acc) {
+    if (is_acc && S.ntc) {
+      f3_tc_task<LV>(p, S, r, idx0, nseg, pr, half * 32 + lane, nbat);
+    } else if (is_acc) {
       if (half == 0) {
         if (r == 0) f3_acc_task<LV, true, 0>(p, S, LB, g, r, idx0, nseg, pr, lane, nbat);
         else f3_acc_task<LV, false, 0>(p, S, LB, g, r, idx0, nseg, pr, lane, nbat);

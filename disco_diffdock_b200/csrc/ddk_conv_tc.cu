@@ -30,7 +30,8 @@ namespace ddk {
 constexpr int TC_N = 80;          // MMA N: 72 hidden units, the ones column, padding to a multiple of 16
 constexpr int TC_ONES = HID;      // B row that is 1 for valid edges
 constexpr int TC_NST = 3;         // operand stages
-constexpr int TC_COLS = 256;      // TMEM columns allocated (3 tiles x 80)
+constexpr int TC_COLS = 512;      // TMEM columns allocated: accumulators (3 tiles x 80) at 0, A operand stages from TC_ACOL
+constexpr int TC_ACOL = 256;      // A operand (hi 8 + lo 8 columns per tile and stage): written with tcgen05.st, read by the MMA (.ts form)
 constexpr int TC_BAR_ROWS = 1;    // named barrier of the row warps
 constexpr int TC_XR = 6;          // staging ring (feature rows, harmonics, hidden units of a chunk) filled by the gather warps
 constexpr int TC_GW = 2;          // gather warps: all global -> shared traffic (cp.async) lives here, because the row threads
@@ -50,8 +51,6 @@ struct TcCfg {
 
 template <int LV>
 struct TcSmem {
-  alignas(128) uint32_t Ahi[TC_NST][TcCfg<LV>::A_WORDS];
-  alignas(128) uint32_t Alo[TC_NST][TcCfg<LV>::A_WORDS];
   alignas(128) uint32_t Bhi[TC_NST][TcCfg<LV>::B_WORDS];
   alignas(128) uint32_t Blo[TC_NST][TcCfg<LV>::B_WORDS];
   alignas(16) float X[TC_XR][KC3][TcCfg<LV>::DINP];
@@ -118,6 +117,13 @@ __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// A operand from tensor memory (lane = row, one 32-bit column per k), B from shared memory
+__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void tc_commit(unsigned long long* b) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem(b)) : "memory");
 }
@@ -144,8 +150,8 @@ __global__ void __launch_bounds__(TcCfg<LV>::THREADS, 1) k_acc_tc(const __grid_c
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   {
-    uint32_t* z = &S.Ahi[0][0];
-    constexpr int nz = 2 * TC_NST * (Cfg::A_WORDS + Cfg::B_WORDS);
+    uint32_t* z = &S.Bhi[0][0];
+    constexpr int nz = 2 * TC_NST * Cfg::B_WORDS;
     static_assert(offsetof(TcSmem<LV>, X) == nz * sizeof(uint32_t), "operand tiles are contiguous");
     for (int i = tid; i < nz; i += Cfg::THREADS) z[i] = 0u;
   }
@@ -211,12 +217,13 @@ __global__ void __launch_bounds__(TcCfg<LV>::THREADS, 1) k_acc_tc(const __grid_c
           uint32_t hi[KC3], lo[KC3];
 #pragma unroll
           for (int e = 0; e < KC3; ++e) tc_split(b[e], hi[e], lo[e]);
-          uint32_t* ah = &S.Ahi[stage][tile * 1024 + rit * 4];
-          uint32_t* al = &S.Alo[stage][tile * 1024 + rit * 4];
-          *reinterpret_cast<uint4*>(ah) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<uint4*>(ah + 512) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-          *reinterpret_cast<uint4*>(al) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-          *reinterpret_cast<uint4*>(al + 512) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+          // A operand straight into tensor memory: this thread's TMEM lane is its row of the tile (no shared-memory round trip:
+          // with both operands in shared memory the MMAs' own operand reads saturated the shared-memory bandwidth)
+          const uint32_t ta = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + TC_ACOL + (stage * TILES + tile) * 16;
+          asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                       ::"r"(ta), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]), "r"(hi[4]), "r"(hi[5]), "r"(hi[6]), "r"(hi[7]) : "memory");
+          asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                       ::"r"(ta + 8), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]), "r"(lo[4]), "r"(lo[5]), "r"(lo[6]), "r"(lo[7]) : "memory");
         }
         // ---- B operand: work item w = (unit j = w % 72, half hk = w / 72 of the 8 edges): row j, 4 edges per 16-byte unit;
         //      items 144 / 145 = the two halves of the ones row (NB items per thread: 2 only at level 0)
@@ -245,7 +252,9 @@ __global__ void __launch_bounds__(TcCfg<LV>::THREADS, 1) k_acc_tc(const __grid_c
         __syncwarp();
         if (lane == 0) tc_mbar_arrive(&S.sempty[buf]);                               // this warp is done with the staging buffer
         TC_T(td)
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // this thread's operand stores -> async proxy
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");       // this thread's A rows are in tensor memory
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // this thread's B operand stores -> async proxy
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         TC_T(te)
         TC_ADD(2, tc_, td) TC_ADD(3, td, te)
         __syncwarp();
@@ -354,12 +363,11 @@ __global__ void __launch_bounds__(TcCfg<LV>::THREADS, 1) k_acc_tc(const __grid_c
         const uint64_t bl = tc_desc(tc_smem(&S.Blo[stage][0]), TC_N * 16, 128);
 #pragma unroll
         for (int t = 0; t < TILES; ++t) {
-          const uint64_t ah = tc_desc(tc_smem(&S.Ahi[stage][t * 1024]), 128 * 16, 128);
-          const uint64_t al = tc_desc(tc_smem(&S.Alo[stage][t * 1024]), 128 * 16, 128);
+          const uint32_t ah = tmem + TC_ACOL + (stage * TILES + t) * 16, al = ah + 8;
           const uint32_t d = tmem + t * TC_N;
-          tc_mma(d, ah, bh, idesc, c > 0);
-          tc_mma(d, ah, bl, idesc, 1);
-          tc_mma(d, al, bh, idesc, 1);
+          tc_mma_ts(d, ah, bh, idesc, c > 0);
+          tc_mma_ts(d, ah, bl, idesc, 1);
+          tc_mma_ts(d, al, bh, idesc, 1);
         }
         tc_commit(&S.empty[stage]);                    // the stage may be refilled once these MMAs have read it
         if (c == nch - 1) tc_commit(&S.accfull);       // the segment's accumulator is complete

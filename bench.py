@@ -294,7 +294,8 @@ def main():
     # the second radial-MLP layer (W = 1872); algorithmic bytes per launch = node features in and out, the edge list, the
     # harmonics and the 72 hidden units of every listed edge.
     hbm_peak, peak_src, peaks_raw = peaks()
-    acc_ms, acc_n = prof['conv_accum_lv3']
+    # the two 84-wide layers: k_conv_fused<3> plus k_acc_tc<3>, which accumulates their long lig<-rec segments on the tensor cores
+    acc_ms, acc_n = prof['conv_accum_lv3'][0] + prof['conv_tc_lv3'][0], prof['conv_accum_lv3'][1]
     total_prof_ms = sum(v[0] for v in prof.values())
     n_nodes = info.NL + info.NR
     passes = REV_STEPS * args.steps                                      # reverse steps in the timed region
@@ -310,7 +311,8 @@ def main():
     clocks = sampler.summary()
     sm_mhz = clocks.get('sm_mhz') or peaks_raw.get('sm_max_mhz', 1965.0)
     fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
-    conv_ms = sum(prof[k][0] for k in ('conv_accum_lv0', 'conv_accum_lv1', 'conv_accum_lv2', 'conv_accum_lv3'))
+    conv_ms = sum(prof[k][0] for k in ('conv_accum_lv0', 'conv_accum_lv1', 'conv_accum_lv2', 'conv_accum_lv3', 'conv_tc_lv0',
+                                       'conv_tc_lv1', 'conv_tc_lv2', 'conv_tc_lv3'))
     # DRAM bytes per launch of this kernel from the committed ncu pass over this very command (tools/gpu_round.sh,
     # tools/launch_summary.py); null when the capture is absent
     traffic, traffic_src = None, None
@@ -318,7 +320,7 @@ def main():
     if os.path.exists(tj) and n_complex == N_COMPLEX:
         td = json.load(open(tj))
         traffic, traffic_src = td['dram_bytes_per_launch'], 'profiles/conv_fused3_traffic.json (' + td['source'] + ')'
-    roofline = {'kernel': 'k_conv_fused<3>', 'bound': 'hbm', 'achieved': bytes_launch / t_launch / 1e9, 'peak': hbm_peak,
+    roofline = {'kernel': 'k_conv_fused<3> (+ k_acc_tc<3>: its long cross segments, 3xTF32 tcgen05)', 'bound': 'hbm', 'achieved': bytes_launch / t_launch / 1e9, 'peak': hbm_peak,
                 'unit': 'GB/s', 'frac': bytes_launch / t_launch / 1e9 / hbm_peak, 'traffic': traffic,
                 'traffic_unit': 'bytes per launch', 'traffic_source': traffic_src, 'algorithmic_bytes_per_launch': bytes_launch,
                 'peak_source': peak_src,
@@ -328,8 +330,8 @@ def main():
                 'fp32_fma': {'achieved_tflops': flop_launch / t_launch / 1e12, 'peak_tflops_at_measured_clock': fp32_peak,
                              'frac': flop_launch / t_launch / 1e12 / fp32_peak,
                              'note': 'the kernel is bound by the FP32 FMA pipe and shared-memory issue, not by HBM (re-associated '
-                                     'tensor product, SURVEY 8d); the HBM fraction is low by design; ncu DRAM traffic of this kernel: '
-                                     'profiles/ (captured at 80 poses per launch, so not comparable per launch)'},
+                                     'tensor product, SURVEY 8d); the HBM fraction is low by design.  FLOP of the layer / time of both '
+                                     'kernels; the long lig<-rec segments run as 3xTF32 tcgen05.mma in k_acc_tc'},
                 'kernel_ms': {k: round(v[0], 3) for k, v in prof.items()}}
     ref_equiv_tflops = edges * FLOP_PER_EDGE_REF / (ms / 1000) / 1e12
 

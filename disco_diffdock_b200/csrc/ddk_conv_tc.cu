@@ -432,7 +432,7 @@ void launch_acc_tc(DdkCtx* c, int layer, const float* x_in, cudaStream_t st) {
   cudaMemsetAsync(dbg, 0, 148 * 10 * sizeof(long long), st);
   a.dbg = dbg;
 #endif
-  LaunchScope ls(c, PC_ACC0 + li.lv, st);
+  LaunchScope ls(c, PC_TC0 + li.lv, st);
   switch (li.lv) {
     case 0: k_acc_tc<0><<<grid, TcCfg<0>::THREADS, sizeof(TcSmem<0>), st>>>(a); break;
     case 1: k_acc_tc<1><<<grid, TcCfg<1>::THREADS, sizeof(TcSmem<1>), st>>>(a); break;

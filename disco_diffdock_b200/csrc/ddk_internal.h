@@ -73,7 +73,7 @@ struct ConSplit {                   // rows [f0, f1) of each irrep class handled
 };
 
 // kernel classes for the optional per-launch CUDA-event timing (ddk_profile_*)
-enum ProfClass { PC_SETUP = 0, PC_GRAPH, PC_PROJ, PC_ACC0, PC_ACC1, PC_ACC2, PC_ACC3, PC_CONTRACT, PC_HEADS, PC_UPDATE, PC_HIDDEN, PC_COUNT };
+enum ProfClass { PC_SETUP = 0, PC_GRAPH, PC_PROJ, PC_ACC0, PC_ACC1, PC_ACC2, PC_ACC3, PC_CONTRACT, PC_HEADS, PC_UPDATE, PC_HIDDEN, PC_TC0, PC_TC1, PC_TC2, PC_TC3, PC_COUNT };
 
 struct ProfRec {
   int cls;

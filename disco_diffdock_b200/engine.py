@@ -439,7 +439,7 @@ class Engine:
         return int(self.lib.ddk_last_edge_count(self.ctx))
 
     PROFILE_CLASSES = ['setup', 'graph', 'node_proj', 'conv_accum_lv0', 'conv_accum_lv1', 'conv_accum_lv2', 'conv_accum_lv3',
-                       'conv_contract', 'heads', 'update', 'edge_hidden']
+                       'conv_contract', 'heads', 'update', 'edge_hidden', 'conv_tc_lv0', 'conv_tc_lv1', 'conv_tc_lv2', 'conv_tc_lv3']
 
     def profile_enable(self, on=True):
         self._check(self.lib.ddk_profile_enable(self.ctx, int(on)), 'ddk_profile_enable')

@@ -195,10 +195,11 @@ int ddk_debug_read(DdkCtx* ctx, const char* name, void* dst_h, size_t max_bytes,
 
 /* Optional per-launch timing with CUDA events on the launching stream (used by bench.py for the roofline line).
  * Kernel classes: 0 setup, 1 graph (lists + edge embeddings), 2 node projections, 3..6 conv accumulate (basis level
- * 0..3), 7 conv contract / finalize, 8 score heads, 9 update, 10 first radial-MLP layer per listed edge (k_edge_hidden).
+ * 0..3), 7 conv contract / finalize, 8 score heads, 9 update, 10 first radial-MLP layer per listed edge (k_edge_hidden),
+ * 11..14 tensor-core accumulation of the long lig<-rec segments (k_acc_tc, basis level 0..3).
  * ddk_profile_read synchronises the device, adds the elapsed milliseconds / launch counts since the last read into
- * ms[11] / launches[11] and clears the records. */
-#define DDK_PROFILE_CLASSES 11
+ * ms[15] / launches[15] and clears the records. */
+#define DDK_PROFILE_CLASSES 15
 int ddk_profile_enable(DdkCtx* ctx, int32_t on);
 int ddk_profile_read(DdkCtx* ctx, double* ms, int64_t* launches);
 

@@ -8,7 +8,7 @@ tail -c 3200 gpurun_out/bench.json; tail -3 gpurun_out/bench.err
 if [ "$1" != "quick" ]; then
   timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2>> gpurun_out/bench.err
   cat gpurun_out/bench_ref.json
-  timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 1500 --csv \
+  timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 1800 --csv \
       --log-file gpurun_out/launches_bench.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/launches_bench.log 2>&1
   python tools/launch_summary.py gpurun_out/launches_bench.csv --traffic-json gpurun_out/conv_fused3_traffic.json | tee gpurun_out/launches_bench_summary.txt
 fi

@@ -34,11 +34,13 @@ print(f'launches {lo}..{hi} ({len(sel)}), device time {tot / 1e6:.1f} ms (cold-c
 for k, (n, t, b) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print(f'{k:34s} n={n:4d}  {t / 1e6:8.2f} ms  {100 * t / tot:5.1f} %   dram {b / n / 1e6:9.2f} MB/launch  {b / max(t, 1) :7.1f} GB/s')
 if args.traffic_json:
-    k3 = [l for l in sel if 'k_conv_fused<3>' in l['name'] or 'k_conv_fused<(int)3>' in l['name']]
-    b = sum(l.get('dram__bytes_read.sum', 0.0) + l.get('dram__bytes_write.sum', 0.0) for l in k3)
-    t = sum(l['gpu__time_duration.sum'] for l in k3)
-    json.dump({'kernel': 'k_conv_fused<3>', 'launches': len(k3), 'dram_bytes_per_launch': b / max(len(k3), 1),
+    is3 = lambda l, k: (k + '<3>') in l['name'] or (k + '<(int)3>') in l['name']
+    k3 = [l for l in sel if is3(l, 'k_conv_fused')]
+    both = [l for l in sel if is3(l, 'k_conv_fused') or is3(l, 'k_acc_tc')]       # the pair that makes one 84-wide conv layer
+    b = sum(l.get('dram__bytes_read.sum', 0.0) + l.get('dram__bytes_write.sum', 0.0) for l in both)
+    t = sum(l['gpu__time_duration.sum'] for l in both)
+    json.dump({'kernel': 'k_conv_fused<3> + k_acc_tc<3>', 'launches': len(k3), 'dram_bytes_per_launch': b / max(len(k3), 1),
                'ms_per_launch_under_ncu': t / max(len(k3), 1) / 1e6, 'share_of_step_under_ncu': t / tot,
                'source': 'ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none '
-                         'python bench.py --steps 1 --warmup 1 --no-cpu-baseline (launches of the timed 400-pose job)'},
+                         'python bench.py --steps 1 --warmup 1 --no-cpu-baseline (launches of one 400-pose job, job index %d of the capture)' % args.job},
               open(args.traffic_json, 'w'), indent=1)

@@ -55,7 +55,9 @@ struct TcSmem {
   alignas(128) uint32_t Blo[TC_NST][TcCfg<LV>::B_WORDS];
   alignas(16) float X[TC_XR][KC3][TcCfg<LV>::DINP];
   alignas(16) float SH[TC_XR][KC3][4];
-  alignas(16) float HS[TC_XR][HID / TcCfg<LV>::J][KC3][TcCfg<LV>::J];   // [slice][edge][J] as k_edge_hidden stores them
+  alignas(16) float HS[TC_XR][HID / TcCfg<LV>::J][KC3 * TcCfg<LV>::J + 8];   // [slice][edge * J + jj] as k_edge_hidden stores them;
+                                                                        // 8 floats of padding per slice: the B-operand reads of a
+                                                                        // warp span 4 slices at the same (edge, jj)
   alignas(128) float OUT[2][TcCfg<LV>::NFP];                           // read-out staging: one slice block, double-buffered
   alignas(8) unsigned long long full[TC_NST], empty[TC_NST], accfull;
   alignas(8) unsigned long long sfull[TC_XR], sempty[TC_XR];           // staging ring: gather warps <-> row warps
@@ -236,7 +238,7 @@ __global__ void __launch_bounds__(TcCfg<LV>::THREADS, 1) k_acc_tc(const __grid_c
             uint32_t h[4], l[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              const float hld = S.HS[buf][hj / J][4 * hk + q][hj % J];   // padded edges hold a copy of the last edge: masked here
+              const float hld = S.HS[buf][hj / J][(4 * hk + q) * J + hj % J];   // padded edges hold a copy of the last edge: masked here
               const float hvq = 4 * hk + q < kc ? hld : 0.f;
               tc_split(hvq, h[q], l[q]);
             }
@@ -337,7 +339,7 @@ __global__ void __launch_bounds__(TcCfg<LV>::THREADS, 1) k_acc_tc(const __grid_c
           for (int q0 = lane; q0 < NSL * KC3 * PJ; q0 += 32) {
             const int r = q0 / (KC3 * PJ), e = (q0 / PJ) % KC3, q = q0 % PJ;
             const int es = min(e, kc - 1);
-            __pipeline_memcpy_async(&S.HS[buf][r][e][4 * q], p.hs + ((size_t)r * p.LT + pos0 + es) * J + 4 * q, 16);
+            __pipeline_memcpy_async(&S.HS[buf][r][e * J + 4 * q], p.hs + ((size_t)r * p.LT + pos0 + es) * J + 4 * q, 16);
           }
         }
         // the barrier receives this thread's arrival when all of its copies above have landed

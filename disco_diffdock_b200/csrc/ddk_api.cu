@@ -605,4 +605,34 @@ int ddk_host_lane_tables_check(void) {
   return 0;
 }
 
+// Host evaluation of the row table k_acc_tc works from (ddk_conv_tc.cu): basis_out[u] for one destination feature row x[84]
+// and one harmonics record sh[4], u in kernel order.  Returns the number of rows of the level, or -1 if a row is missing /
+// duplicated or the table is not sorted by row type (the kernel relies on that for branch-free warps).
+int ddk_host_tc_rows_eval(int32_t lv, const float* x84, const float* sh4, float* basis_out) {
+  if (lv < 0 || lv > 3 || !x84 || !sh4 || !basis_out) return -1;
+  const int U = lv == 0 ? 96 : (lv == 1 ? 138 : (lv == 2 ? 180 : 276));
+  std::vector<TcRow> rows(TC_MAXROWS);
+  build_tc_rows(lv, rows.data());
+  std::vector<int> seen(U, 0);
+  int last_type = 0;
+  for (int p = 0; p < TC_MAXROWS; ++p) {
+    const TcRow& r = rows[p];
+    if (r.u < 0) { if (p < U) return -1; continue; }
+    if (p >= U || r.u >= U || seen[r.u]++ || r.type < last_type) return -1;
+    last_type = r.type;
+    const float* s = sh4;
+    float v;
+    if (r.type == 0) v = x84[r.i0] * s[r.m];
+    else {
+      const float v0 = x84[r.i0], v1 = x84[r.i0 + 1], v2 = x84[r.i0 + 2];
+      if (r.type == 1) v = v0 * s[1] + v1 * s[2] + v2 * s[3];
+      else if (r.m == 1) v = v1 * s[3] - v2 * s[2];
+      else if (r.m == 2) v = v2 * s[1] - v0 * s[3];
+      else v = v0 * s[2] - v1 * s[1];
+    }
+    basis_out[r.u] = v;
+  }
+  return U;
+}
+
 }  // extern "C"

@@ -213,6 +213,11 @@ int ddk_host_axis_angle_to_matrix(const float* axis_angle3_h, float* R9_h);
  * all four levels are covered, otherwise 1 + the first failing level. */
 int ddk_host_lane_tables_check(void);
 
+/* Host evaluation of the basis-row table of the tensor-core accumulation kernel (k_acc_tc; models/tensor_layers.py:65-116): the
+ * raw basis values (no constant factors) of basis level lv for one destination feature row x[84] and one harmonics record sh[4],
+ * written in kernel row order.  Returns the number of rows (96 / 138 / 180 / 276), or -1 if the table is inconsistent. */
+int ddk_host_tc_rows_eval(int32_t lv, const float* x84_h, const float* sh4_h, float* basis_out_h);
+
 #ifdef __cplusplus
 }
 #endif

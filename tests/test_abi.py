@@ -101,3 +101,22 @@ def test_lane_tables_cover_every_basis_row(lib):
     """k_conv_fused: every FasterTensorProduct basis row of every level is owned by exactly one (slot, lane)."""
     lib.ddk_host_lane_tables_check.restype = ctypes.c_int
     assert lib.ddk_host_lane_tables_check() == 0
+
+
+def test_tensor_core_row_table_matches_basis(lib):
+    """k_acc_tc: the (type, source column, harmonic) row table, evaluated on the host, reproduces the FasterTensorProduct basis
+    in kernel order at every level; every row appears once and the table is sorted by row type."""
+    from tests.test_weights_packing import raw_basis
+    lib.ddk_host_tc_rows_eval.restype = ctypes.c_int
+    lib.ddk_host_tc_rows_eval.argtypes = [ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    g = torch.Generator().manual_seed(0)
+    x, sh = torch.randn(5, 84, generator=g), torch.randn(5, 4, generator=g)
+    for lv, U in enumerate((96, 138, 180, 276)):
+        want = raw_basis(x, sh, lv).numpy()
+        assert want.shape[1] == U
+        for i in range(5):
+            xi = np.ascontiguousarray(x[i].numpy(), np.float32)
+            si = np.ascontiguousarray(sh[i].numpy(), np.float32)
+            out = np.zeros(U, np.float32)
+            assert lib.ddk_host_tc_rows_eval(lv, xi.ctypes.data, si.ctypes.data, out.ctypes.data) == U
+            assert np.abs(out - want[i]).max() < 1e-5

@@ -180,7 +180,7 @@ __global__ void k_need_expand(int ER, const int* __restrict__ rr_src, const int*
 __global__ void __launch_bounds__(1024) k_build_group_lists(int NL, int NR, const int* __restrict__ seg_cnt,
                                                             const int* __restrict__ seg_base, int4* __restrict__ glist,
                                                             int* __restrict__ gcnt, unsigned long long* __restrict__ counters,
-                                                            const unsigned char* __restrict__ need) {
+                                                            const unsigned char* __restrict__ need, const int tc_min_chunks) {
   __shared__ int hist[GL_BUCKETS], cursor[GL_BUCKETS];
   __shared__ int nedge;
   const int li = blockIdx.x;                       // work list
@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(1024) k_build_group_lists(int NL, int NR, cons
     int run = 0;
     for (int bkt = GL_BUCKETS - 1; bkt >= 0; --bkt) { cursor[bkt] = run; run += hist[bkt]; }
     gcnt[li] = run;
-    if (!filt) gcnt[F3_NLIST + li] = cursor[TC_MIN_CHUNKS - 1];             // segments with >= TC_MIN_CHUNKS chunks (list head)
+    if (!filt) gcnt[F3_NLIST + li] = cursor[tc_min_chunks - 1];             // segments with >= tc_min_chunks chunks (list head)
     if (!filt) atomicAdd(counters + 1, (unsigned long long)run);            // all non-empty segments
     atomicAdd(counters + 2 + li, (unsigned long long)nedge);                // edges per work list
     atomicAdd(counters + 2 + F3_NLIST + li, (unsigned long long)run);       // segments per work list
@@ -1054,10 +1054,13 @@ void launch_build_group_lists(DdkCtx* c, cudaStream_t st, bool with_needed) {
     k_need_expand<<<(c->ER + 255) / 256, 256, 0, st>>>(c->ER, ptr<int>(c->b_rr_src), ptr<int>(c->b_rr_dst),
                                                       need + (size_t)(h - 1) * c->NR, need + (size_t)h * c->NR);
   }
+  // DDK_TC_MIN_CHUNKS: shortest segment (in 8-edge chunks) that takes the tensor-core path (default TC_MIN_CHUNKS)
+  static const int tc_min_chunks =
+      std::min(GL_BUCKETS - 1, std::max(1, getenv("DDK_TC_MIN_CHUNKS") ? atoi(getenv("DDK_TC_MIN_CHUNKS")) : TC_MIN_CHUNKS));
   LaunchScope ls(c, PC_GRAPH, st);
   k_build_group_lists<<<4 + nhop, 1024, 0, st>>>(c->NL, c->NR, ptr<int>(c->b_seg_cnt), ptr<int>(c->b_seg_base),
                                                  ptr<int4>(c->b_glist), ptr<int>(c->b_gcnt),
-                                                 ptr<unsigned long long>(c->b_edge_total), need);
+                                                 ptr<unsigned long long>(c->b_edge_total), need, tc_min_chunks);
 }
 
 void launch_conv_fused(DdkCtx* c, int layer, const float* x_in, float* x_out, cudaStream_t st, int mode) {

@@ -11,8 +11,8 @@ tail -c 3000 gpurun_out/bench.json
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2>> gpurun_out/bench.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches.csv \
     python tools/profile_step.py --complexes 2 --rev-steps 2 > gpurun_out/launches.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_conv_fused|k_edge_hidden' -s 6 -c 4 \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_conv_fused|k_acc_tc|k_edge_hidden' -s 6 -c 4 \
     -o gpurun_out/prof_fused_dense -f python tools/profile_step.py --complexes 2 --rev-steps 1 > gpurun_out/prof_dense.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_conv_fused|k_edge_hidden' -s 6 -c 4 \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_conv_fused|k_acc_tc|k_edge_hidden' -s 6 -c 4 \
     -o gpurun_out/prof_fused_sparse -f python tools/profile_step.py --complexes 2 --rev-steps 1 --start-step 14 > gpurun_out/prof_sparse.log 2>&1
 ls -la gpurun_out

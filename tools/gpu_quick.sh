@@ -9,7 +9,7 @@ tail -c 2500 gpurun_out/bench.json; tail -5 gpurun_out/bench.err
 for a in "$@"; do
   case $a in
     micro) ./tools/microbench/ffma2_bench > gpurun_out/ffma2_bench.txt 2>&1; cat gpurun_out/ffma2_bench.txt ;;
-    ncu) timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_conv_fused|k_edge_hidden' -s 6 -c 4 \
+    ncu) timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_conv_fused|k_acc_tc|k_edge_hidden' -s 6 -c 4 \
            -o gpurun_out/prof_fused_sparse -f python tools/profile_step.py --complexes 2 --rev-steps 1 --start-step 14 > gpurun_out/prof_sparse.log 2>&1
          tail -2 gpurun_out/prof_sparse.log ;;
     launches) timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches.csv \

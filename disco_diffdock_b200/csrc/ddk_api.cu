@@ -635,4 +635,11 @@ int ddk_host_tc_rows_eval(int32_t lv, const float* x84, const float* sh4, float*
   return U;
 }
 
+// Host build of the TF32 split k_acc_tc applies to both MMA operands: a = hi + lo exactly, hi on the TF32 grid.
+int ddk_host_tc_split(const float* a_h, int32_t n, uint32_t* hi_h, uint32_t* lo_h) {
+  if (!a_h || !hi_h || !lo_h || n < 0) return -1;
+  for (int i = 0; i < n; ++i) host_tc_split(a_h[i], hi_h + i, lo_h + i);
+  return 0;
+}
+
 }  // extern "C"

@@ -21,6 +21,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "ddk_conv.cuh"
@@ -90,9 +91,16 @@ __device__ __forceinline__ uint32_t tc_smem(const void* p) { return (uint32_t)__
 // 13 low bits), lo = a - hi (exact in fp32).  lo is passed as it is: the tensor core reads the upper 19 bits of a TF32 operand,
 // i.e. truncates lo to 10 mantissa bits -- an error of 2^-21 |a|, the size of the lo*lo term the 3-pass product drops anyway.
 // (cvt.rna.tf32.f32 is emulated with ~6 instructions on sm_100a; the split was the bottleneck of the row warps.)
-__device__ __forceinline__ void tc_split(float a, uint32_t& hi, uint32_t& lo) {
+__host__ __device__ __forceinline__ void tc_split(float a, uint32_t& hi, uint32_t& lo) {
+#ifdef __CUDA_ARCH__
   hi = (__float_as_uint(a) + 0x1000u) & 0xffffe000u;
   lo = __float_as_uint(a - __uint_as_float(hi));
+#else
+  uint32_t b; memcpy(&b, &a, 4);
+  hi = (b + 0x1000u) & 0xffffe000u;
+  float h, l; memcpy(&h, &hi, 4);
+  l = a - h; memcpy(&lo, &l, 4);
+#endif
 }
 __device__ __forceinline__ void tc_mbar_init(unsigned long long* b, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tc_smem(b)), "r"(count) : "memory");
@@ -184,7 +192,7 @@ __global__ void __launch_bounds__(TcCfg<LV>::THREADS, 1) k_acc_tc(const __grid_c
     int it = 0, nseg_done = 0;
     for (int i = blockIdx.x; i < n_long; i += gridDim.x) {
       const int4 ge = load_seg_entry(p.glist + i);
-      const int n = ge.y, base = ge.z;
+      const int n = ge.y;
       const int nch = (n + KC3 - 1) / KC3;
       for (int c = 0; c < nch; ++c, ++it) {
         const int kc = min(KC3, n - c * KC3);
@@ -389,6 +397,8 @@ __global__ void __launch_bounds__(TcCfg<LV>::THREADS, 1) k_acc_tc(const __grid_c
 }
 
 // ---------------------------------------------------------------------------------------------- host side
+void host_tc_split(float a, uint32_t* hi, uint32_t* lo) { tc_split(a, *hi, *lo); }
+
 bool tc_enabled() {
   static const bool on = getenv("DDK_TC") == nullptr || atoi(getenv("DDK_TC")) != 0;
   return on;

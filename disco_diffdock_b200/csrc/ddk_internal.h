@@ -180,6 +180,7 @@ bool tc_enabled();                                   // DDK_TC=0 switches the te
 cudaError_t conv_tc_configure();
 size_t tc_scratch_floats_per_segment();
 void build_tc_rows(int lv, TcRow* rows);
+void host_tc_split(float a, uint32_t* hi, uint32_t* lo);   // host build of the TF32 hi / lo split of k_acc_tc (tests)
 void launch_acc_tc(DdkCtx* c, int layer, const float* x_in, cudaStream_t st);
 void host_kabsch(const float* A, const float* Bp, int N, float* R9, float* t3);   // host build of the device routine (tests)
 void host_axis_angle(const float* aa, float* R9);   // opt-in dynamic shared memory sizes (once per process / device)

@@ -52,7 +52,7 @@ class DdkStepCoef(C.Structure):
 
 EXPORTS = ['ddk_abi_version', 'ddk_create', 'ddk_destroy', 'ddk_last_error', 'ddk_set_batch', 'ddk_score', 'ddk_embed',
            'ddk_get_node_features', 'ddk_update', 'ddk_sample', 'ddk_sample_host', 'ddk_kernel_launches',
-           'ddk_last_edge_count', 'ddk_debug_read', 'ddk_host_kabsch', 'ddk_host_axis_angle_to_matrix', 'ddk_host_lane_tables_check', 'ddk_host_tc_rows_eval',
+           'ddk_last_edge_count', 'ddk_debug_read', 'ddk_host_kabsch', 'ddk_host_axis_angle_to_matrix', 'ddk_host_lane_tables_check', 'ddk_host_tc_rows_eval', 'ddk_host_tc_split',
            'ddk_profile_enable', 'ddk_profile_read', 'ddk_edge_total', 'ddk_segment_total', 'ddk_group_totals']
 
 

@@ -218,6 +218,10 @@ int ddk_host_lane_tables_check(void);
  * written in kernel row order.  Returns the number of rows (96 / 138 / 180 / 276), or -1 if the table is inconsistent. */
 int ddk_host_tc_rows_eval(int32_t lv, const float* x84_h, const float* sh4_h, float* basis_out_h);
 
+/* Host build of the TF32 split of k_acc_tc's operands (3xTF32 product hi*hi + hi*lo + lo*hi): for every a[i], hi[i] = a rounded to
+ * the TF32 grid (13 low mantissa bits zero) and lo[i] = a - hi[i] (exact in fp32), both as raw fp32 bit patterns. */
+int ddk_host_tc_split(const float* a_h, int32_t n, uint32_t* hi_h, uint32_t* lo_h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -120,3 +120,20 @@ def test_tensor_core_row_table_matches_basis(lib):
             out = np.zeros(U, np.float32)
             assert lib.ddk_host_tc_rows_eval(lv, xi.ctypes.data, si.ctypes.data, out.ctypes.data) == U
             assert np.abs(out - want[i]).max() < 1e-5
+
+
+def test_tf32_split_is_exact(lib):
+    """k_acc_tc's operand split: hi on the TF32 grid, hi + lo == a exactly, |lo| <= half a TF32 ulp of a, so that the three-pass
+    product hi*hi + hi*lo + lo*hi drops only terms of order 2^-21 (tools/microbench/umma_tf32x3.cu measures 4-6e-7)."""
+    lib.ddk_host_tc_split.restype = ctypes.c_int
+    lib.ddk_host_tc_split.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]
+    rng = np.random.default_rng(0)
+    a = np.concatenate([rng.standard_normal(4096) * 10.0 ** rng.integers(-6, 6, 4096), [0.0, -0.0, 1.0, -1.0, 1.0 + 2.0 ** -11,
+                        1.0 + 2.0 ** -12, 3.4e38 * 0.5, 1e-30, -7.25]]).astype(np.float32)
+    hi, lo = np.zeros(a.size, np.uint32), np.zeros(a.size, np.uint32)
+    assert lib.ddk_host_tc_split(a.ctypes.data, a.size, hi.ctypes.data, lo.ctypes.data) == 0
+    assert not (hi & 0x1fff).any()
+    h, l = hi.view(np.float32), lo.view(np.float32)
+    assert np.array_equal(h + l, a)                                        # exact in fp32
+    assert (np.abs(l.astype(np.float64)) <= np.abs(a.astype(np.float64)) * 2.0 ** -11 * (1 + 2.0 ** -10) + 1e-45).all()
+    assert np.array_equal(np.signbit(h[np.abs(a) > 0]), np.signbit(a[np.abs(a) > 0]))

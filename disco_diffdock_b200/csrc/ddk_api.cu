@@ -335,7 +335,11 @@ int ddk_set_batch(DdkCtx* c, const DdkBatch* b, void* stream) {
   if (tc_enabled()) {   // A_s scratch of the tensor-core path: one block per ligand atom, capped at 4 GB
     const size_t per = tc_scratch_floats_per_segment() * sizeof(float);
     c->tc_cap = (int)std::min<size_t>((size_t)NL, ((size_t)4 << 30) / per);
-    EN(c->b_tc_scratch, (size_t)c->tc_cap * per);
+    if (ensure(c, c->b_tc_scratch, (size_t)c->tc_cap * per) != DDK_OK) {   // optional: without the scratch every segment
+      c->tc_cap = 0;                                                       // stays on the FFMA2 path
+      c->err.clear();
+      cudaGetLastError();
+    }
   }
   EN(c->b_tr, (size_t)B * 3 * 4); EN(c->b_rot, (size_t)B * 3 * 4); EN(c->b_tor, (size_t)std::max(c->RB, 1) * 4);
 #undef EN

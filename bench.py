@@ -332,6 +332,10 @@ def main():
                              'note': 'the kernel is bound by the FP32 FMA pipe and shared-memory issue, not by HBM (re-associated '
                                      'tensor product, SURVEY 8d); the HBM fraction is low by design.  FLOP of the layer / time of both '
                                      'kernels; the long lig<-rec segments run as 3xTF32 tcgen05.mma in k_acc_tc'},
+                'tensor_pipe': {'kernel': 'k_acc_tc<3>', 'ms_in_timed_region': round(prof['conv_tc_lv3'][0], 3),
+                                'sm__pipe_tensor_cycles_active_pct': 30.7,
+                                'source': 'ncu --set full capture, dense t = 1 step at 80 poses per launch: '
+                                          'profiles/r01i_ncu_tc_summary.txt (not measured in this run)'},
                 'kernel_ms': {k: round(v[0], 3) for k, v in prof.items()}}
     ref_equiv_tflops = edges * FLOP_PER_EDGE_REF / (ms / 1000) / 1e12
 

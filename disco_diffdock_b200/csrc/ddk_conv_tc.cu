@@ -4,16 +4,21 @@
 // is a GEMM with M = U basis rows (96 .. 276), N = 72 hidden units (+ a column of ones that yields Bsum), K = the edges of
 // the segment.  For the cross segments of a ligand atom (K = every residue inside the cut-off, up to N_r) the FFMA2 path
 // of k_conv_fused spends ~310 cycles per edge; here the segment is one accumulator in tensor memory:
-//   * 4 warps per 128-row tile evaluate the basis values of 8 edges at a time from the staged destination features /
-//     harmonics, split them into TF32 hi + lo and store them straight into the canonical K-major (no swizzle) UMMA
-//     operand layout (8-row x 16-byte core matrices); the 72 hidden units of the chunk (k_edge_hidden) are split the same
-//     way into the B operand, row 72 = 1 for valid edges;
-//   * one thread issues tcgen05.mma kind::tf32 three times per tile and chunk (hi*hi + hi*lo + lo*hi: fp32-level accuracy,
-//     tools/microbench/umma_tf32x3.cu), M = 128, N = 80, K = 8, accumulating in TMEM; tcgen05.commit releases the
-//     shared-memory stage (3-stage ring, mbarriers) and, after the last chunk, publishes the accumulator;
-//   * the row warps read the accumulator back (tcgen05.ld) and write A_s to a scratch in exactly the per-slice slot layout
-//     [slice][u][J | bsum] the contraction warps of k_conv_fused consume; k_conv_fused then loads these blocks instead of
-//     accumulating (CD_TC), so scheduling, contraction, partial outputs and k_conv_finalize are shared with the FFMA2 path.
+//   * two gather warps move everything a chunk of 8 edges needs (list entries, destination feature rows, harmonics, the 72
+//     hidden units from k_edge_hidden) from global memory into a 6-deep staging ring with cp.async; completion is signalled
+//     with cp.async.mbarrier.arrive.noinc, so they run ahead across segment boundaries and nobody else waits on global memory;
+//   * 4 warps per 128-row tile evaluate the basis values of the 8 edges (rows sorted by type: branch-free), split them into
+//     TF32 hi + lo and write them straight into TENSOR MEMORY with tcgen05.st (the thread's TMEM lane is its row): the A
+//     operand never touches shared memory; the hidden units are split the same way into the B operand in shared memory
+//     (canonical K-major no-swizzle UMMA layout: 8-row x 16-byte core matrices), row 72 = 1 for valid edges (-> Bsum);
+//   * one thread issues tcgen05.mma kind::tf32 (.ts form: A from TMEM, B from shared memory) three times per tile and chunk
+//     (hi*hi + hi*lo + lo*hi: fp32-level accuracy, tools/microbench/umma_tf32x3.cu), M = 128, N = 80, K = 8, accumulating in
+//     TMEM; tcgen05.commit releases the operand stage (3-stage ring, mbarriers) and, after the last chunk, publishes the
+//     accumulator;
+//   * the row warps read the accumulator back (tcgen05.ld), drop it slice by slice into a staging block in exactly the slot
+//     layout [u][J | bsum] the contraction warps of k_conv_fused consume, and one thread sends each block to the scratch with a
+//     bulk asynchronous store; k_conv_fused then loads these blocks instead of accumulating (f3_tc_task), so scheduling,
+//     contraction, partial outputs and k_conv_finalize are shared with the FFMA2 path.
 // Which segments: the group-1 work list is sorted by length; its first gcnt[F3_NLIST + 1] entries have >= TC_MIN_CHUNKS
 // chunks (k_build_group_lists).  Short segments stay on the FFMA2 path, where the per-segment cost dominates anyway.
 // The choice depends only on the segment's own length, so results do not depend on batch composition.

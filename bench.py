@@ -178,7 +178,7 @@ def main():
     if world > 1:
         for p_ in list(m.parameters()) + list(m.buffers()):
             dist.broadcast(p_.data, src=0)
-        m._engine = None
+        m.invalidate()
     eng = m.engine(dev)
     eng.profile_enable(True)
     t2s = partial(du.t_to_sigma, args=cfg)

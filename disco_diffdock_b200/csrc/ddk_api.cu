@@ -569,6 +569,8 @@ int ddk_debug_read(DdkCtx* c, const char* name, void* dst_h, size_t max_bytes, s
   return DDK_OK;
 }
 
+int ddk_debug_set_tc(int32_t on) { return tc_set_override(on < 0 ? -1 : (on != 0)); }
+
 int ddk_profile_enable(DdkCtx* c, int32_t on) {
   if (!c) return DDK_ERR_INVALID;
   c->prof = on != 0;

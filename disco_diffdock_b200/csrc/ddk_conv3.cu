@@ -1050,6 +1050,7 @@ void launch_build_group_lists(DdkCtx* c, cudaStream_t st, bool with_needed) {
   }
   for (int h = 1; h < nhop; ++h) {
     cudaMemsetAsync(need + (size_t)h * c->NR, 0, c->NR, st);
+    if (c->ER == 0) { cudaMemcpyAsync(need + (size_t)h * c->NR, need + (size_t)(h - 1) * c->NR, c->NR, cudaMemcpyDeviceToDevice, st); continue; }   // no receptor contacts: the set does not grow (and a zero-size grid is an invalid launch)
     LaunchScope ls(c, PC_GRAPH, st);
     k_need_expand<<<(c->ER + 255) / 256, 256, 0, st>>>(c->ER, ptr<int>(c->b_rr_src), ptr<int>(c->b_rr_dst),
                                                       need + (size_t)(h - 1) * c->NR, need + (size_t)h * c->NR);

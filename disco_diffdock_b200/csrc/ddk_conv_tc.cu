@@ -454,9 +454,12 @@ __global__ void __launch_bounds__(TcCfg<LV>::THREADS, 1) k_acc_tc(const __grid_c
 // ---------------------------------------------------------------------------------------------- host side
 void host_tc_split(float a, uint32_t* hi, uint32_t* lo) { tc_split(a, *hi, *lo); }
 
+static int g_tc_override = -1;      // ddk_debug_set_tc: -1 = follow the environment
+int tc_set_override(int on) { const int prev = g_tc_override; g_tc_override = on; return prev; }
+
 bool tc_enabled() {
-  static const bool on = getenv("DDK_TC") == nullptr || atoi(getenv("DDK_TC")) != 0;
-  return on;
+  static const bool env_on = getenv("DDK_TC") == nullptr || atoi(getenv("DDK_TC")) != 0;
+  return g_tc_override < 0 ? env_on : g_tc_override != 0;
 }
 
 size_t tc_scratch_floats_per_segment() {

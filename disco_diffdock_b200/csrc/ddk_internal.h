@@ -177,6 +177,7 @@ void launch_conv_fused(DdkCtx* c, int layer, const float* x_in, float* x_out, cu
 void launch_edge_hidden(DdkCtx* c, int layer, cudaStream_t st, int mode);
 cudaError_t heads_configure();
 bool tc_enabled();                                   // DDK_TC=0 switches the tensor-core path off
+int tc_set_override(int on);                         // run-time override of DDK_TC (-1: environment); returns the previous value
 cudaError_t conv_tc_configure();
 size_t tc_scratch_floats_per_segment();
 void build_tc_rows(int lv, TcRow* rows);

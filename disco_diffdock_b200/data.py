@@ -204,6 +204,41 @@ class HeteroData:
                 f'attrs={list(self._attrs.keys())})')
 
 
+def public_view(item):
+    """(node stores, edge stores, graph attributes) of a graph as plain dicts, read through the PUBLIC container API only
+    (``node_types``, ``edge_types``, ``item[key].items()``, ``to_dict()``), so that real ``torch_geometric`` ``HeteroData`` /
+    ``HeteroDataBatch`` objects -- which have none of this module's private fields -- collate exactly like our own."""
+    if isinstance(item, HeteroData):
+        return ({k: s._d for k, s in item._node_stores.items()}, {k: s._d for k, s in item._edge_stores.items()}, item._attrs)
+    nts = list(item.node_types)
+    ets = [tuple(et) for et in item.edge_types]
+    node = {nt: dict(item[nt].items()) for nt in nts}
+    edge = {et: dict(item[et].items()) for et in ets}
+    attrs: Dict[str, Any] = {}
+    if hasattr(item, 'to_dict'):
+        d = item.to_dict()
+        if isinstance(d.get('_global_store'), dict):                 # PyG >= 2.0 keeps graph-level attributes there
+            attrs.update(d['_global_store'])
+        for k, v in d.items():
+            if isinstance(k, str) and k != '_global_store' and k not in node:
+                attrs[k] = v
+    else:                                                            # last resort: the names the hot path reads
+        for k in ('name', 'original_center', 'complex_t', 'rmsd_matching', 'success'):
+            try:
+                attrs[k] = getattr(item, k)
+            except AttributeError:
+                pass
+    attrs.pop('num_graphs', None)
+    return node, edge, attrs
+
+
+def _store_num_nodes(d):
+    for cand in ('x', 'pos', 'batch'):
+        if cand in d and d[cand] is not None:
+            return int(d[cand].shape[0])
+    raise AttributeError('num_nodes')
+
+
 class Batch(HeteroData):
     """Disjoint union of graphs, PyG ``Batch.from_data_list`` semantics for the attributes on the path.
 
@@ -216,19 +251,22 @@ class Batch(HeteroData):
     """
 
     @classmethod
-    def from_data_list(cls, data_list: Sequence[HeteroData]) -> 'Batch':
+    def from_data_list(cls, data_list: Sequence[Any]) -> 'Batch':
         out = cls()
         n = len(data_list)
-        first = data_list[0]
+        views = [public_view(d) for d in data_list]
+        nodes0, edges0, attrs0 = views[0]
         offsets: Dict[str, List[int]] = {}
-        for nt in first._node_stores:
-            stores = [d._node_stores[nt] for d in data_list]
+        for nt in nodes0:
+            stores = [v[0][nt] for v in views]
             st = Store()
-            counts = [s.num_nodes for s in stores]
+            counts = [_store_num_nodes(s) for s in stores]
             off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
             offsets[nt] = off.tolist()
             for k in stores[0].keys():
-                vals = [s._d[k] for s in stores]
+                if k in ('batch', 'ptr'):                  # items that are batches themselves (loader items): regenerated below
+                    continue
+                vals = [s[k] for s in stores]
                 if torch.is_tensor(vals[0]):
                     if vals[0].dim() == 0:
                         st._d[k] = torch.stack(vals)
@@ -242,11 +280,11 @@ class Batch(HeteroData):
             st._d['batch'] = torch.repeat_interleave(torch.arange(n), torch.tensor(counts)).to(dev)
             st._d['ptr'] = torch.from_numpy(off).to(dev)
             out._node_stores[nt] = st
-        for et in first._edge_stores:
-            stores = [d._edge_stores[et] for d in data_list]
+        for et in edges0:
+            stores = [v[1][et] for v in views]
             st = Store()
             for k in stores[0].keys():
-                vals = [s._d[k] for s in stores]
+                vals = [s[k] for s in stores]
                 if k == 'edge_index':
                     so, do = offsets[et[0]], offsets[et[2]]
                     shifted = []
@@ -259,8 +297,8 @@ class Batch(HeteroData):
                 else:
                     st._d[k] = list(vals)
             out._edge_stores[et] = st
-        for k in first._attrs:
-            vals = [d._attrs[k] for d in data_list]
+        for k in attrs0:
+            vals = [v[2][k] for v in views]
             if torch.is_tensor(vals[0]):
                 out._attrs[k] = torch.cat([v.reshape(1, *v.shape[1:]) if v.dim() > 0 and v.shape[0] == 1 else v.unsqueeze(0)
                                            for v in vals], dim=0)

@@ -53,7 +53,7 @@ class DdkStepCoef(C.Structure):
 EXPORTS = ['ddk_abi_version', 'ddk_create', 'ddk_destroy', 'ddk_last_error', 'ddk_set_batch', 'ddk_score', 'ddk_embed',
            'ddk_get_node_features', 'ddk_update', 'ddk_sample', 'ddk_sample_host', 'ddk_kernel_launches',
            'ddk_last_edge_count', 'ddk_debug_read', 'ddk_host_kabsch', 'ddk_host_axis_angle_to_matrix', 'ddk_host_lane_tables_check', 'ddk_host_tc_rows_eval', 'ddk_host_tc_split',
-           'ddk_profile_enable', 'ddk_profile_read', 'ddk_edge_total', 'ddk_segment_total', 'ddk_group_totals']
+           'ddk_profile_enable', 'ddk_profile_read', 'ddk_debug_set_tc', 'ddk_edge_total', 'ddk_segment_total', 'ddk_group_totals']
 
 
 def load_library(path: Optional[str] = None):
@@ -90,6 +90,7 @@ def load_library(path: Optional[str] = None):
     lib.ddk_segment_total.argtypes = [C.c_void_p]
     lib.ddk_group_totals.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.ddk_debug_read.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    lib.ddk_debug_set_tc.argtypes = [C.c_int32]
     lib.ddk_profile_enable.argtypes = [C.c_void_p, C.c_int32]
     lib.ddk_profile_read.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.ddk_host_kabsch.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
@@ -97,6 +98,11 @@ def load_library(path: Optional[str] = None):
     if path is None:
         _lib = lib
     return lib
+
+
+def set_tensor_core_path(on: Optional[bool]) -> int:
+    """Run-time switch of the tcgen05 accumulation path (None: follow DDK_TC); effective from the next ``set_batch``."""
+    return int(load_library().ddk_debug_set_tc(-1 if on is None else int(bool(on))))
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -513,21 +519,32 @@ def _graph_inputs(model, data):
 
 
 def _batch_key(data):
+    """Identity of every step-invariant input of a forward call, plus the tensors themselves.
+
+    The key is (data_ptr, shape, _version) of each tensor.  That identifies CONTENT only while the tensor is alive -- the
+    caching allocator hands a freed block to the next batch of the same shapes -- so the engine keeps the returned tensors
+    referenced for as long as it keeps the key: a live tensor with the same address, shape and version counter is the same
+    data (in-place writes bump ``_version``)."""
     lig, rec = data['ligand'], data['receptor']
-    parts = [lig.x, rec.x, rec.pos, data['ligand', 'ligand'].edge_index, data['receptor', 'receptor'].edge_index]
+    ll, rr = data['ligand', 'ligand'], data['receptor', 'receptor']
+    parts = [lig.x, rec.x, rec.pos, ll.edge_index, ll.edge_attr, rr.edge_index, lig.edge_mask]
+    if 'batch' in lig:
+        parts += [lig.batch, rec.batch]
     if 'latent_h' in lig:
         parts += [lig.latent_h, rec.latent_h]
     if 'unconditional' in lig:
         parts += [lig.unconditional, rec.unconditional]
-    return tuple((p.data_ptr(), tuple(p.shape), p._version) for p in parts)
+    mr = lig.mask_rotate if 'mask_rotate' in lig else None
+    key = tuple((p.data_ptr(), tuple(p.shape), p._version, p.dtype) for p in parts) + (id(mr), int(data.num_graphs))
+    return key, (parts, mr)
 
 
 def _prepare(model, data):
     eng = model.engine(data['ligand'].pos.device if data['ligand'].pos.is_cuda else model.device)
-    key = _batch_key(data)
+    key, alive = _batch_key(data)
     if getattr(eng, '_batch_key', None) != key:
         eng.set_batch(data)
-        eng._batch_key = key
+        eng._batch_key, eng._batch_alive = key, alive
     return eng
 
 

@@ -92,6 +92,13 @@ def run_inference(complexes: Sequence, model, model_args, device, t_to_sigma, *,
     res = {k: [] for k in ('names', 'ligand_pos', 'rmsds', 'centroid_distances', 'min_self_distances',
                            'min_cross_distances', 'run_times', 'data_lists')}
     pool = ThreadPoolExecutor(1) if prefetch and len(chunks) > 1 else None
+    if pool is not None and generator is None and noise_fn is None and not (no_random or ode):
+        # The prefetch thread draws the start poses from the GLOBAL numpy / torch / scipy generators (randomize_position follows
+        # the reference's RNG calls).  The noise of the reverse steps must not interleave with those draws, or a seeded run would
+        # depend on thread timing: it gets its own generator, seeded from the global one before the worker starts.
+        zdev = torch.device('cpu') if host_buffers else torch.device(device)
+        generator = torch.Generator(device=zdev)
+        generator.manual_seed(int(torch.randint(0, 2 ** 62, (1,)).item()))
     nxt = pool.submit(prepare, chunks[0]) if pool else None
     for ci, idx in enumerate(chunks):
         lists = nxt.result() if pool else prepare(idx)

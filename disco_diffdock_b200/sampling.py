@@ -266,6 +266,11 @@ def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_s
             elif noise is not None:
                 z = {'tr': noise['tr'][:, pose0:pose0 + b], 'rot': noise['rot'][:, pose0:pose0 + b],
                      'tor': noise['tor'][:, tor0:tor0 + R] if R else None}
+                if no_final_step_noise:                                     # utils/sampling.py:146-148 holds for supplied noise too
+                    z = {k: (None if v is None else v.clone()) for k, v in z.items()}
+                    for v in z.values():
+                        if v is not None:
+                            v[inference_steps - 1] = 0
             else:
                 zdev = torch.device('cpu') if host_buffers else device
                 z = {'tr': torch.randn(inference_steps, b, 3, device=zdev, generator=generator),

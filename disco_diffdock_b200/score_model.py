@@ -100,7 +100,9 @@ class TensorProductScoreModel(nn.Module):
             self.tor_bond_conv = HeadConvParams(3 * ns, (top['1o'] + top['1e']) * ns, 2 * ns, 2 * ns, ns, dropout)
             self.tor_final_layer = nn.Sequential(nn.Linear(2 * ns, ns, bias=False), nn.Tanh(), nn.Dropout(dropout),
                                                  nn.Linear(ns, 1, bias=False))
-        self._engine = None
+        self._engines = {}            # one libddk context per device
+        self._engines_key = None
+        self._engine_uncond = None
         self.eval()
 
     # ------------------------------------------------------------------------------------------ engine
@@ -112,12 +114,32 @@ class TensorProductScoreModel(nn.Module):
                                no_torsion=self.no_torsion, latent_dim=self.latent_dim,
                                latent_droprate=self.latent_droprate)
 
+    def _weights_key(self):
+        """Changes whenever any parameter / buffer is replaced or written in place (load_state_dict of this module or of a
+        parent wrapper, ``.to()``, dist.broadcast, optimiser-style in-place updates)."""
+        return tuple((v.data_ptr(), v._version) for v in self.state_dict(keep_vars=True).values())
+
     def engine(self, device=None) -> 'engine.Engine':
-        """The CUDA context holding the packed weights (rebuilt when parameters were reloaded)."""
-        if self._engine is None:
-            dev = torch.device(device if device is not None else self.device)
-            self._engine = engine.Engine(self.hyper(), {k: v.detach() for k, v in self.state_dict().items()}, dev)
-        return self._engine
+        """The CUDA context of ``device`` holding the packed weights: one per GPU, rebuilt when the weights changed."""
+        dev = torch.device(device if device is not None else self.device)
+        if dev.type == 'cuda' and dev.index is None:
+            dev = torch.device('cuda', torch.cuda.current_device())
+        key = self._weights_key()
+        if key != self._engines_key:
+            self._engines.clear()
+            self._engine_uncond = None
+            self._engines_key = key
+        eng = self._engines.get(str(dev))
+        if eng is None:
+            eng = engine.Engine(self.hyper(), {k: v.detach() for k, v in self.state_dict().items()}, dev)
+            self._engines[str(dev)] = eng
+        return eng
+
+    def invalidate(self):
+        """Drop the packed-weight contexts (called after anything that changes the parameters)."""
+        self._engines.clear()
+        self._engines_key = None
+        self._engine_uncond = None
 
     def load_state_dict(self, state_dict, strict=True, **kw):
         # tolerate DataParallel / ModelWrapper prefixes (utils/model_utils.py:16-21, evaluate.py:167-174)
@@ -128,7 +150,7 @@ class TensorProductScoreModel(nn.Module):
                 k = k[len('score_model.'):]
             cleaned[k] = v
         out = super().load_state_dict(cleaned, strict=strict, **kw)
-        self._engine = None
+        self.invalidate()
         return out
 
     def to(self, *a, **kw):
@@ -136,10 +158,9 @@ class TensorProductScoreModel(nn.Module):
         for x in a:
             if isinstance(x, (str, torch.device)):
                 self.device = torch.device(x)
-                self._engine = None
         if 'device' in kw:
             self.device = torch.device(kw['device'])
-            self._engine = None
+        self.invalidate()
         return out
 
     def train(self, mode=True):

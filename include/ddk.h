@@ -191,6 +191,10 @@ int ddk_group_totals(DdkCtx* ctx, int64_t* edges, int64_t* segments);   /* cumul
                                                           list ([DDK_WORK_LISTS] each): edge groups 0 lig-lig, 1 lig<-rec, 2 rec-rec,
                                                           3 rec<-lig, and 4 + h = group 2 restricted to the residues within h
                                                           receptor-contact hops of a residue with a cross edge; all steps (sync) */
+/* Process-wide run-time switch of the tensor-core accumulation path (same meaning as the DDK_TC environment variable: 1 on, 0 off,
+ * -1 follow the environment again); takes effect at the next ddk_set_batch.  Returns the previous override.  Parity tests run
+ * every trajectory both ways. */
+int ddk_debug_set_tc(int32_t on);
 int ddk_debug_read(DdkCtx* ctx, const char* name, void* dst_h, size_t max_bytes, size_t* n_bytes);
 
 /* Optional per-launch timing with CUDA events on the launching stream (used by bench.py for the roofline line).

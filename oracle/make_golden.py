@@ -104,6 +104,99 @@ def main():
         print('wrote', name)
     if not only or 'sample_disco' in only:
         write_disco(out_dir, mods)
+    for name in helpers.PRE_CASES:
+        if not only or name in only:
+            write_pretrained(out_dir, mods, name)
+    if not only or 'host_fixtures' in only:
+        write_host_fixtures(out_dir, mods)
+
+
+def write_host_fixtures(out_dir, mods):
+    """randomize_position (utils/sampling.py:12-46) and encode_ar with multinomial decoding (models/model_classes.py:9-49) run by
+    the REFERENCE's functions on the seeded inputs of tests/test_host_parity.py."""
+    import contextlib, io
+    from tests import test_host_parity as T
+    with contextlib.redirect_stdout(io.StringIO()):
+        from models.pretrained_score_encoder import PretrainedScoreEncoder as RefEnc
+    out = {}
+    for key, nr in (('random', False), ('no_random', True)):
+        b = T._rp_inputs(); T._seed(); mods.sampling.randomize_position(b, False, nr, 19.0)
+        out[key] = torch.stack([x['ligand'].pos for x in b]).numpy()
+    np.savez_compressed(os.path.join(out_dir, 'randomize_position.npz'), **out)
+    out = {}
+    for temp in (1.0, 3.0):
+        lst, heads, B = T._ar_case()
+        ref = RefEnc(pretrained_score_model=T._StubScore(), ns=16, latent_dim=1, latent_vocab=1, input_latent_dim=2)
+        ref.load_state_dict(heads, strict=True)
+        ref.eval()
+        torch.manual_seed(123)
+        with torch.no_grad():
+            l, r = ref.encode_ar(ddata.Batch.from_data_list(lst), temp)
+        out[f'l_{temp}'] = l.numpy(); out[f'r_{temp}'] = r.numpy()
+    np.savez_compressed(os.path.join(out_dir, 'encode_ar_multinomial.npz'), **out)
+    print('wrote host fixtures (reference functions)')
+
+
+class _Recorder:
+    """Stands where ``model.score_model`` is called in the reference's sampling() (utils/sampling.py:116-117): records the pose
+    BEFORE every reverse step and the scores the reference's own forward returns for it."""
+
+    def __init__(self, ref_model):
+        self.ref_model, self.pos, self.scores = ref_model, [], []
+
+    def __call__(self, batch):
+        self.pos.append(batch['ligand'].pos.detach().clone())
+        out = self.ref_model(batch)
+        self.scores.append([o.detach().clone() for o in out[:3]])
+        return out
+
+
+def write_pretrained(out_dir, mods, name):
+    """Goldens in the PRETRAINED-weight regime: the reference's unmodified forward / sampling() with the shipped checkpoint
+    (evaluate.py:160-174 loads the same file) on a calibrated synthetic complex (tests/helpers.py PRE_CASES)."""
+    c = helpers.PRE_CASES[name]
+    sd, cfg = helpers.load_checkpoint(c['ckpt'])
+    ref_model, args = ref_loader.build_reference_model(cfg, sd)
+    tables = ref_loader.load_tables()
+    out = dict(weights_fp=fingerprint({k: v.float() for k, v in sd.items()}))
+    if 'ts' in c:
+        for i, t in enumerate(c['ts']):
+            batch = helpers.pre_forward_batch(c, t)
+            with torch.no_grad():
+                tr, rot, tor = ref_model(copy.deepcopy(batch))
+                lig_h, rec_h = ref_model.embed(copy.deepcopy(batch))[:2]
+            out.update({f'tr{i}': tr.numpy(), f'rot{i}': rot.numpy(), f'tor{i}': tor.numpy(), f'lig_h{i}': lig_h.numpy(),
+                        f'rec_h{i}': rec_h.numpy(), f'pos{i}': batch['ligand'].pos.numpy()})
+        out['rec_fp'] = float(batch['receptor'].x.double().abs().sum())
+    else:
+        g, lst, noise, sched, kw = helpers.pre_traj_inputs(c)
+        t2s = partial(mods.diffusion_utils.t_to_sigma, args=args)
+        ref_list = [as_loader_item(x) for x in copy.deepcopy(lst)]
+        rec = _Recorder(ref_model)
+        with ref_loader.InjectedNormal(noise, c['steps']), torch.no_grad():
+            out_list, _ = mods.sampling.sampling(ref_list, SimpleNamespace(score_model=rec), c['steps'], sched, sched, sched,
+                                                 torch.device('cpu'), t2s, args, batch_size=c['B'], no_final_step_noise=False, **kw)
+        final = torch.cat([x['ligand'].pos for x in out_list])
+        out.update(start=torch.cat([x['ligand'].pos for x in lst]).numpy(), final=final.numpy(),
+                   pos_steps=torch.stack(rec.pos + [final]).numpy(),
+                   tr=torch.stack([s[0] for s in rec.scores]).numpy(), rot=torch.stack([s[1] for s in rec.scores]).numpy(),
+                   tor=torch.stack([s[2] for s in rec.scores]).numpy(),
+                   rec_fp=float(lst[0]['receptor'].x.double().abs().sum()))
+        # how well conditioned is this trajectory?  the oracle against itself from start poses perturbed by 2e-6 A
+        def oracle_run(eps, seed):
+            l2 = copy.deepcopy(lst)
+            if eps:
+                gg = torch.Generator().manual_seed(seed)
+                for x in l2:
+                    x['ligand'].pos = x['ligand'].pos + eps * torch.randn(x['ligand'].pos.shape, generator=gg)
+            with torch.no_grad():
+                return restate.sample(sd, cfg, ddata.Batch.from_data_list(l2), tables, sched, noise, inference_steps=c['steps'], **kw).clone()
+        base = oracle_run(0, 0)
+        out['oracle_vs_reference_rmsd'] = float(helpers.rmsd_per_pose(base, final, c['B']).max())
+        out['oracle_spread_2e-6'] = np.array([float(helpers.rmsd_per_pose(base, oracle_run(2e-6, s), c['B']).max()) for s in range(3)])
+        print(name, 'oracle vs reference', out['oracle_vs_reference_rmsd'], 'spread', out['oracle_spread_2e-6'])
+    np.savez_compressed(os.path.join(out_dir, name + '.npz'), **out)
+    print('wrote', name)
 
 
 def write_disco(out_dir, mods):

@@ -556,7 +556,7 @@ def step_coefficients(cfg, t, dt, temp_sampling, temp_psi, temp_sigma_data, ode=
 
 def sample(p, cfg, batch, tables, schedule, noise, inference_steps=None, temp_sampling=(1.0, 1.0, 1.0),
            temp_psi=(0.0, 0.0, 0.0), temp_sigma_data=(0.5, 0.5, 0.5), ode=False, trajectory=None,
-           step_callback=None):
+           step_callback=None, edge_log=None):
     """The reverse-diffusion loop of ``sampling()`` (sampling.py:105-198) for one batch of B copies of one
     complex, with *pre-drawn* noise so that the CPU oracle and the CUDA path consume identical z:
     ``noise = {'tr': [steps,B,3], 'rot': [steps,B,3], 'tor': [steps,B*R]}`` (the reference draws tr, rot, tor
@@ -579,7 +579,10 @@ def sample(p, cfg, batch, tables, schedule, noise, inference_steps=None, temp_sa
         if cfg.latent_droprate > 0:
             lig.unconditional = torch.zeros(lig.num_nodes, 1)
             batch['receptor'].unconditional = torch.zeros(batch['receptor'].num_nodes, 1)
-        tr_s, rot_s, tor_s = forward(p, cfg, batch, tables)
+        trace = {} if edge_log is not None else None
+        tr_s, rot_s, tor_s = forward(p, cfg, batch, tables, trace)
+        if edge_log is not None:
+            edge_log.append(trace['n_edges'])                   # edges of the combined graph of this step (all poses)
         a, b = step_coefficients(cfg, (t, t, t), (dt, dt, dt), temp_sampling, temp_psi, temp_sigma_data, ode)
         tr_p = float(a[0]) * tr_s + float(b[0]) * noise['tr'][s]
         rot_p = float(a[1]) * rot_s + float(b[1]) * noise['rot'][s]

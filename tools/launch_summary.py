@@ -1,7 +1,7 @@
 """Summary of an ncu launch list (`--metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --csv`) of
 `bench.py --steps 1 --warmup 1`: per kernel, launches / total time / share of the step / DRAM bytes per launch, over the
 launches of ONE 400-pose job (the timed step = the second `k_step_consts`-to-`k_update` run of 20 reverse steps).
-Writes profiles/conv_fused3_traffic.json (read by bench.py for roofline.traffic) when --traffic-json is given."""
+Writes profiles/conv_lv3_traffic.json (read by bench.py for roofline.traffic) when --traffic-json is given."""
 import argparse, collections, csv, json, re, sys
 
 ap = argparse.ArgumentParser()
@@ -34,12 +34,12 @@ print(f'launches {lo}..{hi} ({len(sel)}), device time {tot / 1e6:.1f} ms (cold-c
 for k, (n, t, b) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print(f'{k:34s} n={n:4d}  {t / 1e6:8.2f} ms  {100 * t / tot:5.1f} %   dram {b / n / 1e6:9.2f} MB/launch  {b / max(t, 1) :7.1f} GB/s')
 if args.traffic_json:
-    is3 = lambda l, k: (k + '<3>') in l['name'] or (k + '<(int)3>') in l['name']
-    k3 = [l for l in sel if is3(l, 'k_conv_fused')]
-    both = [l for l in sel if is3(l, 'k_conv_fused') or is3(l, 'k_acc_tc')]       # the pair that makes one 84-wide conv layer
+    is3 = lambda l, k: (k + '<3') in l['name'] or (k + '<(int)3') in l['name']
+    k3 = [l for l in sel if is3(l, 'k_conv_fused')] or [l for l in sel if is3(l, 'k_conv_tc')]
+    both = [l for l in sel if is3(l, 'k_conv_fused') or is3(l, 'k_acc_tc') or is3(l, 'k_conv_tc')]   # the kernels of one 84-wide conv layer
     b = sum(l.get('dram__bytes_read.sum', 0.0) + l.get('dram__bytes_write.sum', 0.0) for l in both)
     t = sum(l['gpu__time_duration.sum'] for l in both)
-    json.dump({'kernel': 'k_conv_fused<3> + k_acc_tc<3>', 'launches': len(k3), 'dram_bytes_per_launch': b / max(len(k3), 1),
+    json.dump({'kernel': ' + '.join(sorted(set(short(l['name']) for l in both))), 'workload': 'dense', 'launches': len(k3), 'dram_bytes_per_launch': b / max(len(k3), 1),
                'ms_per_launch_under_ncu': t / max(len(k3), 1) / 1e6, 'share_of_step_under_ncu': t / tot,
                'source': 'ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none '
                          'python bench.py --steps 1 --warmup 1 --no-cpu-baseline (launches of one 400-pose job, job index %d of the capture)' % args.job},

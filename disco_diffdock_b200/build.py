@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libddk.so')
-SOURCES = ['ddk_api.cu', 'ddk_graph.cu', 'ddk_conv.cu', 'ddk_conv3.cu', 'ddk_conv_tc.cu', 'ddk_hidden.cu', 'ddk_heads.cu', 'ddk_update.cu']
+SOURCES = ['ddk_api.cu', 'ddk_graph.cu', 'ddk_conv.cu', 'ddk_conv3.cu', 'ddk_conv_tc.cu', 'ddk_conv_tcr.cu', 'ddk_hidden.cu', 'ddk_heads.cu', 'ddk_update.cu']
 NVCC_FLAGS = (['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '-Xcompiler', '-fPIC']
               + os.environ.get('DDK_NVCC_EXTRA', '').split())     # e.g. -DDDK_CONV_TRACE=1 for tools/conv_trace.sh
 

@@ -130,6 +130,41 @@ int ddk_create(const DdkConfig* cfg, const float* weights_h, size_t n_floats, co
   if ((e = heads_configure()) != cudaSuccess) return bail("cudaFuncSetAttribute(heads)", e);
   if ((e = conv3_configure()) != cudaSuccess) return bail("cudaFuncSetAttribute(conv3)", e);
   if ((e = conv_tc_configure()) != cudaSuccess) return bail("cudaFuncSetAttribute(conv_tc)", e);
+  if ((e = conv_tcr_configure()) != cudaSuccess) return bail("cudaFuncSetAttribute(conv_tcr)", e);
+  {
+    // k_conv_tcr: role tables per basis level, weight slices per (layer, group, role)
+    std::vector<TcrRole> roles((size_t)4 * TCR_MAXROLES);
+    for (int lv = 0; lv < 4; ++lv) {
+      const LayerInfo* li = nullptr;
+      for (const LayerInfo& l : c->layers) if (l.lv == lv) { li = &l; break; }
+      if (!li) continue;
+      c->tcr_nroles[lv] = build_tcr_roles(lv, *li, roles.data() + (size_t)lv * TCR_MAXROLES);
+      if (c->tcr_nroles[lv] <= 0) {
+        g_create_error = "internal: tensor-core role tables of a basis level are inconsistent";
+        cudaFree(c->w); delete c;
+        return DDK_ERR_STATE;
+      }
+    }
+    if ((e = cudaMalloc(&c->tcr_roles, roles.size() * sizeof(TcrRole))) != cudaSuccess) return bail("cudaMalloc(tcr_roles)", e);
+    if ((e = cudaMemcpy(c->tcr_roles, roles.data(), roles.size() * sizeof(TcrRole), cudaMemcpyHostToDevice)) != cudaSuccess)
+      return bail("cudaMemcpy(tcr_roles)", e);
+    std::vector<float> w2r;
+    c->w2r_off.assign((size_t)c->cfg.num_conv_layers * 4 * TCR_MAXROLES, 0);
+    for (int l = 0; l < c->cfg.num_conv_layers; ++l) {
+      const LayerInfo& li = c->layers[l];
+      for (int g = 0; g < 4; ++g)
+        for (int r = 0; r < c->tcr_nroles[li.lv]; ++r) {
+          const TcrRole& R = roles[(size_t)li.lv * TCR_MAXROLES + r];
+          c->w2r_off[((size_t)l * 4 + g) * TCR_MAXROLES + r] = (int64_t)w2r.size();
+          w2r.resize(w2r.size() + (size_t)R.wfloats);
+          build_tcr_weights(li, R, weights_h + c->off[conv_id(l, DDK_WL_W2P + g)], weights_h + c->off[conv_id(l, DDK_WL_B2P + g)],
+                            w2r.data() + w2r.size() - (size_t)R.wfloats);
+        }
+    }
+    if ((e = cudaMalloc(&c->w2r, w2r.size() * sizeof(float))) != cudaSuccess) return bail("cudaMalloc(w2r)", e);
+    if ((e = cudaMemcpy(c->w2r, w2r.data(), w2r.size() * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess)
+      return bail("cudaMemcpy(w2r)", e);
+  }
   {
     std::vector<TcRow> rows((size_t)4 * TC_MAXROWS);
     for (int lv = 0; lv < 4; ++lv) build_tc_rows(lv, rows.data() + (size_t)lv * TC_MAXROWS);
@@ -198,6 +233,8 @@ int ddk_destroy(DdkCtx* c) {
   if (c->w2s) cudaFree(c->w2s);
   if (c->ltab) cudaFree(c->ltab);
   if (c->tc_rows) cudaFree(c->tc_rows);
+  if (c->tcr_roles) cudaFree(c->tcr_roles);
+  if (c->w2r) cudaFree(c->w2r);
   delete c;
   return DDK_OK;
 }
@@ -327,12 +364,12 @@ int ddk_set_batch(DdkCtx* c, const DdkBatch* b, void* stream) {
   EN(c->b_tb, (size_t)B * TB_COUNT * NS * 4);
   EN(c->b_xa, (size_t)c->N * D * 4); EN(c->b_xb, (size_t)c->N * D * 4); EN(c->b_proj, (size_t)c->N * 4 * HID * 4);
   c->nhop = std::min(F3_MAXHOP, c->cfg.num_conv_layers - 1);
-  EN(c->b_glist, ((size_t)nsegs + (size_t)c->nhop * NR) * 16); EN(c->b_gcnt, (F3_NLIST + 4) * 4); EN(c->b_counters, 5 * NSL_MAX * 4);
+  EN(c->b_glist, ((size_t)nsegs + (size_t)c->nhop * NR) * 16); EN(c->b_gcnt, (2 * F3_NLIST + 4) * 4); EN(c->b_counters, 5 * NSL_MAX * 4);
   EN(c->b_need, (size_t)std::max(1, c->nhop) * NR);
   EN(c->b_part, (size_t)nsegs * NSL_MAX * D * 4);
   EN(c->b_hs, (size_t)std::max<int64_t>(total, 1) * HID * 4);
   c->tc_cap = 0;
-  if (tc_enabled()) {   // A_s scratch of the tensor-core path: one block per ligand atom, capped at 4 GB
+  if (conv_path() == 1) {   // A_s scratch of the round-1 tensor-core path (k_acc_tc): one block per ligand atom, capped at 4 GB
     const size_t per = tc_scratch_floats_per_segment() * sizeof(float);
     c->tc_cap = (int)std::min<size_t>((size_t)NL, ((size_t)4 << 30) / per);
     if (ensure(c, c->b_tc_scratch, (size_t)c->tc_cap * per) != DDK_OK) {   // optional: without the scratch every segment
@@ -569,7 +606,7 @@ int ddk_debug_read(DdkCtx* c, const char* name, void* dst_h, size_t max_bytes, s
   return DDK_OK;
 }
 
-int ddk_debug_set_tc(int32_t on) { return tc_set_override(on < 0 ? -1 : (on != 0)); }
+int ddk_debug_set_tc(int32_t on) { return tc_set_override(on < 0 ? -1 : (on > 2 ? 2 : on)); }
 
 int ddk_profile_enable(DdkCtx* c, int32_t on) {
   if (!c) return DDK_ERR_INVALID;
@@ -639,6 +676,14 @@ int ddk_host_tc_rows_eval(int32_t lv, const float* x84, const float* sh4, float*
     basis_out[r.u] = v;
   }
   return U;
+}
+
+int ddk_host_tcr_roles_check(void) { return host_tcr_roles_check(); }
+
+int ddk_host_tc_split_rn(const float* a_h, int32_t n, uint32_t* hi_h, uint32_t* lo_h) {
+  if (!a_h || !hi_h || !lo_h || n < 0) return -1;
+  for (int i = 0; i < n; ++i) host_tc_split_rn(a_h[i], hi_h + i, lo_h + i);
+  return 0;
 }
 
 // Host build of the TF32 split k_acc_tc applies to both MMA operands: a = hi + lo exactly, hi on the TF32 grid.

@@ -115,7 +115,8 @@ void launch_node_proj(DdkCtx* c, int layer, const float* x_in, float* x0_out, cu
 
 void launch_conv_layer(DdkCtx* c, int layer, const float* x_in, float* x_out, cudaStream_t st, int mode) {
   launch_edge_hidden(c, layer, st, mode);
-  launch_conv_fused(c, layer, x_in, x_out, st, mode);
+  if (conv_path() == 2) launch_conv_tcr(c, layer, x_in, x_out, st, mode);
+  else launch_conv_fused(c, layer, x_in, x_out, st, mode);
 }
 
 }  // namespace ddk

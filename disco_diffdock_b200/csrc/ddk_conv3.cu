@@ -204,6 +204,7 @@ __global__ void __launch_bounds__(1024) k_build_group_lists(int NL, int NR, cons
     int run = 0;
     for (int bkt = GL_BUCKETS - 1; bkt >= 0; --bkt) { cursor[bkt] = run; run += hist[bkt]; }
     gcnt[li] = run;
+    gcnt[F3_NLIST + 4 + li] = nedge;                                        // listed edges of this work list in this step
     if (!filt) gcnt[F3_NLIST + li] = cursor[tc_min_chunks - 1];             // segments with >= tc_min_chunks chunks (list head)
     if (!filt) atomicAdd(counters + 1, (unsigned long long)run);            // all non-empty segments
     atomicAdd(counters + 2 + li, (unsigned long long)nedge);                // edges per work list
@@ -1064,6 +1065,19 @@ void launch_build_group_lists(DdkCtx* c, cudaStream_t st, bool with_needed) {
                                                  ptr<unsigned long long>(c->b_edge_total), need, tc_min_chunks);
 }
 
+void launch_conv_finalize(DdkCtx* c, int layer, const float* x_in, float* x_out, cudaStream_t st, bool lig_only, int nsl) {
+  const LayerInfo& li = c->layers[layer];
+  FinArgs f;
+  f.N = lig_only ? c->NL : c->N; f.dout = li.dout; f.nsl = nsl;   // ligand nodes come first
+  f.seg_cnt = ptr<int>(c->b_seg_cnt);
+  f.part = ptr<float>(c->b_part);
+  f.bn_scale = W(c, conv_id(layer, DDK_WL_BN_SCALE));
+  f.bn_shift = W(c, conv_id(layer, DDK_WL_BN_SHIFT));
+  f.x_in = x_in; f.x_out = x_out;
+  LaunchScope ls(c, PC_CONTRACT, st);
+  k_conv_finalize<<<(f.N + 2) / 3, 256, 0, st>>>(f);
+}
+
 void launch_conv_fused(DdkCtx* c, int layer, const float* x_in, float* x_out, cudaStream_t st, int mode) {
   const bool lig_only = mode == CONV_LIG;
   const LayerInfo& li = c->layers[layer];
@@ -1098,7 +1112,7 @@ void launch_conv_fused(DdkCtx* c, int layer, const float* x_in, float* x_out, cu
     a.w8off[k] = w8;
     if (k < li.ncls) w8 += li.cls[k].F * J * li.cls[k].O;
   }
-  const bool tc = tc_enabled() && c->tc_cap > 0;
+  const bool tc = conv_path() == 1 && c->tc_cap > 0;
   a.tc_scratch = tc ? ptr<float>(c->b_tc_scratch) : nullptr;
   a.tc_n_long = ptr<int>(c->b_gcnt) + F3_NLIST + 1;
   a.tc_cap = c->tc_cap;
@@ -1139,17 +1153,7 @@ void launch_conv_fused(DdkCtx* c, int layer, const float* x_in, float* x_out, cu
             layer, li.lv, mode, c->B, span / 1e3, 100.0 * busy / grid / span, 100.0 * (double)(first_end - t0) / span, tasks / grid,
             nrel / grid, 100.0 * work / grid / span, 100.0 * rel / grid / span, 100.0 * claim / grid / span);
   }
-  FinArgs f;
-  f.N = lig_only ? c->NL : c->N; f.dout = li.dout; f.nsl = nsl;   // ligand nodes come first
-  f.seg_cnt = ptr<int>(c->b_seg_cnt);
-  f.part = ptr<float>(c->b_part);
-  f.bn_scale = W(c, conv_id(layer, DDK_WL_BN_SCALE));
-  f.bn_shift = W(c, conv_id(layer, DDK_WL_BN_SHIFT));
-  f.x_in = x_in; f.x_out = x_out;
-  {
-    LaunchScope ls(c, PC_CONTRACT, st);
-    k_conv_finalize<<<(f.N + 2) / 3, 256, 0, st>>>(f);
-  }
+  launch_conv_finalize(c, layer, x_in, x_out, st, lig_only, nsl);
 }
 
 }  // namespace ddk

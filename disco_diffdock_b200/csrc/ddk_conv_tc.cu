@@ -30,6 +30,7 @@
 #include <vector>
 
 #include "ddk_conv.cuh"
+#include "ddk_tc.cuh"
 
 namespace ddk {
 
@@ -97,58 +98,6 @@ struct TcArgs {
 #define TC_T(var)
 #define TC_ADD(slot, a, b)
 #endif
-
-__device__ __forceinline__ uint32_t tc_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-// TF32 split a = hi + lo in three instructions: hi = a rounded to 10 mantissa bits (add half an ulp of the TF32 grid, clear the
-// 13 low bits), lo = a - hi (exact in fp32).  lo is passed as it is: the tensor core reads the upper 19 bits of a TF32 operand,
-// i.e. truncates lo to 10 mantissa bits -- an error of 2^-21 |a|, the size of the lo*lo term the 3-pass product drops anyway.
-// (cvt.rna.tf32.f32 is emulated with ~6 instructions on sm_100a; the split was the bottleneck of the row warps.)
-__host__ __device__ __forceinline__ void tc_split(float a, uint32_t& hi, uint32_t& lo) {
-#ifdef __CUDA_ARCH__
-  hi = (__float_as_uint(a) + 0x1000u) & 0xffffe000u;
-  lo = __float_as_uint(a - __uint_as_float(hi));
-#else
-  uint32_t b; memcpy(&b, &a, 4);
-  hi = (b + 0x1000u) & 0xffffe000u;
-  float h, l; memcpy(&h, &hi, 4);
-  l = a - h; memcpy(&lo, &l, 4);
-#endif
-}
-__device__ __forceinline__ void tc_mbar_init(unsigned long long* b, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tc_smem(b)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void tc_mbar_arrive(unsigned long long* b) {
-  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(tc_smem(b)) : "memory");
-}
-__device__ __forceinline__ void tc_mbar_wait(unsigned long long* b, uint32_t parity) {
-  uint32_t ok = 0;
-  while (!ok) {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(tc_smem(b)), "r"(parity) : "memory");
-  }
-}
-// K-major, no-swizzle shared-memory descriptor: start address, K-direction (leading) and 8-row-group (stride) byte offsets in
-// 16-byte units, descriptor version 1 (cute/arch/mma_sm100_desc.hpp; validated in tools/microbench/umma_tf32x3.cu)
-__device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16) |
-         ((uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32) | ((uint64_t)1 << 46);
-}
-__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-// A operand from tensor memory (lane = row, one 32-bit column per k), B from shared memory
-__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tc_commit(unsigned long long* b) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem(b)) : "memory");
-}
 
 template <int LV>
 __global__ void __launch_bounds__(TcCfg<LV>::THREADS, 1) k_acc_tc(const __grid_constant__ TcArgs p) {
@@ -457,10 +406,15 @@ void host_tc_split(float a, uint32_t* hi, uint32_t* lo) { tc_split(a, *hi, *lo);
 static int g_tc_override = -1;      // ddk_debug_set_tc: -1 = follow the environment
 int tc_set_override(int on) { const int prev = g_tc_override; g_tc_override = on; return prev; }
 
-bool tc_enabled() {
-  static const bool env_on = getenv("DDK_TC") == nullptr || atoi(getenv("DDK_TC")) != 0;
-  return g_tc_override < 0 ? env_on : g_tc_override != 0;
+// DDK_TC: 0 = FFMA2 kernels only (k_conv_fused), 1 = k_conv_fused + k_acc_tc for the long lig<-rec segments (round-1 path),
+// 2 = k_conv_tcr: every accumulation on the tensor cores, contraction from tensor memory (default)
+int conv_path() {
+  static const int env = getenv("DDK_TC") == nullptr ? 2 : atoi(getenv("DDK_TC"));
+  const int v = g_tc_override < 0 ? env : g_tc_override;
+  return v < 0 ? 0 : (v > 2 ? 2 : v);
 }
+bool tc_enabled() { return conv_path() == 1; }
+void host_tc_split_rn(float a, uint32_t* hi, uint32_t* lo) { tc_split_rn(a, *hi, *lo); }
 
 size_t tc_scratch_floats_per_segment() {
   size_t m = 0;

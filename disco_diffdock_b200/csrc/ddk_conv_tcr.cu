@@ -1,0 +1,763 @@
+// k_conv_tcr: one tensor-product convolution layer with the outer-product accumulation of EVERY segment on the 5th-generation
+// tensor cores and the contraction against the second radial-MLP layer in the same CTA, straight from tensor memory.
+//
+// Algebra (ddk_conv.cu, /root/reference/models/tensor_layers.py:65-116, 147-168): for a (node s, edge group g) segment
+//     out_s = W2p (*) A_s + b2p (*) Bsum_s,   A_s[u][j] = sum_e basis_e[u] * h_e[j],   Bsum_s[u] = sum_e basis_e[u].
+// A_s (U x 73 fp32, 80 KB at level 3) is the accumulator of a GEMM with K = the edges of the segment; the contraction needs
+// the whole packed weight block of the edge group (539 KB at level 3), which fits neither shared memory nor a second trip
+// through HBM / L2 (89 KB per segment: k_acc_tc + k_conv_fused pay exactly that for the long segments).  Here the work of a
+// layer is cut into ROLES = (a set of irrep classes, a range of hidden units) such that
+//   * the basis rows of a role fit ONE M = 128 accumulator tile (<= 128 rows),
+//   * its slice of the packed weights (<= 150 KB) stays RESIDENT in shared memory while a CTA works on the role,
+//   * several segments' accumulators (N = 80 / 48 / 32 columns each) sit side by side in tensor memory.
+// Level 3: roles {1o}, {1e} (108 rows x all 72 hidden units + the ones column) and {0e, 0o} x three thirds of the hidden units
+// (60 rows x 24 + ones); the lower levels analogously (build_tcr_roles).  A CTA owns one (edge group, role) "combo" at a
+// time and claims blocks of segments from per-combo counters (as k_conv_fused does); every segment is visited once per role
+// and each visit writes an 84-wide partial output row that k_conv_finalize adds in a fixed order.  Warp roles inside a CTA:
+//   * 2 gather warps: list entries, destination feature rows, harmonics and the role's hidden units of 8 edges -> staging ring
+//     (cp.async, completion on mbarriers; they run ahead across segment boundaries);
+//   * 4 row warps: thread p evaluates basis row p of the 8 edges, splits it into TF32 hi + lo and writes it into TENSOR MEMORY
+//     (tcgen05.st; the A operand never touches shared memory); they also split the hidden units into the B operand
+//     (K-major no-swizzle UMMA layout in shared memory, one extra row of ones -> Bsum);
+//   * 1 MMA thread: three tcgen05.mma kind::tf32 (.ts form) per chunk -- hi*hi + hi*lo + lo*hi -- into the segment's
+//     accumulator slot; tcgen05.commit frees the operand stage and publishes the finished accumulator;
+//   * 8 contraction warps: tcgen05.ld the accumulators of G finished segments (G = 2 for vector roles, 4 for scalar roles) and
+//     contract them with the resident weights in packed FFMA2 -- every weight read from shared memory is used for G segments
+//     (and, in vector roles, for the three components that sit in neighbouring lanes: broadcast) --, reduce over the rows of
+//     each (class, component) through shared memory in a fixed order and write the partial rows.
+// Measured pacing of tcgen05.mma kind::tf32 on B200 (tools/microbench/umma_pacing.cu): max(46, N / 2) cycles per instruction for
+// M = 64 and 128 alike, so an M = 128 x N = 80 tile costs the same as any narrower one -- the reason every role keeps the
+// widest N its weights allow and one tile.
+// Results do not depend on the claiming order: every (segment, role) partial is produced by one fixed instruction sequence.
+#include <cuda_pipeline_primitives.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "ddk_tc.cuh"
+
+namespace ddk {
+
+constexpr int TR_NST = 3;            // operand stages (A in tensor memory, B in shared memory)
+constexpr int TR_XR = 6;             // staging ring of the gather warps
+constexpr int TR_GW = 2;             // gather warps
+constexpr int TR_ROWW = 4;           // row warps = one 128-row tile
+constexpr int TR_CONW = 8;           // contraction warps
+constexpr int TR_THREADS = (TR_ROWW + 1 + TR_GW + TR_CONW) * 32;   // 480
+constexpr int TR_W_MMA = TR_ROWW, TR_W_GATHER = TR_ROWW + 1, TR_W_CON = TR_ROWW + 1 + TR_GW;
+constexpr int TR_COLS = 512;         // tensor-memory columns allocated
+constexpr int TR_ACOL = 448;         // A operand stages: TR_NST x (8 hi + 8 lo) columns from here; accumulator slots below
+constexpr int TR_NMAX = 80;          // widest MMA N
+constexpr int TR_BAR_CON = 1;        // named barrier of the contraction warps
+constexpr int TR_GV = 2, TR_GS = 4;  // segments contracted together: vector roles / scalar roles
+constexpr int TR_RED_FLOATS = 6144;  // partial outputs of a group: max(G_V * 2 halves * 128 rows * 6, G_S * 64 rows * 24)
+constexpr int TR_RED2 = 256;
+
+struct TrArgs {
+  int NL, N;
+  int nb_segs;                       // segments per task (multiple of 8)
+  int gmask;                         // bit g set: edge group g is processed
+  const int4* glist; int goff[4]; int gci[4];
+  const int* gcnt;                   // [list] segments; [2 F3_NLIST + 4 ... ] see launch_build_group_lists
+  const int* gedges;                 // [list] listed edges of this step
+  int* counters;                     // [4 * nroles] segment cursor of each combo
+  const int2* seg_list;
+  const float* x;                    // [N][84] layer input
+  const float* hs; size_t LT;        // [72 / J][LT][J] hidden units of every listed edge (k_edge_hidden)
+  const float4* sh_pool;
+  const TcrRole* roles; int nroles;  // roles of the level
+  const float* W[4][TCR_MAXROLES];   // resident weight slice of (group, role)
+  float* part;                       // [2 N][nroles][84]
+};
+
+template <int LV>
+struct TrCfg {
+  static constexpr int U = AccCfg<LV>::U, DINP = AccCfg<LV>::DINP, XQ = DINP / 4;
+  static constexpr int J = f3_J(LV), NSL = HID / J;
+};
+
+template <int LV>
+struct TrSmem {
+  alignas(128) uint32_t Bhi[TR_NST][TR_NMAX * 8];
+  alignas(128) uint32_t Blo[TR_NST][TR_NMAX * 8];
+  alignas(16) float X[TR_XR][KC3][TrCfg<LV>::DINP];
+  alignas(16) float SH[TR_XR][KC3][4];
+  alignas(16) float HS[TR_XR][TrCfg<LV>::NSL][KC3 * TrCfg<LV>::J + 8];
+  alignas(16) float RED[TR_RED_FLOATS];
+  alignas(16) float RED2[2][TR_RED2];
+  alignas(16) TcrRole role;                                             // the resident role's tables
+  alignas(8) unsigned long long full[TR_NST], empty[TR_NST];            // operand stages: row warps <-> MMA thread
+  alignas(8) unsigned long long sfull[TR_XR], sempty[TR_XR];            // staging ring: gather warps <-> row warps
+  alignas(8) unsigned long long accfull[TCR_MAXACC], accempty[TCR_MAXACC];   // accumulator slots: MMA thread <-> contraction warps
+  alignas(8) unsigned long long bar_w;                                  // completion of the weight-slice bulk copy
+  uint32_t tmem_base;
+  int task[8];                       // g, role, idx0, nseg, reload, combo cursor, resident combo (g * nroles + role), -
+  alignas(128) float Wsl[1];         // the resident weight slice follows (TCR_WMAX floats, dynamic)
+};
+
+__device__ __forceinline__ void tr_bar_con() { asm volatile("bar.sync %0, %1;" ::"n"(TR_BAR_CON), "n"(TR_CONW * 32) : "memory"); }
+
+typedef unsigned long long tr_f32x2;
+__device__ __forceinline__ void tr_ffma2(tr_f32x2& d, const tr_f32x2 a, const tr_f32x2 b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ tr_f32x2 tr_pack2(const float x, const float y) {
+  tr_f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+  return r;
+}
+__device__ __forceinline__ void tr_unpack2(const tr_f32x2 v, float& x, float& y) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v));
+}
+__device__ __forceinline__ void tr_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr));
+}
+
+// ---------------------------------------------------------------------------------------------- contraction warps
+// One group of G segments (slots sg .. sg + G - 1; nvalid of them real).  VEC: lane = basis row (class, component c, row f of the
+// class) with the three components in neighbouring lanes, so the 6 weights of (f, j) are one broadcast 8-byte load per pair;
+// the two warp sets split the columns.  Scalar roles: lane = row, the two warp sets split the 24 outputs.
+template <int LV, bool VEC>
+__device__ __forceinline__ void tr_con_group(const TrArgs& p, TrSmem<LV>& S, const float* __restrict__ Wsl, const uint32_t tmem,
+                                             const int sg, const int nvalid, const int seg0, const int g_edge, const int role_id,
+                                             const int cw, const int q, const int lane, const int ct, const int gi) {
+  constexpr int G = VEC ? TR_GV : TR_GS, NACC = 2 * G;
+  constexpr int O = VEC ? 6 : 24, OT = VEC ? 6 : 12;          // outputs per row; outputs per thread
+  constexpr int NP2 = OT / 2;
+  const TcrRole& R = S.role;
+  const int N = R.N, ncol = R.ncol;
+  const int set = cw >> 2;                                    // warp set 0 / 1
+  const int prow = 32 * q + lane;
+  const bool active = prow < R.nrows && (VEC || true);
+  // columns [c0, c1) and first output of this thread
+  int c0 = 0, c1 = ncol, o0 = 0;
+  if (VEC) { c0 = set ? 40 : 0; c1 = set ? ncol : min(40, ncol); } else { o0 = 12 * set; }
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    const int s = sg + g, slot = s % NACC;
+    tc_mbar_wait_sleep(&S.accfull[slot], (s / NACC) & 1);
+  }
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  tr_f32x2 acc[G][NP2];
+#pragma unroll
+  for (int g = 0; g < G; ++g)
+#pragma unroll
+    for (int k = 0; k < NP2; ++k) acc[g][k] = 0ull;
+  const float* wrow = Wsl + (active ? R.woff[prow] : 0) + o0;
+  const uint32_t tlane = tmem + ((uint32_t)(32 * q) << 16);
+  for (int cb = c0 & ~7; cb < c1; cb += 8) {
+    uint32_t v[G][8];
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+      if (g < nvalid) tr_ld8(tlane + ((sg + g) % NACC) * N + cb, v[g]);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (active) {
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        const int col = cb + jj;
+        if (col >= c0 && col < c1) {
+          const float* w = wrow + col * O;
+          tr_f32x2 wv[NP2];
+          if (VEC) {
+#pragma unroll
+            for (int k = 0; k < NP2; ++k) wv[k] = *reinterpret_cast<const tr_f32x2*>(w + 2 * k);
+          } else {
+#pragma unroll
+            for (int k = 0; k < NP2 / 2; ++k) {
+              const float4 t4 = *reinterpret_cast<const float4*>(w + 4 * k);
+              wv[2 * k] = tr_pack2(t4.x, t4.y); wv[2 * k + 1] = tr_pack2(t4.z, t4.w);
+            }
+          }
+#pragma unroll
+          for (int g = 0; g < G; ++g)
+            if (g < nvalid) {
+              const float a = __uint_as_float(v[g][jj]);
+              const tr_f32x2 aa = tr_pack2(a, a);
+#pragma unroll
+              for (int k = 0; k < NP2; ++k) tr_ffma2(acc[g][k], aa, wv[k]);
+            }
+        }
+      }
+    }
+  }
+  // every accumulator value this thread needs is in registers: the slots may be refilled
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncwarp();
+  if (lane == 0) {
+#pragma unroll
+    for (int g = 0; g < G; ++g) tc_mbar_arrive(&S.accempty[(sg + g) % NACC]);
+  }
+  // ---- partial outputs of the rows -> RED[g][h][row][o]
+  constexpr int H = VEC ? 2 : 1, RR = VEC ? 128 : 64;
+  if (active) {
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+      if (g < nvalid) {
+        float* r = &S.RED[(((g * H) + (VEC ? set : 0)) * RR + prow) * O + o0];
+#pragma unroll
+        for (int k = 0; k < NP2; ++k) {
+          float a0, a1;
+          tr_unpack2(acc[g][k], a0, a1);
+          r[2 * k] = a0; r[2 * k + 1] = a1;
+        }
+      }
+  }
+  tr_bar_con();
+  // ---- stage 1: thread (g, row group rg = (class, component), output o, part) adds its share of the group's rows
+  const int nrg = R.nrg, np = R.np, nout = nrg * O;
+  float* red2 = &S.RED2[gi & 1][0];
+  if (ct < G * nout * np) {
+    const int part = ct % np;
+    int rest = ct / np;
+    const int o = rest % O; rest /= O;
+    const int rg = rest % nrg, g = rest / nrg;
+    float s = 0.f;
+    if (g < nvalid) {
+      const int F = R.rgF[rg];
+      const int f0 = (part * F) / np, f1 = ((part + 1) * F) / np;
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        const float* base = &S.RED[((g * H + h) * RR) * O + o];
+        for (int f = f0; f < f1; ++f) s += base[R.rgrow[rg][f] * O];
+      }
+    }
+    red2[ct] = s;
+  }
+  tr_bar_con();
+  // ---- stage 2: the 84-wide partial row of (segment, role): owned columns from the sums, zeros elsewhere
+  for (int t2 = ct; t2 < G * D; t2 += TR_CONW * 32) {
+    const int g = t2 / D, f = t2 % D;
+    if (g < nvalid) {
+      const int src = R.outsrc[f];
+      float v = 0.f;
+      if (src >= 0) {
+        const float* b = red2 + (g * nout + src) * np;
+        for (int k = 0; k < np; ++k) v += b[k];
+      }
+      const int sid = __ldg(&p.glist[g_edge + seg0 + g].x);
+      p.part[((size_t)sid * p.nroles + role_id) * D + f] = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- the kernel
+template <int LV>
+__global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constant__ TrArgs p) {
+  using Cfg = TrCfg<LV>;
+  constexpr int DINP = Cfg::DINP, XQ = Cfg::XQ, J = Cfg::J;
+  extern __shared__ __align__(128) unsigned char tr_raw[];
+  TrSmem<LV>& S = *reinterpret_cast<TrSmem<LV>*>(tr_raw);
+  float* const Wsl = &S.Wsl[0];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ncombo = 4 * p.nroles;
+
+  // ---- one-time setup
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem(&S.tmem_base)), "n"(TR_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == TR_W_MMA * 32) {
+    for (int s = 0; s < TR_NST; ++s) { tc_mbar_init(&S.full[s], TR_ROWW); tc_mbar_init(&S.empty[s], 1); }
+    for (int s = 0; s < TR_XR; ++s) { tc_mbar_init(&S.sfull[s], 32 * TR_GW); tc_mbar_init(&S.sempty[s], TR_ROWW); }
+    for (int s = 0; s < TCR_MAXACC; ++s) { tc_mbar_init(&S.accfull[s], 1); tc_mbar_init(&S.accempty[s], TR_CONW); }
+    tc_mbar_init(&S.bar_w, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // first combo of this CTA: the combos share the CTAs in proportion to a rough cost model (per listed edge and per segment,
+    // vector roles about twice the scalar ones), so few CTAs have to migrate -- and reload a weight slice -- before the tail
+    float cost[4 * TCR_MAXROLES], total = 0.f;
+    for (int cmb = 0; cmb < ncombo; ++cmb) {
+      const int g = cmb / p.nroles, r = cmb % p.nroles;
+      float c = 0.f;
+      if ((p.gmask >> g) & 1) {
+        const float ne = (float)p.gedges[p.gci[g]], ns = (float)p.gcnt[p.gci[g]];
+        c = p.roles[r].isS ? ne * 10.f + ns * 400.f : ne * 18.f + ns * 500.f;
+      }
+      cost[cmb] = c; total += c;
+    }
+    const float pos = ((float)blockIdx.x + 0.5f) / (float)gridDim.x * total;
+    int first = 0;
+    float run = 0.f;
+    for (int cmb = 0; cmb < ncombo; ++cmb) { run += cost[cmb]; first = cmb; if (run > pos) break; }
+    S.task[5] = first; S.task[6] = -1;
+  }
+  {
+    uint32_t* z = &S.Bhi[0][0];
+    constexpr int nz = 2 * TR_NST * TR_NMAX * 8;
+    for (int i = tid; i < nz; i += TR_THREADS) z[i] = 0u;
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = S.tmem_base;
+
+  int it = 0;        // 8-edge chunks so far (gather / row warps / MMA thread count the same sequence)
+  int sg = 0;        // accumulator slots so far (MMA thread / contraction warps); a multiple of the group size between tasks
+  int nwl = 0;       // weight-slice loads so far
+  int gcount = 0;    // contraction groups so far
+
+  for (;;) {
+    // ---- claim a task: (combo, block of segments); stay on the resident combo while it has work
+    if (tid == 0) {
+      int combo = S.task[5], found = 0;
+      for (int tries = 0; tries < ncombo && !found; ++tries) {
+        const int g = combo / p.nroles;
+        const int gall = ((p.gmask >> g) & 1) ? p.gcnt[p.gci[g]] : 0;
+        const int rem = gall - *reinterpret_cast<volatile int*>(p.counters + combo);
+        if (rem > 0) {
+          const int size = max(8, min(p.nb_segs, (rem / 8) / 8 * 8));       // guided self-scheduling
+          const int start = atomicAdd(p.counters + combo, size);
+          if (start < gall) {
+            S.task[0] = g; S.task[1] = combo % p.nroles; S.task[2] = start; S.task[3] = min(size, gall - start);
+            S.task[4] = (combo != S.task[6]);
+            S.task[5] = combo; S.task[6] = combo;
+            found = 1;
+            break;
+          }
+        }
+        combo = (combo + 1) % ncombo;
+      }
+      if (!found) S.task[0] = -1;
+    }
+    __syncthreads();
+    const int g = S.task[0];
+    if (g < 0) break;
+    const int role_id = S.task[1], idx0 = S.task[2], nseg = S.task[3];
+    if (S.task[4]) {
+      // every read of the previous slice / role tables happened before the __syncthreads that ended the previous task
+      const TcrRole* src = p.roles + role_id;
+      if (tid == 0) {
+        const uint32_t bytes = (uint32_t)src->wfloats * 4u;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        tc_mbar_expect_tx(&S.bar_w, bytes);
+        tc_bulk_g2s(Wsl, p.W[g][role_id], bytes, &S.bar_w);
+      }
+      {
+        const int4* s4 = reinterpret_cast<const int4*>(src);
+        int4* d4 = reinterpret_cast<int4*>(&S.role);
+        static_assert(sizeof(TcrRole) % 16 == 0, "role tables are copied in 16-byte pieces");
+        for (int i = tid; i < (int)(sizeof(TcrRole) / 16); i += TR_THREADS) d4[i] = __ldg(s4 + i);
+      }
+      // the accumulator-slot ring depends on the role kind (4 slots of 80 columns / 8 slots of 32 or 48): every pipeline is
+      // drained here, so the slot barriers restart from phase 0 together with the slot counter
+      if (tid == TR_W_MMA * 32) {
+        for (int sI = 0; sI < TCR_MAXACC; ++sI) {
+          asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(tc_smem(&S.accfull[sI])) : "memory");
+          asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(tc_smem(&S.accempty[sI])) : "memory");
+          tc_mbar_init(&S.accfull[sI], 1); tc_mbar_init(&S.accempty[sI], TR_CONW);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      }
+      sg = 0;
+      tc_mbar_wait_sleep(&S.bar_w, nwl & 1);
+      ++nwl;
+      __syncthreads();
+    }
+    const TcrRole& R = S.role;
+    const int N = R.N, nj = R.nj, j0 = R.j0, sl0 = R.sl0, nsl = R.nsl;
+    const bool vec = !R.isS;
+    const int G = vec ? TR_GV : TR_GS, NACC = 2 * G;
+    const int4* wl = p.glist + p.goff[g] + idx0;
+
+    if (warp < TR_ROWW) {
+      // ================================================================== row warps: A operand -> tensor memory, B -> smem
+      const TcRow rd = R.rows[tid];
+      const bool plain = __all_sync(0xffffffffu, rd.type == 0);
+      const int i1 = rd.type == 0 ? rd.i0 : rd.i0 + 1, i2 = rd.type == 0 ? rd.i0 : rd.i0 + 2;
+      const float w_t0 = rd.type == 0 ? 1.f : 0.f, w_dt = rd.type == 1 ? 1.f : 0.f;
+      const float w_c1 = (rd.type == 2 && rd.m == 1) ? 1.f : 0.f, w_c2 = (rd.type == 2 && rd.m == 2) ? 1.f : 0.f,
+                  w_c3 = (rd.type == 2 && rd.m == 3) ? 1.f : 0.f;
+      // B operand work items of this thread: item w = (row n = w % (nj + 1) of the tile, half hk = w / (nj + 1) of the 8 edges)
+      const int nb_items = 2 * (nj + 1);
+      int bn[2], bh[2];
+#pragma unroll
+      for (int b2 = 0; b2 < 2; ++b2) {
+        const int w = tid + 128 * b2;
+        bn[b2] = w < nb_items ? w % (nj + 1) : -1;
+        bh[b2] = w < nb_items ? w / (nj + 1) : 0;
+      }
+      for (int i = 0; i < nseg; ++i) {
+        const int n = load_seg_entry(wl + i).y;
+        const int nch = (n + KC3 - 1) / KC3;
+        for (int c = 0; c < nch; ++c, ++it) {
+          const int kc = min(KC3, n - c * KC3);
+          const int buf = it % TR_XR, stage = it % TR_NST;
+          tc_mbar_wait(&S.sfull[buf], (it / TR_XR) & 1);
+          tc_mbar_wait(&S.empty[stage], ((it / TR_NST) & 1) ^ 1);
+          float b[KC3];
+          if (plain) {
+            float xv[KC3], sv[KC3];
+#pragma unroll
+            for (int e = 0; e < KC3; ++e) { xv[e] = S.X[buf][e][rd.i0]; sv[e] = S.SH[buf][e][rd.m]; }
+#pragma unroll
+            for (int e = 0; e < KC3; ++e) b[e] = xv[e] * sv[e];
+          } else {
+#pragma unroll
+            for (int e = 0; e < KC3; ++e) {
+              const float4 s4 = *reinterpret_cast<const float4*>(&S.SH[buf][e][0]);
+              const float v0 = S.X[buf][e][rd.i0], v1 = S.X[buf][e][i1], v2 = S.X[buf][e][i2];
+              const float t0 = v0 * S.SH[buf][e][rd.m];
+              float dt = v0 * s4.y; dt = fmaf(v1, s4.z, dt); dt = fmaf(v2, s4.w, dt);
+              const float c1 = fmaf(v1, s4.w, -(v2 * s4.z)), c2 = fmaf(v2, s4.y, -(v0 * s4.w)), c3 = fmaf(v0, s4.z, -(v1 * s4.y));
+              b[e] = w_t0 * t0 + w_dt * dt + w_c1 * c1 + w_c2 * c2 + w_c3 * c3;
+            }
+          }
+          {
+            uint32_t hi[KC3], lo[KC3];
+#pragma unroll
+            for (int e = 0; e < KC3; ++e) tc_split_rn(b[e], hi[e], lo[e]);
+            const uint32_t ta = tmem + ((uint32_t)(32 * warp) << 16) + TR_ACOL + stage * 16;
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                         ::"r"(ta), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]), "r"(hi[4]), "r"(hi[5]), "r"(hi[6]), "r"(hi[7]) : "memory");
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                         ::"r"(ta + 8), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]), "r"(lo[4]), "r"(lo[5]), "r"(lo[6]), "r"(lo[7]) : "memory");
+          }
+#pragma unroll
+          for (int b2 = 0; b2 < 2; ++b2) {
+            const int nrow = bn[b2], hk = bh[b2];
+            if (nrow >= 0) {
+              uint32_t h[4], l[4];
+              if (nrow < nj) {
+                const int hj = j0 + nrow, sl = hj / J - sl0, jj = hj % J;
+#pragma unroll
+                for (int qd = 0; qd < 4; ++qd) {
+                  const float hld = S.HS[buf][sl][(4 * hk + qd) * J + jj];
+                  tc_split_rn(4 * hk + qd < kc ? hld : 0.f, h[qd], l[qd]);      // padded edges hold a copy of the last edge
+                }
+              } else {                                                           // the ones row -> Bsum
+#pragma unroll
+                for (int qd = 0; qd < 4; ++qd) { h[qd] = 4 * hk + qd < kc ? 0x3f800000u : 0u; l[qd] = 0u; }
+              }
+              *reinterpret_cast<uint4*>(&S.Bhi[stage][(nrow + N * hk) * 4]) = make_uint4(h[0], h[1], h[2], h[3]);
+              *reinterpret_cast<uint4*>(&S.Blo[stage][(nrow + N * hk) * 4]) = make_uint4(l[0], l[1], l[2], l[3]);
+            }
+          }
+          __syncwarp();
+          if (lane == 0) tc_mbar_arrive(&S.sempty[buf]);
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) tc_mbar_arrive(&S.full[stage]);
+        }
+      }
+    } else if (warp == TR_W_MMA) {
+      // ================================================================== MMA issue (one thread)
+      if (lane == 0) {
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        for (int i = 0; i < nseg; ++i, ++sg) {
+          const int nch = (load_seg_entry(wl + i).y + KC3 - 1) / KC3;
+          const int slot = sg % NACC;
+          tc_mbar_wait(&S.accempty[slot], ((sg / NACC) & 1) ^ 1);                  // the contraction warps have read the slot's old content
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t d = tmem + slot * N;
+          for (int c = 0; c < nch; ++c, ++it) {
+            const int stage = it % TR_NST;
+            tc_mbar_wait(&S.full[stage], (it / TR_NST) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint64_t bhd = tc_desc(tc_smem(&S.Bhi[stage][0]), N * 16, 128);
+            const uint64_t bld = tc_desc(tc_smem(&S.Blo[stage][0]), N * 16, 128);
+            const uint32_t ah = tmem + TR_ACOL + stage * 16, al = ah + 8;
+            tc_mma_ts(d, ah, bhd, idesc, c > 0);
+            tc_mma_ts(d, ah, bld, idesc, 1);
+            tc_mma_ts(d, al, bhd, idesc, 1);
+            tc_commit(&S.empty[stage]);
+            if (c == nch - 1) tc_commit(&S.accfull[slot]);
+          }
+        }
+        for (; sg % G != 0; ++sg) {                                              // pad the last group of the task with empty slots
+          const int slot = sg % NACC;
+          tc_mbar_wait(&S.accempty[slot], ((sg / NACC) & 1) ^ 1);
+          tc_mbar_arrive(&S.accfull[slot]);
+        }
+      }
+    } else if (warp < TR_W_CON) {
+      // ================================================================== gather warps: global -> staging ring (cp.async only)
+      const int gw = warp - TR_W_GATHER;               // 0: feature rows + harmonics, 1: hidden units of the role
+      for (int i = 0; i < nseg; ++i) {
+        const int4 ge = load_seg_entry(wl + i);
+        const int n = ge.y, base = ge.z;
+        const int nch = (n + KC3 - 1) / KC3;
+        int2 ent_next = make_int2(0, 0);
+        if (gw == 0 && lane < KC3) ent_next = p.seg_list[base + min(lane, n - 1)];
+        for (int c = 0; c < nch; ++c, ++it) {
+          const int kc = min(KC3, n - c * KC3), pos0 = base + c * KC3;
+          const int buf = it % TR_XR;
+          const int2 ent = ent_next;
+          if (gw == 0 && lane < KC3 && c + 1 < nch) ent_next = p.seg_list[pos0 + KC3 + min(lane, n - (c + 1) * KC3 - 1)];
+          tc_mbar_wait(&S.sempty[buf], ((it / TR_XR) & 1) ^ 1);
+          if (gw == 0) {
+            constexpr int NP = KC3 * XQ + KC3;            // 16-byte pieces: feature rows, then one harmonics record per edge
+#pragma unroll
+            for (int k = 0; k < (NP + 31) / 32; ++k) {    // uniform trip count: the shuffles need the whole warp
+              const int q0 = lane + 32 * k;
+              const bool on = q0 < NP, isx = q0 < KC3 * XQ;
+              const int e = !on ? 0 : (isx ? q0 / XQ : q0 - KC3 * XQ), qq = isx ? q0 % XQ : 0;
+              const int es = min(e, kc - 1);
+              const int slot = __shfl_sync(0xffffffffu, ent.x, es), dst = __shfl_sync(0xffffffffu, ent.y, es);
+              if (on) {
+                if (isx) __pipeline_memcpy_async(&S.X[buf][e][4 * qq], p.x + (size_t)dst * D + 4 * qq, 16);
+                else __pipeline_memcpy_async(&S.SH[buf][e][0], p.sh_pool + slot, 16);
+              }
+            }
+          } else {
+            constexpr int PJ = J / 4;                     // 16-byte pieces per (slice, edge)
+            for (int q0 = lane; q0 < nsl * KC3 * PJ; q0 += 32) {
+              const int r = q0 / (KC3 * PJ), e = (q0 / PJ) % KC3, qq = q0 % PJ;
+              const int es = min(e, kc - 1);
+              __pipeline_memcpy_async(&S.HS[buf][r][e * J + 4 * qq], p.hs + ((size_t)(sl0 + r) * p.LT + pos0 + es) * J + 4 * qq, 16);
+            }
+          }
+          asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tc_smem(&S.sfull[buf])) : "memory");
+        }
+      }
+      asm volatile("cp.async.wait_all;" ::: "memory");
+    } else {
+      // ================================================================== contraction warps
+      const int cw = warp - TR_W_CON, q = warp & 3, ct = cw * 32 + lane;
+      const int ngroups = (nseg + G - 1) / G;
+      for (int grp = 0; grp < ngroups; ++grp, sg += G, ++gcount) {
+        const int nvalid = min(G, nseg - grp * G);
+        if (vec) tr_con_group<LV, true>(p, S, Wsl, tmem, sg, nvalid, idx0 + grp * G, p.goff[g], role_id, cw, q, lane, ct, gcount);
+        else tr_con_group<LV, false>(p, S, Wsl, tmem, sg, nvalid, idx0 + grp * G, p.goff[g], role_id, cw, q, lane, ct, gcount);
+      }
+    }
+    // every thread keeps only the counters its own warp role uses (`it`: gather / row warps / MMA thread; `sg`: MMA thread /
+    // contraction warps) and advances them by walking the same task sequence, so they agree without any exchange
+    __syncthreads();
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TR_COLS));
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+static int tcr_ncols16(int n) { return (n + 15) / 16 * 16; }
+
+// Roles of basis level lv (see the header).  cls: the irrep classes of a layer of that level (build_layers).
+int build_tcr_roles(int lv, const LayerInfo& li, TcrRole* roles) {
+  const int J = f3_J(lv);
+  std::vector<TcRow> all(TC_MAXROWS);
+  build_tc_rows(lv, all.data());                      // (type, i0, m, u) of every basis row of the level
+  std::vector<TcRow> byu(li.U);
+  for (int p = 0; p < TC_MAXROWS; ++p) if (all[p].u >= 0) byu[all[p].u] = all[p];
+  struct Spec { std::vector<int> cls; int j0, nj; bool isS; };
+  std::vector<Spec> specs;
+  std::vector<int> vcls, scls;
+  for (int k = 0; k < li.ncls; ++k) (li.cls[k].ncomp == 3 ? vcls : scls).push_back(k);
+  // vector roles: as many classes per role as fit one tile
+  {
+    std::vector<int> cur; int rows = 0;
+    for (int k : vcls) {
+      const int r = 3 * li.cls[k].F;
+      if (!cur.empty() && rows + r > 128) { specs.push_back({cur, 0, HID, false}); cur.clear(); rows = 0; }
+      cur.push_back(k); rows += r;
+    }
+    if (!cur.empty()) specs.push_back({cur, 0, HID, false});
+  }
+  // scalar roles: all scalar classes, the hidden units in thirds (levels 0, 3: slices of 24 / 8) or halves (levels 1, 2: 12)
+  if (!scls.empty()) {
+    const int parts = (lv == 0 || lv == 3) ? 3 : 2;
+    for (int h = 0; h < parts; ++h) specs.push_back({scls, h * (HID / parts), HID / parts, true});
+  }
+  if ((int)specs.size() > TCR_MAXROLES) return -1;
+  for (size_t r = 0; r < specs.size(); ++r) {
+    const Spec& sp = specs[r];
+    TcrRole& R = roles[r];
+    memset(&R, 0, sizeof(R));
+    R.isS = sp.isS; R.j0 = sp.j0; R.nj = sp.nj; R.ncol = sp.nj + 1; R.N = tcr_ncols16(R.ncol);
+    if (sp.j0 % J || sp.nj % J) return -1;
+    R.sl0 = sp.j0 / J; R.nsl = sp.nj / J;
+    R.O = sp.isS ? 24 : 6;
+    // weight block of one (class, f): ncol x O floats, padded so that consecutive blocks start in different bank groups
+    const int blk = R.ncol * R.O;
+    R.wstride = sp.isS ? ((blk + 3) / 4 * 4 + (((blk + 3) / 4) % 2 == 0 ? 4 : 0)) : (blk % 4 == 2 ? blk : blk + 2);
+    // rows: type-sorted (plain products first); in vector roles the three components of (class, f) in neighbouring lanes
+    int n = 0, wblocks = 0;
+    std::vector<int> blk_of((size_t)li.ncls * 64, -1);
+    for (int k : sp.cls) for (int f = 0; f < li.cls[k].F; ++f) blk_of[(size_t)k * 64 + f] = wblocks++;
+    for (int pass = 0; pass < 3; ++pass)
+      for (int k : sp.cls) {
+        const ClassInfo& ci = li.cls[k];
+        for (int f = 0; f < ci.F; ++f) {
+          if (byu[ci.uoff + f].type != pass) continue;
+          for (int c = 0; c < ci.ncomp; ++c) {
+            if (n >= 128) return -1;
+            const int u = ci.uoff + c * ci.F + f;
+            if (byu[u].type != pass) return -1;            // the components of a row share its type
+            R.rows[n] = byu[u];
+            R.woff[n] = blk_of[(size_t)k * 64 + f] * R.wstride;
+            ++n;
+          }
+        }
+      }
+    R.nrows = n;
+    if (sp.isS && n > 64) return -1;
+    for (int i = n; i < 128; ++i) { R.rows[i] = TcRow{0, 0, 0, -1}; R.woff[i] = 0; }
+    R.wfloats = (wblocks * R.wstride + 3) / 4 * 4;
+    if (R.wfloats > TCR_WMAX) return -1;
+    // row groups (class, component) and the output columns they feed
+    for (int f = 0; f < D; ++f) R.outsrc[f] = -1;
+    int nrg = 0;
+    for (int k : sp.cls) {
+      const ClassInfo& ci = li.cls[k];
+      if (ci.O != R.O) return -1;
+      for (int c = 0; c < ci.ncomp; ++c) {
+        if (nrg >= TCR_MAXRG || ci.F > TCR_MAXF) return -1;
+        R.rgF[nrg] = ci.F;
+        for (int f = 0; f < ci.F; ++f) {
+          const int u = ci.uoff + c * ci.F + f;
+          int pos = -1;
+          for (int i = 0; i < n; ++i) if (R.rows[i].u == u) pos = i;
+          if (pos < 0) return -1;
+          R.rgrow[nrg][f] = (short)pos;
+        }
+        for (int o = 0; o < ci.O; ++o) R.outsrc[ci.col0 + (ci.ncomp == 3 ? 3 * o + c : o)] = (short)(nrg * R.O + o);
+        ++nrg;
+      }
+    }
+    R.nrg = nrg;
+    const int G = sp.isS ? TR_GS : TR_GV;
+    R.np = std::max(1, std::min(8, (TR_CONW * 32) / (G * nrg * R.O)));
+    if (G * nrg * R.O * R.np > TR_RED2 || G * (sp.isS ? 1 : 2) * (sp.isS ? 64 : 128) * R.O > TR_RED_FLOATS) return -1;
+    if (2 * G > TCR_MAXACC || 2 * G * R.N > TR_ACOL) return -1;
+  }
+  return (int)specs.size();
+}
+
+// The weight slice of (layer, group, role): for every (class, f) block of the role [ncol][O] floats (the role's hidden units,
+// then the bias row that multiplies Bsum; zero for roles that do not start at hidden unit 0 -- their Bsum share is counted once)
+void build_tcr_weights(const LayerInfo& li, const TcrRole& R, const float* w2p, const float* b2p, float* out) {
+  std::fill(out, out + R.wfloats, 0.f);
+  std::vector<char> done(128, 0);
+  for (int i = 0; i < R.nrows; ++i) {
+    const int u = R.rows[i].u;
+    int k = 0;
+    while (k + 1 < li.ncls && u >= li.cls[k + 1].uoff) ++k;
+    const ClassInfo& ci = li.cls[k];
+    const int f = (u - ci.uoff) % ci.F;
+    float* blk = out + R.woff[i];
+    for (int jj = 0; jj < R.nj; ++jj)
+      for (int o = 0; o < ci.O; ++o) blk[jj * ci.O + o] = w2p[ci.woff + ((int64_t)f * HID + (R.j0 + jj)) * ci.O + o];
+    if (R.j0 == 0)
+      for (int o = 0; o < ci.O; ++o) blk[R.nj * ci.O + o] = b2p[ci.boff + (int64_t)f * ci.O + o];
+  }
+}
+
+size_t tcr_smem_bytes(int lv) {
+  const size_t base = lv == 0 ? offsetof(TrSmem<0>, Wsl) : lv == 1 ? offsetof(TrSmem<1>, Wsl) : lv == 2 ? offsetof(TrSmem<2>, Wsl)
+                                                                                                       : offsetof(TrSmem<3>, Wsl);
+  return base + (size_t)TCR_WMAX * sizeof(float);
+}
+
+cudaError_t conv_tcr_configure() {
+  cudaError_t e;
+  e = cudaFuncSetAttribute(k_conv_tcr<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcr_smem_bytes(0));
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_conv_tcr<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcr_smem_bytes(1));
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_conv_tcr<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcr_smem_bytes(2));
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(k_conv_tcr<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcr_smem_bytes(3));
+}
+
+void launch_conv_tcr(DdkCtx* c, int layer, const float* x_in, float* x_out, cudaStream_t st, int mode) {
+  const bool lig_only = mode == CONV_LIG;
+  const LayerInfo& li = c->layers[layer];
+  const int nroles = c->tcr_nroles[li.lv];
+  TrArgs a;
+  a.NL = c->NL; a.N = c->N;
+  a.gmask = lig_only ? 0x3 : 0xf;
+  const int nsegs = 2 * (lig_only ? c->NL : c->N);
+  static const int tasks_per_cta = getenv("DDK_TCR_TASKS_PER_CTA") ? atoi(getenv("DDK_TCR_TASKS_PER_CTA")) : 12;
+  int nb = (int)((int64_t)nsegs * nroles / (c->sm_count * tasks_per_cta)) / 8 * 8;
+  a.nb_segs = std::min(256, std::max(8, nb));
+  a.glist = ptr<int4>(c->b_glist);
+  a.goff[0] = 0; a.goff[1] = c->NL; a.goff[2] = 2 * c->NL; a.goff[3] = 2 * c->NL + c->NR;
+  for (int g = 0; g < 4; ++g) a.gci[g] = g;
+  if (mode >= CONV_NEEDED) { const int h = mode - CONV_NEEDED; a.goff[2] = 2 * c->NL + 2 * c->NR + h * c->NR; a.gci[2] = 4 + h; }
+  a.gcnt = ptr<int>(c->b_gcnt);
+  a.gedges = ptr<int>(c->b_gcnt) + F3_NLIST + 4;
+  a.counters = ptr<int>(c->b_counters);
+  a.seg_list = ptr<int2>(c->b_seg_list);
+  a.x = x_in; a.hs = ptr<float>(c->b_hs); a.LT = (size_t)c->list_total;
+  a.sh_pool = ptr<float4>(c->b_sh_pool);
+  a.roles = c->tcr_roles + (size_t)li.lv * TCR_MAXROLES; a.nroles = nroles;
+  for (int g = 0; g < 4; ++g)
+    for (int r = 0; r < TCR_MAXROLES; ++r)
+      a.W[g][r] = r < nroles ? c->w2r + c->w2r_off[((size_t)layer * 4 + g) * TCR_MAXROLES + r] : nullptr;
+  a.part = ptr<float>(c->b_part);
+  cudaMemsetAsync(c->b_counters.p, 0, 4 * TCR_MAXROLES * sizeof(int), st);
+  const int grid = c->sm_count;
+  {
+    LaunchScope ls(c, PC_TC0 + li.lv, st);
+    switch (li.lv) {
+      case 0: k_conv_tcr<0><<<grid, TR_THREADS, tcr_smem_bytes(0), st>>>(a); break;
+      case 1: k_conv_tcr<1><<<grid, TR_THREADS, tcr_smem_bytes(1), st>>>(a); break;
+      case 2: k_conv_tcr<2><<<grid, TR_THREADS, tcr_smem_bytes(2), st>>>(a); break;
+      default: k_conv_tcr<3><<<grid, TR_THREADS, tcr_smem_bytes(3), st>>>(a); break;
+    }
+  }
+  launch_conv_finalize(c, layer, x_in, x_out, st, lig_only, nroles);
+}
+
+// ---- host checks (callable without a GPU): every basis row of a level is owned by exactly one role row, the weight slices
+// reproduce the packed weights, and the shapes fit the kernel's budgets.  Returns 0 if all four levels pass, else 1 + level.
+int host_tcr_roles_check() {
+  for (int lv = 0; lv < 4; ++lv) {
+    // class tables of a layer of this level (as build_layers in ddk_api.cu)
+    const int lin = lv, lout = std::min(lv + 1, 3);
+    int mi0e = NS, mi1o = lin >= 1 ? NV : 0, mi1e = lin >= 2 ? NV : 0, mi0o = lin >= 3 ? NS : 0;
+    int mo[4] = {NS, lout >= 1 ? NV : 0, lout >= 2 ? NV : 0, lout >= 3 ? NS : 0};
+    int F[4] = {mi0e + mi1o, mi0e + mi1o + mi1e, mi1o + mi1e + mi0o, mi1e + mi0o};
+    int ncomp[4] = {1, 3, 3, 1}, col0[4] = {0, 24, 42, 60};
+    LayerInfo li{};
+    li.lv = lv;
+    int uoff = 0; int64_t woff = 0, boff = 0;
+    for (int k = 0; k < 4; ++k) {
+      if (F[k] == 0 || mo[k] == 0) continue;
+      ClassInfo ci{};
+      ci.F = F[k]; ci.O = mo[k]; ci.ncomp = ncomp[k]; ci.uoff = uoff; ci.col0 = col0[k]; ci.woff = woff; ci.boff = boff;
+      li.cls[li.ncls++] = ci;
+      uoff += ncomp[k] * F[k]; woff += (int64_t)F[k] * HID * mo[k]; boff += (int64_t)F[k] * mo[k];
+    }
+    li.U = uoff;
+    std::vector<TcrRole> roles(TCR_MAXROLES);
+    const int nr = build_tcr_roles(lv, li, roles.data());
+    if (nr <= 0) return 1 + lv;
+    // coverage: every (row u, hidden unit j) and every (row u, bias) exactly once
+    std::vector<int> cover((size_t)li.U * (HID + 1), 0);
+    std::vector<float> w2p((size_t)woff), b2p((size_t)boff);
+    for (size_t i = 0; i < w2p.size(); ++i) w2p[i] = 1.f + (float)i;
+    for (size_t i = 0; i < b2p.size(); ++i) b2p[i] = -1.f - (float)i;
+    for (int r = 0; r < nr; ++r) {
+      const TcrRole& R = roles[r];
+      std::vector<float> sl((size_t)R.wfloats);
+      build_tcr_weights(li, R, w2p.data(), b2p.data(), sl.data());
+      for (int i = 0; i < R.nrows; ++i) {
+        const int u = R.rows[i].u;
+        int k = 0;
+        while (k + 1 < li.ncls && u >= li.cls[k + 1].uoff) ++k;
+        const ClassInfo& ci = li.cls[k];
+        const int f = (u - ci.uoff) % ci.F;
+        for (int jj = 0; jj < R.nj; ++jj) {
+          cover[(size_t)u * (HID + 1) + R.j0 + jj]++;
+          for (int o = 0; o < ci.O; ++o)
+            if (sl[R.woff[i] + jj * ci.O + o] != w2p[ci.woff + ((int64_t)f * HID + R.j0 + jj) * ci.O + o]) return 1 + lv;
+        }
+        if (R.j0 == 0) {
+          cover[(size_t)u * (HID + 1) + HID]++;
+          for (int o = 0; o < ci.O; ++o)
+            if (sl[R.woff[i] + R.nj * ci.O + o] != b2p[ci.boff + (int64_t)f * ci.O + o]) return 1 + lv;
+        }
+      }
+    }
+    for (int v : cover) if (v != 1) return 1 + lv;
+  }
+  return 0;
+}
+
+}  // namespace ddk

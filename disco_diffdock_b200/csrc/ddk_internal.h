@@ -68,6 +68,31 @@ struct TcRow { short type, i0, m, u; };   // basis row: 0 = x[i0] * sh[m]; 1 = x
 constexpr int TC_MAXROWS = 384;
 constexpr int TC_MIN_CHUNKS = 8;            // segments with at least this many 8-edge chunks take the tensor-core path
 
+// tensor-core conv with resident contraction (ddk_conv_tcr.cu): a ROLE = (irrep classes, range of hidden units) of a basis level
+constexpr int TCR_MAXROLES = 5;     // roles per level
+constexpr int TCR_MAXACC = 8;       // accumulator slots in tensor memory
+constexpr int TCR_WMAX = 36240;     // floats of the largest resident weight slice (level 3, scalar classes, 24 hidden units + bias)
+constexpr int TCR_MAXRG = 6;        // row groups (class, component) per role
+constexpr int TCR_MAXF = 36;        // rows per row group
+struct alignas(16) TcrRole {
+  int nrows;                        // basis rows of the role (<= 128; scalar roles <= 64)
+  int ncol;                         // contracted accumulator columns: nj hidden units + the ones column (Bsum)
+  int N;                            // MMA N: ncol rounded up to 16
+  int j0, nj;                       // hidden units [j0, j0 + nj)
+  int sl0, nsl;                     // ... as slices of k_edge_hidden's layout (J = f3_J(level) units per slice)
+  int O;                            // outputs per row: 6 (vector classes) or 24 (scalar classes)
+  int isS;                          // scalar-class role
+  int wstride, wfloats;             // floats of one (class, f) weight block incl. padding; floats of the whole slice
+  int nrg, np;                      // row groups; reduction parts per output
+  int pad_[3];
+  TcRow rows[128];                  // basis row evaluated by row thread p (u = -1: padding)
+  int woff[128];                    // offset of row p's weight block inside the slice
+  short rgrow[TCR_MAXRG][TCR_MAXF]; // row threads of row group rg
+  int rgF[TCR_MAXRG];
+  short outsrc[D];                  // node-feature column f <- output rg * O + o of this role, or -1
+};
+static_assert(sizeof(TcrRole) % 16 == 0, "copied in 16-byte pieces");
+
 struct ConSplit {                   // rows [f0, f1) of each irrep class handled by each contraction warp
   int f0[F3_CON][4], f1[F3_CON][4];
 };
@@ -126,6 +151,10 @@ struct DdkCtx {
   int nhop = 0;                       // hops computed per step = num_conv_layers - 1
   ddk::Buf b_hs;                      // [72 / J][list_total][J]: hidden units of every listed edge of the current layer
   ddk::TcRow* tc_rows = nullptr;      // [4 levels][TC_MAXROWS]
+  ddk::TcrRole* tcr_roles = nullptr;  // [4 levels][TCR_MAXROLES] (device)
+  int tcr_nroles[4] = {0, 0, 0, 0};
+  float* w2r = nullptr;               // weight slices of k_conv_tcr: [layer][group][role]
+  std::vector<int64_t> w2r_off;       // [(layer * 4 + group) * TCR_MAXROLES + role] (floats)
   ddk::Buf b_tc_scratch;              // [segment][slice][U][J + 1]: A_s blocks of the tensor-core path
   int tc_cap = 0;                     // segments the scratch holds (0: tensor-core path off)
 
@@ -183,6 +212,14 @@ size_t tc_scratch_floats_per_segment();
 void build_tc_rows(int lv, TcRow* rows);
 void host_tc_split(float a, uint32_t* hi, uint32_t* lo);   // host build of the TF32 hi / lo split of k_acc_tc (tests)
 void launch_acc_tc(DdkCtx* c, int layer, const float* x_in, cudaStream_t st);
+int conv_path();                                     // 0: FFMA2 only, 1: FFMA2 + k_acc_tc for the long segments, 2: k_conv_tcr
+cudaError_t conv_tcr_configure();
+int build_tcr_roles(int lv, const LayerInfo& li, TcrRole* roles);
+void build_tcr_weights(const LayerInfo& li, const TcrRole& R, const float* w2p, const float* b2p, float* out);
+void launch_conv_tcr(DdkCtx* c, int layer, const float* x_in, float* x_out, cudaStream_t st, int mode);
+void launch_conv_finalize(DdkCtx* c, int layer, const float* x_in, float* x_out, cudaStream_t st, bool lig_only, int nsl);
+int host_tcr_roles_check();
+void host_tc_split_rn(float a, uint32_t* hi, uint32_t* lo);
 void host_kabsch(const float* A, const float* Bp, int N, float* R9, float* t3);   // host build of the device routine (tests)
 void host_axis_angle(const float* aa, float* R9);   // opt-in dynamic shared memory sizes (once per process / device)
 

@@ -53,7 +53,7 @@ class DdkStepCoef(C.Structure):
 EXPORTS = ['ddk_abi_version', 'ddk_create', 'ddk_destroy', 'ddk_last_error', 'ddk_set_batch', 'ddk_score', 'ddk_embed',
            'ddk_get_node_features', 'ddk_update', 'ddk_sample', 'ddk_sample_host', 'ddk_kernel_launches',
            'ddk_last_edge_count', 'ddk_debug_read', 'ddk_host_kabsch', 'ddk_host_axis_angle_to_matrix', 'ddk_host_lane_tables_check', 'ddk_host_tc_rows_eval', 'ddk_host_tc_split',
-           'ddk_profile_enable', 'ddk_profile_read', 'ddk_debug_set_tc', 'ddk_edge_total', 'ddk_segment_total', 'ddk_group_totals']
+           'ddk_profile_enable', 'ddk_profile_read', 'ddk_debug_set_tc', 'ddk_host_tcr_roles_check', 'ddk_host_tc_split_rn', 'ddk_edge_total', 'ddk_segment_total', 'ddk_group_totals']
 
 
 def load_library(path: Optional[str] = None):
@@ -100,9 +100,10 @@ def load_library(path: Optional[str] = None):
     return lib
 
 
-def set_tensor_core_path(on: Optional[bool]) -> int:
-    """Run-time switch of the tcgen05 accumulation path (None: follow DDK_TC); effective from the next ``set_batch``."""
-    return int(load_library().ddk_debug_set_tc(-1 if on is None else int(bool(on))))
+def set_tensor_core_path(mode) -> int:
+    """Run-time choice of the conv kernels (None: follow DDK_TC; 0 FFMA2 only, 1 FFMA2 + k_acc_tc, 2 k_conv_tcr); effective
+    from the next ``set_batch``."""
+    return int(load_library().ddk_debug_set_tc(-1 if mode is None else int(mode)))
 
 
 def _ptr(t: Optional[torch.Tensor]):

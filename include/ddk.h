@@ -191,9 +191,11 @@ int ddk_group_totals(DdkCtx* ctx, int64_t* edges, int64_t* segments);   /* cumul
                                                           list ([DDK_WORK_LISTS] each): edge groups 0 lig-lig, 1 lig<-rec, 2 rec-rec,
                                                           3 rec<-lig, and 4 + h = group 2 restricted to the residues within h
                                                           receptor-contact hops of a residue with a cross edge; all steps (sync) */
-/* Process-wide run-time switch of the tensor-core accumulation path (same meaning as the DDK_TC environment variable: 1 on, 0 off,
- * -1 follow the environment again); takes effect at the next ddk_set_batch.  Returns the previous override.  Parity tests run
- * every trajectory both ways. */
+/* Process-wide run-time choice of the conv-layer kernels (same meaning as the DDK_TC environment variable): 2 = k_conv_tcr, every
+ * outer-product accumulation as 3xTF32 tcgen05.mma with the contraction from tensor memory (default); 1 = the round-1 pair
+ * k_conv_fused (FFMA2) + k_acc_tc (long lig<-rec segments on the tensor cores); 0 = k_conv_fused only (all fp32 FMA: the
+ * strictest rounding, for ill-conditioned trajectories); -1 = follow the environment again.  Takes effect at the next
+ * ddk_set_batch.  Returns the previous override.  Parity tests run the trajectories in every mode. */
 int ddk_debug_set_tc(int32_t on);
 int ddk_debug_read(DdkCtx* ctx, const char* name, void* dst_h, size_t max_bytes, size_t* n_bytes);
 
@@ -225,6 +227,15 @@ int ddk_host_tc_rows_eval(int32_t lv, const float* x84_h, const float* sh4_h, fl
 /* Host build of the TF32 split of k_acc_tc's operands (3xTF32 product hi*hi + hi*lo + lo*hi): for every a[i], hi[i] = a rounded to
  * the TF32 grid (13 low mantissa bits zero) and lo[i] = a - hi[i] (exact in fp32), both as raw fp32 bit patterns. */
 int ddk_host_tc_split(const float* a_h, int32_t n, uint32_t* hi_h, uint32_t* lo_h);
+
+/* Host self check of k_conv_tcr's role tables (callable without a GPU): at every basis level each (basis row, hidden unit) pair and
+ * each (basis row, bias) pair is owned by exactly one role, the per-role weight slices reproduce the packed second-layer weights
+ * (models/tensor_layers.py:154-156 re-associated, disco_diffdock_b200/weights.py) and every shape fits the kernel's tensor-memory /
+ * shared-memory budgets.  Returns 0, or 1 + the first failing level. */
+int ddk_host_tcr_roles_check(void);
+
+/* Host build of k_conv_tcr's operand split: hi and lo both on the TF32 grid, |a - hi - lo| <= 2^-22 |a|. */
+int ddk_host_tc_split_rn(const float* a_h, int32_t n, uint32_t* hi_h, uint32_t* lo_h);
 
 #ifdef __cplusplus
 }

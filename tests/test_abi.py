@@ -137,3 +137,25 @@ def test_tf32_split_is_exact(lib):
     assert np.array_equal(h + l, a)                                        # exact in fp32
     assert (np.abs(l.astype(np.float64)) <= np.abs(a.astype(np.float64)) * 2.0 ** -11 * (1 + 2.0 ** -10) + 1e-45).all()
     assert np.array_equal(np.signbit(h[np.abs(a) > 0]), np.signbit(a[np.abs(a) > 0]))
+
+
+def test_tensor_core_role_tables(lib):
+    """k_conv_tcr: at every basis level each (basis row, hidden unit) and (basis row, bias) pair belongs to exactly one role, the
+    resident weight slices reproduce the packed second-layer weights, and the shapes fit tensor memory / shared memory."""
+    lib.ddk_host_tcr_roles_check.restype = ctypes.c_int
+    assert lib.ddk_host_tcr_roles_check() == 0
+
+
+def test_tf32_split_rounded_lo(lib):
+    """k_conv_tcr's operand split: hi and lo both on the TF32 grid (nothing is left to the tensor core's truncation),
+    |a - hi - lo| <= 2^-22 |a|."""
+    lib.ddk_host_tc_split_rn.restype = ctypes.c_int
+    lib.ddk_host_tc_split_rn.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]
+    rng = np.random.default_rng(1)
+    a = np.concatenate([rng.standard_normal(4096) * 10.0 ** rng.integers(-6, 6, 4096), [0.0, -0.0, 1.0, -1.0, 1.0 + 2.0 ** -11,
+                        1.0 + 2.0 ** -12, 1.0 + 2.0 ** -23, 1e-30, -7.25]]).astype(np.float32)
+    hi, lo = np.zeros(a.size, np.uint32), np.zeros(a.size, np.uint32)
+    assert lib.ddk_host_tc_split_rn(a.ctypes.data, a.size, hi.ctypes.data, lo.ctypes.data) == 0
+    assert not (hi & 0x1fff).any() and not (lo & 0x1fff).any()
+    h, l = hi.view(np.float32).astype(np.float64), lo.view(np.float32).astype(np.float64)
+    assert (np.abs(a.astype(np.float64) - h - l) <= np.abs(a.astype(np.float64)) * 2.0 ** -22 + 1e-45).all()

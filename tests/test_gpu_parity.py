@@ -39,8 +39,9 @@ def _need_cuda():
 
 
 def rel_err(a, b):
+    """max |a - b| relative to the largest reference entry of the tensor (no absolute floor)."""
     a, b = a.detach().cpu().double(), b.detach().cpu().double()
-    return float((a - b).abs().max() / max(1.0, float(b.abs().max())))
+    return float((a - b).abs().max() / max(1e-30, float(b.abs().max())))
 
 
 def oracle_forward(sd, cfg, batch):
@@ -204,6 +205,34 @@ def test_update_matches_oracle():
     rmsd = helpers.rmsd_per_pose(want, got.cpu(), B)
     dump('update', {'rmsd': rmsd.tolist()})
     assert float(rmsd.max()) < 2e-5, rmsd
+
+
+@pytest.mark.parametrize('mode', [0, 1, 2])
+def test_conv_kernel_paths_match_reference_golden(mode):
+    """The three conv-kernel choices (DDK_TC = 0 FFMA2 only, 1 FFMA2 + k_acc_tc, 2 k_conv_tcr) against the same reference
+    vectors: config-1 forward (node features, scores) and an 8-step sampling run."""
+    from disco_diffdock_b200 import engine as dengine
+    dengine.set_tensor_core_path(mode)
+    try:
+        z = np.load(os.path.join(GOLD, 'forward_cfg1.npz'))
+        m, sd, cfg, batch = make_golden.forward_inputs(make_golden.CASES['forward_cfg1'])
+        m = m.to('cuda')
+        tr, rot, tor = m(batch)
+        lig_h, rec_h = m.embed(batch)[:2]
+        d = {'tr': rel_err(tr, torch.from_numpy(z['tr'])), 'rot': rel_err(rot, torch.from_numpy(z['rot'])),
+             'tor': rel_err(tor, torch.from_numpy(z['tor'])),
+             'lig_h': float((lig_h.cpu() - torch.from_numpy(z['lig_h'])).abs().max()),
+             'rec_h': float((rec_h.cpu() - torch.from_numpy(z['rec_h'])).abs().max())}
+        c = make_golden.CASES['sample_small']
+        zs = np.load(os.path.join(GOLD, 'sample_small.npz'))
+        m2, sd2, cfg2, lst, noise, sched, temps = make_golden.sample_inputs(c)
+        pos = run_gpu_sampling(m2.to('cuda'), cfg2, lst, sched, noise, c['steps'], temps, c['B'])
+        d['sample_small_rmsd'] = helpers.rmsd_per_pose(torch.from_numpy(zs['pos']), pos, c['B']).tolist()
+        dump(f'conv_path_{mode}', d)
+        assert max(d['tr'], d['rot'], d['tor']) < 2e-5 and max(d['lig_h'], d['rec_h']) < 3e-5, d
+        assert max(d['sample_small_rmsd']) < 1e-3, d
+    finally:
+        dengine.set_tensor_core_path(None)
 
 
 def run_gpu_sampling(m, cfg, lst, sched, noise, steps, temps, B, host_buffers=False):

@@ -52,11 +52,11 @@ def vec_rel(got, want):
 
 
 @pytest.mark.parametrize('name', ['pre_forward', 'pre_forward_disco'])
-@pytest.mark.parametrize('tc', [1, 0])
+@pytest.mark.parametrize('tc', [2, 1, 0])
 def test_pretrained_forward_matches_reference(name, tc):
     c = helpers.PRE_CASES[name]
     z = np.load(os.path.join(GOLD, name + '.npz'))
-    dengine.set_tensor_core_path(bool(tc))
+    dengine.set_tensor_core_path(tc)
     m, sd, cfg = helpers.make_checkpoint_model(c['ckpt'])
     m = m.to('cuda')
     d = {}
@@ -79,7 +79,7 @@ def test_pretrained_forward_matches_reference(name, tc):
 def _traj_setup(name, tc):
     c = helpers.PRE_CASES[name]
     z = np.load(os.path.join(GOLD, name + '.npz'))
-    dengine.set_tensor_core_path(bool(tc))
+    dengine.set_tensor_core_path(tc)
     m, sd, cfg = helpers.make_checkpoint_model(c['ckpt'])
     m = m.to('cuda')
     g, lst, noise, sched, kw = helpers.pre_traj_inputs(c)
@@ -89,7 +89,7 @@ def _traj_setup(name, tc):
 
 
 @pytest.mark.parametrize('name', ['pre_traj_ode', 'pre_traj_temps'])
-@pytest.mark.parametrize('tc', [1, 0])
+@pytest.mark.parametrize('tc', [2, 1, 0])
 def test_pretrained_teacher_forced_steps(name, tc):
     """Every reverse step from the reference's own pose: scores (truly relative) and the pose after one step."""
     c, z, m, cfg, g, lst, noise, sched, kw = _traj_setup(name, tc)
@@ -118,7 +118,7 @@ def test_pretrained_teacher_forced_steps(name, tc):
     assert worst['step_rmsd'] < 1e-4, worst
 
 
-@pytest.mark.parametrize('tc', [1, 0])
+@pytest.mark.parametrize('tc', [2, 1, 0])
 def test_pretrained_free_running_ode_trajectory(tc):
     """20 reverse steps through the drop-in sampling() with the shipped DiffDock-S weights vs the reference's sampling()."""
     name = 'pre_traj_ode'

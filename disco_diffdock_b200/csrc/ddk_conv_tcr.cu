@@ -40,13 +40,13 @@
 
 namespace ddk {
 
-constexpr int TR_NST = 3;            // operand stages (A in tensor memory, B in shared memory)
-constexpr int TR_XR = 6;             // staging ring of the gather warps
-constexpr int TR_GW = 2;             // gather warps
-constexpr int TR_ROWW = 4;           // row warps = one 128-row tile
+constexpr int TR_NSETS = 3;          // row-warp sets: set s produces the operands of chunks it = s (mod 3) -- three chunks in flight
+constexpr int TR_NST = TR_NSETS;     // operand stages (A in tensor memory, B in shared memory): one per set
+constexpr int TR_XR = 6;             // staging ring of the gather warp
+constexpr int TR_ROWW = 4;           // row warps per set = one 128-row tile
 constexpr int TR_CONW = 8;           // contraction warps
-constexpr int TR_THREADS = (TR_ROWW + 1 + TR_GW + TR_CONW) * 32;   // 480
-constexpr int TR_W_MMA = TR_ROWW, TR_W_GATHER = TR_ROWW + 1, TR_W_CON = TR_ROWW + 1 + TR_GW;
+constexpr int TR_W_MMA = TR_NSETS * TR_ROWW, TR_W_GATHER = TR_W_MMA + 1, TR_W_CON = TR_W_MMA + 4;   // warps 12 | 13 | 16..23
+constexpr int TR_THREADS = (TR_W_CON + TR_CONW) * 32;   // 768 (warps 14, 15 idle: the contraction warps start at a multiple of 4)
 constexpr int TR_COLS = 512;         // tensor-memory columns allocated
 constexpr int TR_ACOL = 448;         // A operand stages: TR_NST x (8 hi + 8 lo) columns from here; accumulator slots below
 constexpr int TR_NMAX = 80;          // widest MMA N
@@ -65,7 +65,7 @@ struct TrArgs {
   int* counters;                     // [4 * nroles] segment cursor of each combo
   const int2* seg_list;
   const float* x;                    // [N][84] layer input
-  const float* hs; size_t LT;        // [72 / J][LT][J] hidden units of every listed edge (k_edge_hidden)
+  const float* hs;                   // [list position][72] hidden units of every listed edge (k_edge_hidden, edge-major)
   const float4* sh_pool;
   const TcrRole* roles; int nroles;  // roles of the level
   const float* W[4][TCR_MAXROLES];   // resident weight slice of (group, role)
@@ -82,9 +82,9 @@ template <int LV>
 struct TrSmem {
   alignas(128) uint32_t Bhi[TR_NST][TR_NMAX * 8];
   alignas(128) uint32_t Blo[TR_NST][TR_NMAX * 8];
-  alignas(16) float X[TR_XR][KC3][TrCfg<LV>::DINP];
+  alignas(16) float X[TR_XR][KC3][TrCfg<LV>::DINP];                     // destination feature rows of the chunk's edges
   alignas(16) float SH[TR_XR][KC3][4];
-  alignas(16) float HS[TR_XR][TrCfg<LV>::NSL][KC3 * TrCfg<LV>::J + 8];
+  alignas(16) float HS[TR_XR][KC3][HID];                                // the role's hidden units of each edge (first nj floats)
   alignas(16) float RED[TR_RED_FLOATS];
   alignas(16) float RED2[2][TR_RED2];
   alignas(16) TcrRole role;                                             // the resident role's tables
@@ -116,6 +116,11 @@ __device__ __forceinline__ void tr_ld8(uint32_t taddr, uint32_t (&v)[8]) {
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr));
 }
 
+__device__ __forceinline__ void tr_ld4(uint32_t taddr, uint32_t (&v)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr));
+}
+
 // ---------------------------------------------------------------------------------------------- contraction warps
 // One group of G segments (slots sg .. sg + G - 1; nvalid of them real).  VEC: lane = basis row (class, component c, row f of the
 // class) with the three components in neighbouring lanes, so the 6 weights of (f, j) are one broadcast 8-byte load per pair;
@@ -125,59 +130,55 @@ __device__ __forceinline__ void tr_con_group(const TrArgs& p, TrSmem<LV>& S, con
                                              const int sg, const int nvalid, const int seg0, const int g_edge, const int role_id,
                                              const int cw, const int q, const int lane, const int ct, const int gi) {
   constexpr int G = VEC ? TR_GV : TR_GS, NACC = 2 * G;
-  constexpr int O = VEC ? 6 : 24, OT = VEC ? 6 : 12;          // outputs per row; outputs per thread
-  constexpr int NP2 = OT / 2;
+  constexpr int O = VEC ? 6 : 24;                              // outputs per basis row; every thread computes 6 of them
   const TcrRole& R = S.role;
   const int N = R.N, ncol = R.ncol;
   const int set = cw >> 2;                                    // warp set 0 / 1
-  const int prow = 32 * q + lane;
-  const bool active = prow < R.nrows && (VEC || true);
-  // columns [c0, c1) and first output of this thread
+  // VEC: lane = basis row, the two warp sets split the columns.  Scalar roles: every row sits in lanes l and l + 16 of its
+  // quarter (the accumulator rows are duplicated by the row warps), and (warp set, lane half) selects 6 of its 24 outputs.
+  const int rrow = VEC ? 32 * q + lane : 16 * q + (lane & 15);          // row index in RED / in the role's row groups
+  const bool active = VEC ? rrow < R.nrows : rrow < R.ndist;
   int c0 = 0, c1 = ncol, o0 = 0;
-  if (VEC) { c0 = set ? 40 : 0; c1 = set ? ncol : min(40, ncol); } else { o0 = 12 * set; }
+  if (VEC) { c0 = set ? 40 : 0; c1 = set ? ncol : min(40, ncol); } else { o0 = 12 * set + 6 * (lane >> 4); }
 #pragma unroll
   for (int g = 0; g < G; ++g) {
     const int s = sg + g, slot = s % NACC;
     tc_mbar_wait_sleep(&S.accfull[slot], (s / NACC) & 1);
   }
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  tr_f32x2 acc[G][NP2];
+  tr_f32x2 acc[G][3];
 #pragma unroll
   for (int g = 0; g < G; ++g)
 #pragma unroll
-    for (int k = 0; k < NP2; ++k) acc[g][k] = 0ull;
-  const float* wrow = Wsl + (active ? R.woff[prow] : 0) + o0;
+    for (int k = 0; k < 3; ++k) acc[g][k] = 0ull;
+  const float* wrow = Wsl + (active ? R.woff[32 * q + lane] : 0) + o0;
   const uint32_t tlane = tmem + ((uint32_t)(32 * q) << 16);
-  for (int cb = c0 & ~7; cb < c1; cb += 8) {
-    uint32_t v[G][8];
+  constexpr int CW = VEC ? 8 : 4;                            // accumulator columns per load (4 segments x 4 in scalar roles)
+  for (int cb = c0; cb < c1; cb += CW) {
+    uint32_t v[G][CW];
 #pragma unroll
     for (int g = 0; g < G; ++g)
-      if (g < nvalid) tr_ld8(tlane + ((sg + g) % NACC) * N + cb, v[g]);
+      if (g < nvalid) {
+        if constexpr (VEC) tr_ld8(tlane + ((sg + g) % NACC) * N + cb, v[g]);
+        else tr_ld4(tlane + ((sg + g) % NACC) * N + cb, v[g]);
+      }
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
     if (active) {
 #pragma unroll
-      for (int jj = 0; jj < 8; ++jj) {
+      for (int jj = 0; jj < CW; ++jj) {
         const int col = cb + jj;
-        if (col >= c0 && col < c1) {
+        if (col < c1) {
           const float* w = wrow + col * O;
-          tr_f32x2 wv[NP2];
-          if (VEC) {
+          tr_f32x2 wv[3];
 #pragma unroll
-            for (int k = 0; k < NP2; ++k) wv[k] = *reinterpret_cast<const tr_f32x2*>(w + 2 * k);
-          } else {
-#pragma unroll
-            for (int k = 0; k < NP2 / 2; ++k) {
-              const float4 t4 = *reinterpret_cast<const float4*>(w + 4 * k);
-              wv[2 * k] = tr_pack2(t4.x, t4.y); wv[2 * k + 1] = tr_pack2(t4.z, t4.w);
-            }
-          }
+          for (int k = 0; k < 3; ++k) wv[k] = *reinterpret_cast<const tr_f32x2*>(w + 2 * k);
 #pragma unroll
           for (int g = 0; g < G; ++g)
             if (g < nvalid) {
               const float a = __uint_as_float(v[g][jj]);
               const tr_f32x2 aa = tr_pack2(a, a);
 #pragma unroll
-              for (int k = 0; k < NP2; ++k) tr_ffma2(acc[g][k], aa, wv[k]);
+              for (int k = 0; k < 3; ++k) tr_ffma2(acc[g][k], aa, wv[k]);
             }
         }
       }
@@ -196,9 +197,9 @@ __device__ __forceinline__ void tr_con_group(const TrArgs& p, TrSmem<LV>& S, con
 #pragma unroll
     for (int g = 0; g < G; ++g)
       if (g < nvalid) {
-        float* r = &S.RED[(((g * H) + (VEC ? set : 0)) * RR + prow) * O + o0];
+        float* r = &S.RED[(((g * H) + (VEC ? set : 0)) * RR + rrow) * O + o0];
 #pragma unroll
-        for (int k = 0; k < NP2; ++k) {
+        for (int k = 0; k < 3; ++k) {
           float a0, a1;
           tr_unpack2(acc[g][k], a0, a1);
           r[2 * k] = a0; r[2 * k + 1] = a1;
@@ -247,7 +248,7 @@ __device__ __forceinline__ void tr_con_group(const TrArgs& p, TrSmem<LV>& S, con
 template <int LV>
 __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constant__ TrArgs p) {
   using Cfg = TrCfg<LV>;
-  constexpr int DINP = Cfg::DINP, XQ = Cfg::XQ, J = Cfg::J;
+  constexpr int DINP = Cfg::DINP;
   extern __shared__ __align__(128) unsigned char tr_raw[];
   TrSmem<LV>& S = *reinterpret_cast<TrSmem<LV>*>(tr_raw);
   float* const Wsl = &S.Wsl[0];
@@ -261,31 +262,31 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
   }
   if (tid == TR_W_MMA * 32) {
     for (int s = 0; s < TR_NST; ++s) { tc_mbar_init(&S.full[s], TR_ROWW); tc_mbar_init(&S.empty[s], 1); }
-    for (int s = 0; s < TR_XR; ++s) { tc_mbar_init(&S.sfull[s], 32 * TR_GW); tc_mbar_init(&S.sempty[s], TR_ROWW); }
+    for (int s = 0; s < TR_XR; ++s) { tc_mbar_init(&S.sfull[s], 1); tc_mbar_init(&S.sempty[s], TR_ROWW); }
     for (int s = 0; s < TCR_MAXACC; ++s) { tc_mbar_init(&S.accfull[s], 1); tc_mbar_init(&S.accempty[s], TR_CONW); }
     tc_mbar_init(&S.bar_w, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     // first combo of this CTA: the combos share the CTAs in proportion to a rough cost model (per listed edge and per segment,
     // vector roles about twice the scalar ones), so few CTAs have to migrate -- and reload a weight slice -- before the tail
-    float cost[4 * TCR_MAXROLES], total = 0.f;
-    for (int cmb = 0; cmb < ncombo; ++cmb) {
+    auto combo_cost = [&](int cmb) {
       const int g = cmb / p.nroles, r = cmb % p.nroles;
-      float c = 0.f;
-      if ((p.gmask >> g) & 1) {
-        const float ne = (float)p.gedges[p.gci[g]], ns = (float)p.gcnt[p.gci[g]];
-        c = p.roles[r].isS ? ne * 10.f + ns * 400.f : ne * 18.f + ns * 500.f;
-      }
-      cost[cmb] = c; total += c;
-    }
+      if (!((p.gmask >> g) & 1)) return 0.f;
+      const float ne = (float)p.gedges[p.gci[g]], ns = (float)p.gcnt[p.gci[g]];
+      return p.roles[r].isS ? ne * 10.f + ns * 400.f : ne * 18.f + ns * 500.f;
+    };
+    float total = 0.f;
+    for (int cmb = 0; cmb < ncombo; ++cmb) total += combo_cost(cmb);
     const float pos = ((float)blockIdx.x + 0.5f) / (float)gridDim.x * total;
     int first = 0;
     float run = 0.f;
-    for (int cmb = 0; cmb < ncombo; ++cmb) { run += cost[cmb]; first = cmb; if (run > pos) break; }
+    for (int cmb = 0; cmb < ncombo; ++cmb) { run += combo_cost(cmb); first = cmb; if (run > pos) break; }
     S.task[5] = first; S.task[6] = -1;
   }
   {
+    // operand tiles and staging rings start as zeros: the bulk copies of a partial chunk leave the rows of absent edges as they
+    // are (their hidden units are masked to 0 in the B operand, so whatever FINITE values they hold contribute nothing)
     uint32_t* z = &S.Bhi[0][0];
-    constexpr int nz = 2 * TR_NST * TR_NMAX * 8;
+    constexpr int nz = (int)((offsetof(TrSmem<LV>, RED) - offsetof(TrSmem<LV>, Bhi)) / 4);
     for (int i = tid; i < nz; i += TR_THREADS) z[i] = 0u;
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -357,14 +358,16 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
       __syncthreads();
     }
     const TcrRole& R = S.role;
-    const int N = R.N, nj = R.nj, j0 = R.j0, sl0 = R.sl0, nsl = R.nsl;
+    const int N = R.N, nj = R.nj, j0 = R.j0;
     const bool vec = !R.isS;
     const int G = vec ? TR_GV : TR_GS, NACC = 2 * G;
     const int4* wl = p.glist + p.goff[g] + idx0;
 
-    if (warp < TR_ROWW) {
+    if (warp < TR_W_MMA) {
       // ================================================================== row warps: A operand -> tensor memory, B -> smem
-      const TcRow rd = R.rows[tid];
+      // set = warp / 4 produces the chunks it = set (mod TR_NSETS) into operand stage `set`; thread (quarter, lane) = tile row
+      const int set = warp >> 2, rt = (warp & 3) * 32 + lane;
+      const TcRow rd = R.rows[rt];
       const bool plain = __all_sync(0xffffffffu, rd.type == 0);
       const int i1 = rd.type == 0 ? rd.i0 : rd.i0 + 1, i2 = rd.type == 0 ? rd.i0 : rd.i0 + 2;
       const float w_t0 = rd.type == 0 ? 1.f : 0.f, w_dt = rd.type == 1 ? 1.f : 0.f;
@@ -375,7 +378,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
       int bn[2], bh[2];
 #pragma unroll
       for (int b2 = 0; b2 < 2; ++b2) {
-        const int w = tid + 128 * b2;
+        const int w = rt + 128 * b2;
         bn[b2] = w < nb_items ? w % (nj + 1) : -1;
         bh[b2] = w < nb_items ? w / (nj + 1) : 0;
       }
@@ -383,8 +386,9 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
         const int n = load_seg_entry(wl + i).y;
         const int nch = (n + KC3 - 1) / KC3;
         for (int c = 0; c < nch; ++c, ++it) {
+          if (it % TR_NSETS != set) continue;
           const int kc = min(KC3, n - c * KC3);
-          const int buf = it % TR_XR, stage = it % TR_NST;
+          const int buf = it % TR_XR, stage = set;
           tc_mbar_wait(&S.sfull[buf], (it / TR_XR) & 1);
           tc_mbar_wait(&S.empty[stage], ((it / TR_NST) & 1) ^ 1);
           float b[KC3];
@@ -409,7 +413,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
             uint32_t hi[KC3], lo[KC3];
 #pragma unroll
             for (int e = 0; e < KC3; ++e) tc_split_rn(b[e], hi[e], lo[e]);
-            const uint32_t ta = tmem + ((uint32_t)(32 * warp) << 16) + TR_ACOL + stage * 16;
+            const uint32_t ta = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + TR_ACOL + stage * 16;
             asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                          ::"r"(ta), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]), "r"(hi[4]), "r"(hi[5]), "r"(hi[6]), "r"(hi[7]) : "memory");
             asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
@@ -421,11 +425,10 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
             if (nrow >= 0) {
               uint32_t h[4], l[4];
               if (nrow < nj) {
-                const int hj = j0 + nrow, sl = hj / J - sl0, jj = hj % J;
 #pragma unroll
                 for (int qd = 0; qd < 4; ++qd) {
-                  const float hld = S.HS[buf][sl][(4 * hk + qd) * J + jj];
-                  tc_split_rn(4 * hk + qd < kc ? hld : 0.f, h[qd], l[qd]);      // padded edges hold a copy of the last edge
+                  const float hld = S.HS[buf][4 * hk + qd][nrow];
+                  tc_split_rn(4 * hk + qd < kc ? hld : 0.f, h[qd], l[qd]);      // rows of absent edges hold stale (finite) data
                 }
               } else {                                                           // the ones row -> Bsum
 #pragma unroll
@@ -474,50 +477,37 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
           tc_mbar_arrive(&S.accfull[slot]);
         }
       }
-    } else if (warp < TR_W_CON) {
-      // ================================================================== gather warps: global -> staging ring (cp.async only)
-      const int gw = warp - TR_W_GATHER;               // 0: feature rows + harmonics, 1: hidden units of the role
+    } else if (warp == TR_W_GATHER) {
+      // ================================================================== gather warp: global -> staging ring, bulk copies
+      // lane (kind = lane / 8, e = lane % 8) moves one contiguous piece of edge e: its destination feature row, its harmonics
+      // record, or the role's hidden units; the copies complete on the ring slot's mbarrier (complete_tx)
+      const int e = lane & 7, kind = lane >> 3;
+      const uint32_t xbytes = DINP * 4, hbytes = (uint32_t)nj * 4;
       for (int i = 0; i < nseg; ++i) {
         const int4 ge = load_seg_entry(wl + i);
         const int n = ge.y, base = ge.z;
         const int nch = (n + KC3 - 1) / KC3;
         int2 ent_next = make_int2(0, 0);
-        if (gw == 0 && lane < KC3) ent_next = p.seg_list[base + min(lane, n - 1)];
+        if (lane < KC3) ent_next = p.seg_list[base + min(lane, n - 1)];
         for (int c = 0; c < nch; ++c, ++it) {
           const int kc = min(KC3, n - c * KC3), pos0 = base + c * KC3;
           const int buf = it % TR_XR;
           const int2 ent = ent_next;
-          if (gw == 0 && lane < KC3 && c + 1 < nch) ent_next = p.seg_list[pos0 + KC3 + min(lane, n - (c + 1) * KC3 - 1)];
+          if (lane < KC3 && c + 1 < nch) ent_next = p.seg_list[pos0 + KC3 + min(lane, n - (c + 1) * KC3 - 1)];
+          const int slot = __shfl_sync(0xffffffffu, ent.x, e), dst = __shfl_sync(0xffffffffu, ent.y, e);
           tc_mbar_wait(&S.sempty[buf], ((it / TR_XR) & 1) ^ 1);
-          if (gw == 0) {
-            constexpr int NP = KC3 * XQ + KC3;            // 16-byte pieces: feature rows, then one harmonics record per edge
-#pragma unroll
-            for (int k = 0; k < (NP + 31) / 32; ++k) {    // uniform trip count: the shuffles need the whole warp
-              const int q0 = lane + 32 * k;
-              const bool on = q0 < NP, isx = q0 < KC3 * XQ;
-              const int e = !on ? 0 : (isx ? q0 / XQ : q0 - KC3 * XQ), qq = isx ? q0 % XQ : 0;
-              const int es = min(e, kc - 1);
-              const int slot = __shfl_sync(0xffffffffu, ent.x, es), dst = __shfl_sync(0xffffffffu, ent.y, es);
-              if (on) {
-                if (isx) __pipeline_memcpy_async(&S.X[buf][e][4 * qq], p.x + (size_t)dst * D + 4 * qq, 16);
-                else __pipeline_memcpy_async(&S.SH[buf][e][0], p.sh_pool + slot, 16);
-              }
-            }
-          } else {
-            constexpr int PJ = J / 4;                     // 16-byte pieces per (slice, edge)
-            for (int q0 = lane; q0 < nsl * KC3 * PJ; q0 += 32) {
-              const int r = q0 / (KC3 * PJ), e = (q0 / PJ) % KC3, qq = q0 % PJ;
-              const int es = min(e, kc - 1);
-              __pipeline_memcpy_async(&S.HS[buf][r][e * J + 4 * qq], p.hs + ((size_t)(sl0 + r) * p.LT + pos0 + es) * J + 4 * qq, 16);
-            }
+          if (lane == 0) tc_mbar_expect_tx(&S.sfull[buf], (uint32_t)kc * (xbytes + 16u + hbytes));
+          __syncwarp();
+          if (e < kc) {
+            if (kind == 0) tc_bulk_g2s(&S.X[buf][e][0], p.x + (size_t)dst * D, xbytes, &S.sfull[buf]);
+            else if (kind == 1) tc_bulk_g2s(&S.SH[buf][e][0], p.sh_pool + slot, 16u, &S.sfull[buf]);
+            else if (kind == 2) tc_bulk_g2s(&S.HS[buf][e][0], p.hs + (size_t)(pos0 + e) * HID + j0, hbytes, &S.sfull[buf]);
           }
-          asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tc_smem(&S.sfull[buf])) : "memory");
         }
       }
-      asm volatile("cp.async.wait_all;" ::: "memory");
-    } else {
+    } else if (warp >= TR_W_CON) {
       // ================================================================== contraction warps
-      const int cw = warp - TR_W_CON, q = warp & 3, ct = cw * 32 + lane;
+      const int cw = warp - TR_W_CON, q = warp & 3, ct = cw * 32 + lane;    // TR_W_CON is a multiple of 4: q = cw & 3
       const int ngroups = (nseg + G - 1) / G;
       for (int grp = 0; grp < ngroups; ++grp, sg += G, ++gcount) {
         const int nvalid = min(G, nseg - grp * G);
@@ -571,12 +561,16 @@ int build_tcr_roles(int lv, const LayerInfo& li, TcrRole* roles) {
     R.isS = sp.isS; R.j0 = sp.j0; R.nj = sp.nj; R.ncol = sp.nj + 1; R.N = tcr_ncols16(R.ncol);
     if (sp.j0 % J || sp.nj % J) return -1;
     R.sl0 = sp.j0 / J; R.nsl = sp.nj / J;
+    if ((sp.j0 * 4) % 16 || (sp.nj * 4) % 16) return -1;   // bulk copies of the role's hidden units
     R.O = sp.isS ? 24 : 6;
-    // weight block of one (class, f): ncol x O floats, padded so that consecutive blocks start in different bank groups
+    // weight block of one (class, f): ncol x O floats; the stride between blocks is = 2 (mod 4) floats, i.e. an odd number of
+    // 8-byte words, so that the 8-byte loads of lanes working on different blocks fall into different banks
     const int blk = R.ncol * R.O;
-    R.wstride = sp.isS ? ((blk + 3) / 4 * 4 + (((blk + 3) / 4) % 2 == 0 ? 4 : 0)) : (blk % 4 == 2 ? blk : blk + 2);
-    // rows: type-sorted (plain products first); in vector roles the three components of (class, f) in neighbouring lanes
-    int n = 0, wblocks = 0;
+    R.wstride = blk % 4 == 2 ? blk : blk + 2;
+    // distinct rows: type-sorted (plain products first); in vector roles the three components of (class, f) in neighbouring lanes
+    int nd = 0, wblocks = 0;
+    std::vector<TcRow> drow(128);
+    std::vector<int> dwoff(128, 0);
     std::vector<int> blk_of((size_t)li.ncls * 64, -1);
     for (int k : sp.cls) for (int f = 0; f < li.cls[k].F; ++f) blk_of[(size_t)k * 64 + f] = wblocks++;
     for (int pass = 0; pass < 3; ++pass)
@@ -585,21 +579,34 @@ int build_tcr_roles(int lv, const LayerInfo& li, TcrRole* roles) {
         for (int f = 0; f < ci.F; ++f) {
           if (byu[ci.uoff + f].type != pass) continue;
           for (int c = 0; c < ci.ncomp; ++c) {
-            if (n >= 128) return -1;
+            if (nd >= 128) return -1;
             const int u = ci.uoff + c * ci.F + f;
             if (byu[u].type != pass) return -1;            // the components of a row share its type
-            R.rows[n] = byu[u];
-            R.woff[n] = blk_of[(size_t)k * 64 + f] * R.wstride;
-            ++n;
+            drow[nd] = byu[u];
+            dwoff[nd] = blk_of[(size_t)k * 64 + f] * R.wstride;
+            ++nd;
           }
         }
       }
-    R.nrows = n;
-    if (sp.isS && n > 64) return -1;
-    for (int i = n; i < 128; ++i) { R.rows[i] = TcRow{0, 0, 0, -1}; R.woff[i] = 0; }
+    R.ndist = nd;
+    for (int i = 0; i < 128; ++i) { R.rows[i] = TcRow{0, 0, 0, -1}; R.woff[i] = 0; }
+    if (sp.isS) {
+      // scalar roles: distinct row d = 16 q + l sits in lanes l and l + 16 of quarter q (tile rows 32 q + l and 32 q + 16 + l): the
+      // two copies of its accumulator row let (warp set, lane half) split its 24 outputs four ways without any shuffle
+      if (nd > 64) return -1;
+      for (int d = 0; d < nd; ++d)
+        for (int h = 0; h < 2; ++h) {
+          const int lane_row = 32 * (d / 16) + 16 * h + (d % 16);
+          R.rows[lane_row] = drow[d]; R.woff[lane_row] = dwoff[d];
+        }
+      R.nrows = 128;
+    } else {
+      for (int d = 0; d < nd; ++d) { R.rows[d] = drow[d]; R.woff[d] = dwoff[d]; }
+      R.nrows = nd;
+    }
     R.wfloats = (wblocks * R.wstride + 3) / 4 * 4;
     if (R.wfloats > TCR_WMAX) return -1;
-    // row groups (class, component) and the output columns they feed
+    // row groups (class, component) and the output columns they feed; rgrow = index of the row in RED (distinct-row index)
     for (int f = 0; f < D; ++f) R.outsrc[f] = -1;
     int nrg = 0;
     for (int k : sp.cls) {
@@ -611,7 +618,7 @@ int build_tcr_roles(int lv, const LayerInfo& li, TcrRole* roles) {
         for (int f = 0; f < ci.F; ++f) {
           const int u = ci.uoff + c * ci.F + f;
           int pos = -1;
-          for (int i = 0; i < n; ++i) if (R.rows[i].u == u) pos = i;
+          for (int i = 0; i < nd; ++i) if (drow[i].u == u) pos = i;
           if (pos < 0) return -1;
           R.rgrow[nrg][f] = (short)pos;
         }
@@ -635,6 +642,7 @@ void build_tcr_weights(const LayerInfo& li, const TcrRole& R, const float* w2p, 
   std::vector<char> done(128, 0);
   for (int i = 0; i < R.nrows; ++i) {
     const int u = R.rows[i].u;
+    if (u < 0) continue;
     int k = 0;
     while (k + 1 < li.ncls && u >= li.cls[k + 1].uoff) ++k;
     const ClassInfo& ci = li.cls[k];
@@ -683,7 +691,7 @@ void launch_conv_tcr(DdkCtx* c, int layer, const float* x_in, float* x_out, cuda
   a.gedges = ptr<int>(c->b_gcnt) + F3_NLIST + 4;
   a.counters = ptr<int>(c->b_counters);
   a.seg_list = ptr<int2>(c->b_seg_list);
-  a.x = x_in; a.hs = ptr<float>(c->b_hs); a.LT = (size_t)c->list_total;
+  a.x = x_in; a.hs = ptr<float>(c->b_hs);
   a.sh_pool = ptr<float4>(c->b_sh_pool);
   a.roles = c->tcr_roles + (size_t)li.lv * TCR_MAXROLES; a.nroles = nroles;
   for (int g = 0; g < 4; ++g)
@@ -739,6 +747,7 @@ int host_tcr_roles_check() {
       build_tcr_weights(li, R, w2p.data(), b2p.data(), sl.data());
       for (int i = 0; i < R.nrows; ++i) {
         const int u = R.rows[i].u;
+        if (u < 0 || (R.isS && (i & 16))) continue;          // padding lanes; the duplicate lanes of scalar roles
         int k = 0;
         while (k + 1 < li.ncls && u >= li.cls[k + 1].uoff) ++k;
         const ClassInfo& ci = li.cls[k];

@@ -153,7 +153,7 @@ void launch_edge_hidden(DdkCtx* c, int layer, cudaStream_t st, int mode) {
   a.proj = ptr<float>(c->b_proj);
   for (int g = 0; g < 4; ++g) a.W1[g] = W(c, conv_id(layer, DDK_WL_W1 + g));
   a.gmask = lig_only ? 0x3 : 0xf;
-  a.hs = ptr<float>(c->b_hs); a.LT = (size_t)c->list_total; a.J = f3_J(c->layers[layer].lv);
+  a.hs = ptr<float>(c->b_hs); a.LT = (size_t)c->list_total; a.J = conv_path() == 2 ? HID : f3_J(c->layers[layer].lv);   // k_conv_tcr reads edge-major records [list position][72]
   const int nsegs = 2 * c->N;
   const int grid = std::min(c->sm_count * 4, std::max(1, nsegs / 8));   // 4 CTAs of 96 threads are resident per SM
   LaunchScope ls(c, PC_HIDDEN, st);

@@ -75,7 +75,7 @@ constexpr int TCR_WMAX = 36240;     // floats of the largest resident weight sli
 constexpr int TCR_MAXRG = 6;        // row groups (class, component) per role
 constexpr int TCR_MAXF = 36;        // rows per row group
 struct alignas(16) TcrRole {
-  int nrows;                        // basis rows of the role (<= 128; scalar roles <= 64)
+  int nrows;                        // tile rows in use (<= 128)
   int ncol;                         // contracted accumulator columns: nj hidden units + the ones column (Bsum)
   int N;                            // MMA N: ncol rounded up to 16
   int j0, nj;                       // hidden units [j0, j0 + nj)
@@ -84,7 +84,8 @@ struct alignas(16) TcrRole {
   int isS;                          // scalar-class role
   int wstride, wfloats;             // floats of one (class, f) weight block incl. padding; floats of the whole slice
   int nrg, np;                      // row groups; reduction parts per output
-  int pad_[3];
+  int ndist;                        // distinct basis rows (scalar roles hold every row twice: tile rows 32 q + l and 32 q + 16 + l)
+  int pad_[2];
   TcRow rows[128];                  // basis row evaluated by row thread p (u = -1: padding)
   int woff[128];                    // offset of row p's weight block inside the slice
   short rgrow[TCR_MAXRG][TCR_MAXF]; // row threads of row group rg

@@ -182,3 +182,116 @@ def load_complex_pack(path: str) -> List[ddata.HeteroData]:
         g.name = str(z[f'{i}/name'])
         out.append(g)
     return out
+
+
+# ---------------------------------------------------------------------------------------------- pose-sharded driver
+def pose_noise(seed: int, ci: int, k: int, steps: int, n_rot: int) -> Dict[str, torch.Tensor]:
+    """The noise stream of pose (complex ci, sample k): keyed by the pose id, not by rank, batch or call order, so a sharded run
+    consumes exactly the z of the unsharded one.  Draw order tr, rot, tor like utils/sampling.py:146-165."""
+    g = torch.Generator().manual_seed(((int(seed) * 1000003 + int(ci)) * 8191 + int(k)) % (2 ** 63 - 1))
+    return {'tr': torch.randn(steps, 3, generator=g), 'rot': torch.randn(steps, 3, generator=g),
+            'tor': torch.randn(steps, n_rot, generator=g)}
+
+
+def seeded_start_poses(complex_graph, ci: int, n: int, seed: int, no_torsion: bool, no_random: bool, tr_sigma_max: float):
+    """evaluate.py:229-233 for one complex with the global numpy / torch generators seeded from (seed, ci) -- every rank that owns
+    a sample of the complex derives the same ``n`` start poses -- and restored afterwards."""
+    np_state, torch_state = np.random.get_state(), torch.random.get_rng_state()
+    try:
+        s = (int(seed) * 7919 + int(ci) * 104729 + 17) % (2 ** 32)
+        np.random.seed(s)
+        torch.manual_seed(s)
+        dl = [copy.deepcopy(complex_graph) for _ in range(n)]
+        randomize_position(dl, no_torsion, no_random, tr_sigma_max)
+        return dl
+    finally:
+        np.random.set_state(np_state)
+        torch.random.set_rng_state(torch_state)
+
+
+def run_inference_sharded(complexes: Sequence, model, model_args, device, t_to_sigma, *, samples_per_complex=40,
+                          inference_steps=20, actual_steps=None, seed=0, rank: Optional[int] = None, world: Optional[int] = None,
+                          poses_per_call=400, no_torsion=None, no_random=False, no_final_step_noise=False, ode=False,
+                          temp_sampling=1.0, temp_psi=0.0, temp_sigma_data=0.5, host_buffers=True, broadcast_weights=True,
+                          gather=True, sampler=None) -> Dict[str, object]:
+    """``samples_per_complex`` poses for every complex, the (complex, sample) poses sharded over the ranks of the process group
+    (one process per GPU; evaluate.py:219-400 is the single-process loop this replaces).  One broadcast of the weights, then no
+    communication until ONE all-gather of the final poses; ranks take contiguous pose ranges balanced by N_l * N_r
+    (``dist.shard_poses``).  Start poses and noise are keyed by (seed, complex, sample), and a pose's trajectory does not depend
+    on what it is batched with (tests), so the result is bit-identical for every world size.
+
+    Returns ``{'names', 'ligand_pos': [per complex: tensor [samples, N_l, 3]], 'shard': [(complex, first, stop)], 'run_time'}``;
+    with ``gather=False`` (or on ranks > 0 when the backend cannot gather) only the rank's own poses are filled in."""
+    from . import dist as ddist
+    import torch.distributed as tdist
+    if world is None:
+        world = tdist.get_world_size() if tdist.is_initialized() else 1
+    if rank is None:
+        rank = tdist.get_rank() if tdist.is_initialized() else 0
+    sampler = sampler or sampling
+    N = samples_per_complex
+    schedule = get_t_schedule(inference_steps=inference_steps)
+    steps = actual_steps if actual_steps is not None else inference_steps
+    no_torsion = bool(getattr(model_args, 'no_torsion', False)) if no_torsion is None else no_torsion
+    if broadcast_weights and tdist.is_initialized() and world > 1:
+        sm = model.score_model if hasattr(model, 'score_model') else model
+        ddist.broadcast_module(sm, src=0)
+        if hasattr(sm, 'invalidate'):
+            sm.invalidate()
+    cost = [float(g['ligand'].pos.shape[0]) * float(g['receptor'].pos.shape[0]) for g in complexes]
+    shard = ddist.shard_poses([N] * len(complexes), cost, rank, world)
+    n_rot = [int(g['ligand'].edge_mask.sum()) for g in complexes]
+    local: Dict[tuple, torch.Tensor] = {}
+    t0 = time.time()
+    # calls of at most poses_per_call poses, whole shard entries per call (an entry = a run of copies of one complex)
+    calls, cur, cur_n = [], [], 0
+    for ci, a, b in shard:
+        k = a
+        while k < b:
+            take = min(b - k, max(1, poses_per_call - cur_n))
+            cur.append((ci, k, k + take)); cur_n += take; k += take
+            if cur_n >= poses_per_call:
+                calls.append(cur); cur, cur_n = [], 0
+    if cur:
+        calls.append(cur)
+    start_cache: Dict[int, list] = {}
+    for call in calls:
+        flat, zs = [], []
+        for ci, a, b in call:
+            if ci not in start_cache:
+                start_cache = {ci: seeded_start_poses(complexes[ci], ci, N, seed, no_torsion, no_random, model_args.tr_sigma_max)}
+            flat += start_cache[ci][a:b]
+            zs += [pose_noise(seed, ci, k, steps, n_rot[ci]) for k in range(a, b)]
+        noise = None
+        if not (no_random or ode):
+            noise = {'tr': torch.stack([z['tr'] for z in zs], dim=1), 'rot': torch.stack([z['rot'] for z in zs], dim=1),
+                     'tor': torch.cat([z['tor'] for z in zs], dim=1)}
+        sampler(data_list=flat, model=model, inference_steps=steps, tr_schedule=schedule, rot_schedule=schedule,
+                tor_schedule=schedule, device=device, t_to_sigma=t_to_sigma, model_args=model_args, no_random=no_random, ode=ode,
+                batch_size=len(flat), no_final_step_noise=no_final_step_noise, temp_sampling=temp_sampling, temp_psi=temp_psi,
+                temp_sigma_data=temp_sigma_data, noise=noise, host_buffers=host_buffers)
+        i = 0
+        for ci, a, b in call:
+            for k in range(a, b):
+                local[(ci, k)] = flat[i]['ligand'].pos.detach().to('cpu', torch.float32)
+                i += 1
+    run_time = time.time() - t0
+    # ---- one gather of the final poses: [pose id, padded coordinates]
+    max_nl = max(int(g['ligand'].pos.shape[0]) for g in complexes)
+    ids = sorted(local.keys())
+    buf = torch.zeros(len(ids), max_nl, 3)
+    for r, key in enumerate(ids):
+        buf[r, :local[key].shape[0]] = local[key]
+    idt = torch.tensor(ids, dtype=torch.int64).reshape(-1, 2)
+    if gather and tdist.is_initialized() and world > 1:
+        counts = []
+        for r in range(world):
+            counts.append(sum(b - a for _, a, b in ddist.shard_poses([N] * len(complexes), cost, r, world)))
+        gdev = torch.device(device) if tdist.get_backend() == 'nccl' else torch.device('cpu')
+        buf = ddist.gather_poses(buf.to(gdev), counts).cpu()
+        idt = ddist.gather_poses(idt.to(gdev), counts).cpu()
+    out_pos = [torch.full((N, int(g['ligand'].pos.shape[0]), 3), float('nan')) for g in complexes]
+    for r in range(idt.shape[0]):
+        ci, k = int(idt[r, 0]), int(idt[r, 1])
+        out_pos[ci][k] = buf[r, :out_pos[ci].shape[1]]
+    return {'names': [_name(g) for g in complexes], 'ligand_pos': out_pos, 'shard': shard, 'run_time': run_time}

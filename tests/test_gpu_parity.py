@@ -429,3 +429,47 @@ def test_radius_truncation_at_32_neighbours():
     assert got0 == want0, 'ligand-ligand edge multiset differs under truncation'
     assert eng.last_edge_count() == trc['n_edges']
     assert max(d['tr'], d['rot'], d['tor']) < 2e-5, d
+
+
+def test_sharded_inference_is_bit_identical_to_unsharded():
+    """SURVEY 8e / north_star: sharding samples_per_complex x complexes over ranks.  The shards of world = 2 and 3, run one after
+    the other on this GPU, reproduce the world = 1 poses BIT FOR BIT (start poses and noise are keyed by (seed, complex, sample);
+    a pose does not depend on its batch), and those match the oracle."""
+    from functools import partial
+    from disco_diffdock_b200 import inference
+    m, sd, cfg = helpers.make_model(2, gain=5.0)
+    m = m.to('cuda')
+    N, steps = 5, 8
+    gs = [synthetic.make_complex(91, 14, 40), synthetic.make_complex(92, 22, 64), synthetic.make_complex(93, 10, 24)]
+    complexes = [synthetic.as_loader_item(g) for g in gs]
+    t2s = partial(du.t_to_sigma, args=cfg)
+    kw = dict(samples_per_complex=N, inference_steps=steps, seed=11, no_final_step_noise=True, broadcast_weights=False, **helpers.README_TEMPS)
+    full = inference.run_inference_sharded(complexes, m, cfg, torch.device('cuda'), t2s, rank=0, world=1, poses_per_call=400, **kw)
+    assert not any(torch.isnan(p).any() for p in full['ligand_pos'])
+    diffs = {}
+    for world in (2, 3):
+        merged = [torch.full_like(p, float('nan')) for p in full['ligand_pos']]
+        for r in range(world):
+            part = inference.run_inference_sharded(complexes, m, cfg, torch.device('cuda'), t2s, rank=r, world=world, poses_per_call=6,
+                                                   gather=False, **kw)
+            for ci in range(3):
+                mask = ~torch.isnan(part['ligand_pos'][ci][:, 0, 0])
+                merged[ci][mask] = part['ligand_pos'][ci][mask]
+        diffs[world] = max(float((a - b).abs().max()) for a, b in zip(merged, full['ligand_pos']))
+    # oracle on complex 1 from the same start poses and noise
+    dl = inference.seeded_start_poses(complexes[1], 1, N, 11, False, False, cfg.tr_sigma_max)
+    lst = []
+    for k in range(N):
+        g = copy.deepcopy(gs[1]); g['ligand'].pos = dl[k]['ligand'].pos.clone(); lst.append(g)
+    R = int(gs[1]['ligand'].edge_mask.sum())
+    zs = [inference.pose_noise(11, 1, k, steps, R) for k in range(N)]
+    noise = {'tr': torch.stack([z['tr'] for z in zs], 1), 'rot': torch.stack([z['rot'] for z in zs], 1), 'tor': torch.cat([z['tor'] for z in zs], 1)}
+    for k in noise:
+        noise[k][-1] = 0
+    with torch.no_grad():
+        want = restate.sample(sd, cfg, ddata.Batch.from_data_list(lst), load_tables(), du.get_t_schedule(steps), noise,
+                              inference_steps=steps, **helpers.README_TEMPS)
+    rmsd = helpers.rmsd_per_pose(want, full['ligand_pos'][1].reshape(-1, 3), N)
+    dump('sharded_inference', {'max_abs_diff_vs_unsharded': diffs, 'rmsd_vs_oracle': rmsd.tolist()})
+    assert max(diffs.values()) == 0.0, diffs
+    assert float(rmsd.max()) < 1e-3, rmsd

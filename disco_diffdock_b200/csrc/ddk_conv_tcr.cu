@@ -70,6 +70,7 @@ struct TrArgs {
   const TcrRole* roles; int nroles;  // roles of the level
   const float* W[4][TCR_MAXROLES];   // resident weight slice of (group, role)
   float* part;                       // [2 N][nroles][84]
+  long long* dbg;                    // DDK_TCR_TRACE build: [grid][32] cycle counters
 };
 
 template <int LV>
@@ -96,6 +97,14 @@ struct TrSmem {
   int task[8];                       // g, role, idx0, nseg, reload, combo cursor, resident combo (g * nroles + role), -
   alignas(128) float Wsl[1];         // the resident weight slice follows (TCR_WMAX floats, dynamic)
 };
+
+#if DDK_TCR_TRACE     // build with DDK_NVCC_EXTRA=-DDDK_TCR_TRACE=1 (tools/tcr_trace.sh): per CTA cycle counters of one thread per warp role
+#define TR_T(var) const long long var = clock64();
+#define TR_ADD(slot, a, b) dbgacc[slot] += (b) - (a);
+#else
+#define TR_T(var)
+#define TR_ADD(slot, a, b)
+#endif
 
 __device__ __forceinline__ void tr_bar_con() { asm volatile("bar.sync %0, %1;" ::"n"(TR_BAR_CON), "n"(TR_CONW * 32) : "memory"); }
 
@@ -295,6 +304,11 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = S.tmem_base;
 
+#if DDK_TCR_TRACE
+  long long dbgacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const long long tk0 = clock64();
+  long long t_reload = 0, n_tasks = 0, n_reload = 0;
+#endif
   int it = 0;        // 8-edge chunks so far (gather / row warps / MMA thread count the same sequence)
   int sg = 0;        // accumulator slots so far (MMA thread / contraction warps); a multiple of the group size between tasks
   int nwl = 0;       // weight-slice loads so far
@@ -327,6 +341,10 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
     const int g = S.task[0];
     if (g < 0) break;
     const int role_id = S.task[1], idx0 = S.task[2], nseg = S.task[3];
+#if DDK_TCR_TRACE
+    ++n_tasks;
+    const long long trl0 = clock64();
+#endif
     if (S.task[4]) {
       // every read of the previous slice / role tables happened before the __syncthreads that ended the previous task
       const TcrRole* src = p.roles + role_id;
@@ -356,6 +374,9 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
       tc_mbar_wait_sleep(&S.bar_w, nwl & 1);
       ++nwl;
       __syncthreads();
+#if DDK_TCR_TRACE
+      ++n_reload; t_reload += clock64() - trl0;
+#endif
     }
     const TcrRole& R = S.role;
     const int N = R.N, nj = R.nj, j0 = R.j0;
@@ -389,8 +410,12 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
           if (it % TR_NSETS != set) continue;
           const int kc = min(KC3, n - c * KC3);
           const int buf = it % TR_XR, stage = set;
+          TR_T(ra)
           tc_mbar_wait(&S.sfull[buf], (it / TR_XR) & 1);
+          TR_T(rb)
           tc_mbar_wait(&S.empty[stage], ((it / TR_NST) & 1) ^ 1);
+          TR_T(rc)
+          TR_ADD(0, ra, rb) TR_ADD(1, rb, rc)
           float b[KC3];
           if (plain) {
             float xv[KC3], sv[KC3];
@@ -440,11 +465,17 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
           }
           __syncwarp();
           if (lane == 0) tc_mbar_arrive(&S.sempty[buf]);
+          TR_T(rd_)
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
           if (lane == 0) tc_mbar_arrive(&S.full[stage]);
+          TR_T(re)
+          TR_ADD(2, rc, rd_) TR_ADD(3, rd_, re)
+#if DDK_TCR_TRACE
+          dbgacc[4] += 1;
+#endif
         }
       }
     } else if (warp == TR_W_MMA) {
@@ -454,12 +485,18 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
         for (int i = 0; i < nseg; ++i, ++sg) {
           const int nch = (load_seg_entry(wl + i).y + KC3 - 1) / KC3;
           const int slot = sg % NACC;
+          TR_T(ma)
           tc_mbar_wait(&S.accempty[slot], ((sg / NACC) & 1) ^ 1);                  // the contraction warps have read the slot's old content
+          TR_T(mb)
+          TR_ADD(0, ma, mb)
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t d = tmem + slot * N;
           for (int c = 0; c < nch; ++c, ++it) {
             const int stage = it % TR_NST;
+            TR_T(mc)
             tc_mbar_wait(&S.full[stage], (it / TR_NST) & 1);
+            TR_T(md)
+            TR_ADD(1, mc, md)
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint64_t bhd = tc_desc(tc_smem(&S.Bhi[stage][0]), N * 16, 128);
             const uint64_t bld = tc_desc(tc_smem(&S.Blo[stage][0]), N * 16, 128);
@@ -469,6 +506,8 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
             tc_mma_ts(d, al, bhd, idesc, 1);
             tc_commit(&S.empty[stage]);
             if (c == nch - 1) tc_commit(&S.accfull[slot]);
+            TR_T(me)
+            TR_ADD(2, md, me)
           }
         }
         for (; sg % G != 0; ++sg) {                                              // pad the last group of the task with empty slots
@@ -495,7 +534,10 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
           const int2 ent = ent_next;
           if (lane < KC3 && c + 1 < nch) ent_next = p.seg_list[pos0 + KC3 + min(lane, n - (c + 1) * KC3 - 1)];
           const int slot = __shfl_sync(0xffffffffu, ent.x, e), dst = __shfl_sync(0xffffffffu, ent.y, e);
+          TR_T(ga)
           tc_mbar_wait(&S.sempty[buf], ((it / TR_XR) & 1) ^ 1);
+          TR_T(gb)
+          TR_ADD(0, ga, gb)
           if (lane == 0) tc_mbar_expect_tx(&S.sfull[buf], (uint32_t)kc * (xbytes + 16u + hbytes));
           __syncwarp();
           if (e < kc) {
@@ -503,6 +545,8 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
             else if (kind == 1) tc_bulk_g2s(&S.SH[buf][e][0], p.sh_pool + slot, 16u, &S.sfull[buf]);
             else if (kind == 2) tc_bulk_g2s(&S.HS[buf][e][0], p.hs + (size_t)(pos0 + e) * HID + j0, hbytes, &S.sfull[buf]);
           }
+          TR_T(gc)
+          TR_ADD(1, gb, gc)
         }
       }
     } else if (warp >= TR_W_CON) {
@@ -511,14 +555,34 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
       const int ngroups = (nseg + G - 1) / G;
       for (int grp = 0; grp < ngroups; ++grp, sg += G, ++gcount) {
         const int nvalid = min(G, nseg - grp * G);
+#if DDK_TCR_TRACE
+        {                                             // time spent waiting for the group's accumulators (then the group itself)
+          const long long ca = clock64();
+          for (int g2 = 0; g2 < G; ++g2) tc_mbar_wait_sleep(&S.accfull[(sg + g2) % NACC], ((sg + g2) / NACC) & 1);
+          dbgacc[0] += clock64() - ca;
+        }
+        const long long cb_ = clock64();
+#endif
         if (vec) tr_con_group<LV, true>(p, S, Wsl, tmem, sg, nvalid, idx0 + grp * G, p.goff[g], role_id, cw, q, lane, ct, gcount);
         else tr_con_group<LV, false>(p, S, Wsl, tmem, sg, nvalid, idx0 + grp * G, p.goff[g], role_id, cw, q, lane, ct, gcount);
+#if DDK_TCR_TRACE
+        dbgacc[1] += clock64() - cb_; dbgacc[2] += 1;
+#endif
       }
     }
     // every thread keeps only the counters its own warp role uses (`it`: gather / row warps / MMA thread; `sg`: MMA thread /
     // contraction warps) and advances them by walking the same task sequence, so they agree without any exchange
     __syncthreads();
   }
+#if DDK_TCR_TRACE
+  if (p.dbg) {
+    long long* o = p.dbg + (size_t)blockIdx.x * 32;
+    if (tid == 0) { for (int k = 0; k < 5; ++k) o[k] = dbgacc[k]; o[5] = clock64() - tk0; o[6] = n_tasks; o[7] = n_reload; o[8] = t_reload; }
+    if (tid == TR_W_MMA * 32) for (int k = 0; k < 3; ++k) o[10 + k] = dbgacc[k];
+    if (tid == TR_W_GATHER * 32) for (int k = 0; k < 2; ++k) o[14 + k] = dbgacc[k];
+    if (tid == TR_W_CON * 32) for (int k = 0; k < 3; ++k) o[18 + k] = dbgacc[k];
+  }
+#endif
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TR_COLS));
@@ -700,6 +764,13 @@ void launch_conv_tcr(DdkCtx* c, int layer, const float* x_in, float* x_out, cuda
   a.part = ptr<float>(c->b_part);
   cudaMemsetAsync(c->b_counters.p, 0, 4 * TCR_MAXROLES * sizeof(int), st);
   const int grid = c->sm_count;
+  a.dbg = nullptr;
+#if DDK_TCR_TRACE
+  static long long* dbg = nullptr;
+  if (!dbg) cudaMalloc(&dbg, 256 * 32 * sizeof(long long));
+  cudaMemsetAsync(dbg, 0, 256 * 32 * sizeof(long long), st);
+  a.dbg = dbg;
+#endif
   {
     LaunchScope ls(c, PC_TC0 + li.lv, st);
     switch (li.lv) {
@@ -709,6 +780,20 @@ void launch_conv_tcr(DdkCtx* c, int layer, const float* x_in, float* x_out, cuda
       default: k_conv_tcr<3><<<grid, TR_THREADS, tcr_smem_bytes(3), st>>>(a); break;
     }
   }
+#if DDK_TCR_TRACE
+  {
+    std::vector<long long> h((size_t)grid * 32);
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h.data(), dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    double s_[32] = {0};
+    for (int b = 0; b < grid; ++b) for (int k = 0; k < 32; ++k) s_[k] += (double)h[(size_t)b * 32 + k] / grid;
+    fprintf(stderr, "[tcr_trace] layer %d lv %d mode %d kcycles per CTA: total %.0f, tasks %.1f, reloads %.1f (%.0f) | row warp 0 (set 0): chunks %.0f, "
+                    "wait staging %.0f, wait stage %.0f, operands %.0f, fences %.0f | mma: wait slot %.0f, wait operands %.0f, issue %.0f | "
+                    "gather: wait ring %.0f, issue %.0f | contraction warp 0: wait acc %.0f, groups %.0f (%.0f)\n",
+            layer, li.lv, mode, s_[5] / 1e3, s_[6], s_[7], s_[8] / 1e3, s_[4], s_[0] / 1e3, s_[1] / 1e3, s_[2] / 1e3, s_[3] / 1e3,
+            s_[10] / 1e3, s_[11] / 1e3, s_[12] / 1e3, s_[14] / 1e3, s_[15] / 1e3, s_[18] / 1e3, s_[19] / 1e3, s_[20]);
+  }
+#endif
   launch_conv_finalize(c, layer, x_in, x_out, st, lig_only, nroles);
 }
 

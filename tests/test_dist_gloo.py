@@ -81,7 +81,10 @@ def _fake_sampler(data_list, noise=None, **kw):
     off = 0
     for i, g in enumerate(data_list):
         R = int(g['ligand'].edge_mask.sum())
-        g['ligand'].pos = g['ligand'].pos * 1.25 + noise['tr'][:, i].sum(0) + noise['rot'][:, i].sum() + noise['tor'][:, off:off + R].sum()
+        # sums in float64 over contiguous copies: the stand-in itself must not depend on the strides of the batch it sits in
+        z = (noise['tr'][:, i].contiguous().double().sum(0) + noise['rot'][:, i].contiguous().double().sum()
+             + noise['tor'][:, off:off + R].contiguous().double().sum())
+        g['ligand'].pos = (g['ligand'].pos.double() * 1.25 + z).float()
         off += R
     return data_list, None
 

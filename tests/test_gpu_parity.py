@@ -437,7 +437,7 @@ def test_sharded_inference_is_bit_identical_to_unsharded():
     a pose does not depend on its batch), and those match the oracle."""
     from functools import partial
     from disco_diffdock_b200 import inference
-    m, sd, cfg = helpers.make_model(2, gain=5.0)
+    m, sd, cfg = helpers.make_model(2, gain=1.0)
     m = m.to('cuda')
     N, steps = 5, 8
     gs = [synthetic.make_complex(91, 14, 40), synthetic.make_complex(92, 22, 64), synthetic.make_complex(93, 10, 24)]

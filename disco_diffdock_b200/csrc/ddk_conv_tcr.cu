@@ -54,6 +54,8 @@ constexpr int TR_BAR_CON = 1;        // named barrier of the contraction warps
 constexpr int TR_GV = 2, TR_GS = 4;  // segments contracted together: vector roles / scalar roles
 constexpr int TR_RED_FLOATS = 6144;  // partial outputs of a group: max(G_V * 2 halves * 128 rows * 6, G_S * 64 rows * 24)
 constexpr int TR_RED2 = 256;
+constexpr int TR_MAXSEG = 256;       // segments per task
+constexpr int TR_PF = 4;             // chunks the gather warp fetches list entries ahead
 
 struct TrArgs {
   int NL, N;
@@ -95,6 +97,7 @@ struct TrSmem {
   alignas(8) unsigned long long bar_w;                                  // completion of the weight-slice bulk copy
   uint32_t tmem_base;
   int task[8];                       // g, role, idx0, nseg, reload, combo cursor, resident combo (g * nroles + role), -
+  int seg_id[TR_MAXSEG], seg_n[TR_MAXSEG], seg_base[TR_MAXSEG];   // the task's work-list entries (staged once per task)
   alignas(128) float Wsl[1];         // the resident weight slice follows (TCR_WMAX floats, dynamic)
 };
 
@@ -247,7 +250,7 @@ __device__ __forceinline__ void tr_con_group(const TrArgs& p, TrSmem<LV>& S, con
         const float* b = red2 + (g * nout + src) * np;
         for (int k = 0; k < np; ++k) v += b[k];
       }
-      const int sid = __ldg(&p.glist[g_edge + seg0 + g].x);
+      const int sid = S.seg_id[seg0 + g];
       p.part[((size_t)sid * p.nroles + role_id) * D + f] = v;
     }
   }
@@ -271,7 +274,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
   }
   if (tid == TR_W_MMA * 32) {
     for (int s = 0; s < TR_NST; ++s) { tc_mbar_init(&S.full[s], TR_ROWW); tc_mbar_init(&S.empty[s], 1); }
-    for (int s = 0; s < TR_XR; ++s) { tc_mbar_init(&S.sfull[s], 1); tc_mbar_init(&S.sempty[s], TR_ROWW); }
+    for (int s = 0; s < TR_XR; ++s) { tc_mbar_init(&S.sfull[s], 32); tc_mbar_init(&S.sempty[s], TR_ROWW); }
     for (int s = 0; s < TCR_MAXACC; ++s) { tc_mbar_init(&S.accfull[s], 1); tc_mbar_init(&S.accempty[s], TR_CONW); }
     tc_mbar_init(&S.bar_w, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -378,11 +381,19 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
       ++n_reload; t_reload += clock64() - trl0;
 #endif
     }
+    {
+      // the task's work-list entries -> shared memory: every warp role walks them, nobody waits on a global load per segment
+      const int4* wle = p.glist + p.goff[g] + idx0;
+      for (int i = tid; i < nseg; i += TR_THREADS) {
+        const int4 e4 = load_seg_entry(wle + i);
+        S.seg_id[i] = e4.x; S.seg_n[i] = e4.y; S.seg_base[i] = e4.z;
+      }
+    }
+    __syncthreads();
     const TcrRole& R = S.role;
     const int N = R.N, nj = R.nj, j0 = R.j0;
     const bool vec = !R.isS;
     const int G = vec ? TR_GV : TR_GS, NACC = 2 * G;
-    const int4* wl = p.glist + p.goff[g] + idx0;
 
     if (warp < TR_W_MMA) {
       // ================================================================== row warps: A operand -> tensor memory, B -> smem
@@ -404,7 +415,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
         bh[b2] = w < nb_items ? w / (nj + 1) : 0;
       }
       for (int i = 0; i < nseg; ++i) {
-        const int n = load_seg_entry(wl + i).y;
+        const int n = S.seg_n[i];
         const int nch = (n + KC3 - 1) / KC3;
         for (int c = 0; c < nch; ++c, ++it) {
           if (it % TR_NSETS != set) continue;
@@ -483,7 +494,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
       if (lane == 0) {
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         for (int i = 0; i < nseg; ++i, ++sg) {
-          const int nch = (load_seg_entry(wl + i).y + KC3 - 1) / KC3;
+          const int nch = (S.seg_n[i] + KC3 - 1) / KC3;
           const int slot = sg % NACC;
           TR_T(ma)
           tc_mbar_wait(&S.accempty[slot], ((sg / NACC) & 1) ^ 1);                  // the contraction warps have read the slot's old content
@@ -517,38 +528,64 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
         }
       }
     } else if (warp == TR_W_GATHER) {
-      // ================================================================== gather warp: global -> staging ring, bulk copies
-      // lane (kind = lane / 8, e = lane % 8) moves one contiguous piece of edge e: its destination feature row, its harmonics
-      // record, or the role's hidden units; the copies complete on the ring slot's mbarrier (complete_tx)
-      const int e = lane & 7, kind = lane >> 3;
-      const uint32_t xbytes = DINP * 4, hbytes = (uint32_t)nj * 4;
+      // ================================================================== gather warp: global -> staging ring
+      // lane = (edge e = lane / 4 of the chunk, sub = lane % 4): the four lanes of an edge copy its record in interleaved 16-byte
+      // pieces -- destination feature row, harmonics, the role's hidden units -- with cp.async (LDGSTS; bulk copies are per-warp
+      // instructions and serialise when every lane has its own address: measured 1700 cycles per chunk).  Completion is signalled
+      // to the ring slot's mbarrier by cp.async.mbarrier.arrive.noinc, so the warp never waits for its own copies.
+      const int e = lane >> 2, sub = lane & 3;
+      constexpr int XQ = DINP / 4;
+      const int hq = nj / 4;
+      // list entries (edge slot, destination node) are fetched TR_PF chunks ahead of their use: lane l < 8 keeps the entry of edge l
+      // of the next TR_PF chunks in registers, so the L2 latency of the entry loads never sits on the chunk's critical path
+      int hi_ = 0, hc = 0;                              // head of the prefetch stream: (segment, chunk)
+      auto head_load = [&]() {
+        int2 v = make_int2(0, 0);
+        if (hi_ < nseg) {
+          const int n = S.seg_n[hi_], pos0 = S.seg_base[hi_] + hc * KC3;
+          if (lane < KC3) v = __ldg(&p.seg_list[pos0 + min(lane, n - hc * KC3 - 1)]);
+          if (++hc * KC3 >= n) { ++hi_; hc = 0; }
+        }
+        return v;
+      };
+      int2 fifo[TR_PF];
+#pragma unroll
+      for (int k = 0; k < TR_PF; ++k) fifo[k] = head_load();
       for (int i = 0; i < nseg; ++i) {
-        const int4 ge = load_seg_entry(wl + i);
-        const int n = ge.y, base = ge.z;
+        const int n = S.seg_n[i], base = S.seg_base[i];
         const int nch = (n + KC3 - 1) / KC3;
-        int2 ent_next = make_int2(0, 0);
-        if (lane < KC3) ent_next = p.seg_list[base + min(lane, n - 1)];
         for (int c = 0; c < nch; ++c, ++it) {
           const int kc = min(KC3, n - c * KC3), pos0 = base + c * KC3;
           const int buf = it % TR_XR;
-          const int2 ent = ent_next;
-          if (lane < KC3 && c + 1 < nch) ent_next = p.seg_list[pos0 + KC3 + min(lane, n - (c + 1) * KC3 - 1)];
+          const int2 ent = fifo[0];
+#pragma unroll
+          for (int k = 0; k + 1 < TR_PF; ++k) fifo[k] = fifo[k + 1];
+          fifo[TR_PF - 1] = head_load();
           const int slot = __shfl_sync(0xffffffffu, ent.x, e), dst = __shfl_sync(0xffffffffu, ent.y, e);
           TR_T(ga)
           tc_mbar_wait(&S.sempty[buf], ((it / TR_XR) & 1) ^ 1);
           TR_T(gb)
           TR_ADD(0, ga, gb)
-          if (lane == 0) tc_mbar_expect_tx(&S.sfull[buf], (uint32_t)kc * (xbytes + 16u + hbytes));
-          __syncwarp();
-          if (e < kc) {
-            if (kind == 0) tc_bulk_g2s(&S.X[buf][e][0], p.x + (size_t)dst * D, xbytes, &S.sfull[buf]);
-            else if (kind == 1) tc_bulk_g2s(&S.SH[buf][e][0], p.sh_pool + slot, 16u, &S.sfull[buf]);
-            else if (kind == 2) tc_bulk_g2s(&S.HS[buf][e][0], p.hs + (size_t)(pos0 + e) * HID + j0, hbytes, &S.sfull[buf]);
+          if (e < kc) {                                 // rows of absent edges keep their stale (finite) content
+            const float* xs = p.x + (size_t)dst * D + 4 * sub;
+            float* xd = &S.X[buf][e][4 * sub];
+#pragma unroll
+            for (int k = 0; k < (XQ + 3) / 4; ++k)
+              if (sub + 4 * k < XQ) __pipeline_memcpy_async(xd + 16 * k, xs + 16 * k, 16);
+            if (sub == 0) __pipeline_memcpy_async(&S.SH[buf][e][0], p.sh_pool + slot, 16);
+            const float* hsrc = p.hs + (size_t)(pos0 + e) * HID + j0 + 4 * sub;
+            float* hd = &S.HS[buf][e][4 * sub];
+#pragma unroll
+            for (int k = 0; k < (HID / 4 + 3) / 4; ++k)
+              if (sub + 4 * k < hq) __pipeline_memcpy_async(hd + 16 * k, hsrc + 16 * k, 16);
           }
+          // the barrier receives this thread's arrival when all of its copies above have landed
+          asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tc_smem(&S.sfull[buf])) : "memory");
           TR_T(gc)
           TR_ADD(1, gb, gc)
         }
       }
+      asm volatile("cp.async.wait_all;" ::: "memory");
     } else if (warp >= TR_W_CON) {
       // ================================================================== contraction warps
       const int cw = warp - TR_W_CON, q = warp & 3, ct = cw * 32 + lane;    // TR_W_CON is a multiple of 4: q = cw & 3
@@ -563,8 +600,8 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
         }
         const long long cb_ = clock64();
 #endif
-        if (vec) tr_con_group<LV, true>(p, S, Wsl, tmem, sg, nvalid, idx0 + grp * G, p.goff[g], role_id, cw, q, lane, ct, gcount);
-        else tr_con_group<LV, false>(p, S, Wsl, tmem, sg, nvalid, idx0 + grp * G, p.goff[g], role_id, cw, q, lane, ct, gcount);
+        if (vec) tr_con_group<LV, true>(p, S, Wsl, tmem, sg, nvalid, grp * G, 0, role_id, cw, q, lane, ct, gcount);
+        else tr_con_group<LV, false>(p, S, Wsl, tmem, sg, nvalid, grp * G, 0, role_id, cw, q, lane, ct, gcount);
 #if DDK_TCR_TRACE
         dbgacc[1] += clock64() - cb_; dbgacc[2] += 1;
 #endif

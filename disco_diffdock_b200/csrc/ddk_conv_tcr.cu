@@ -264,7 +264,8 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
   extern __shared__ __align__(128) unsigned char tr_raw[];
   TrSmem<LV>& S = *reinterpret_cast<TrSmem<LV>*>(tr_raw);
   float* const Wsl = &S.Wsl[0];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);     // warp-uniform by construction: role branches stay uniform
   const int ncombo = 4 * p.nroles;
 
   // ---- one-time setup
@@ -490,44 +491,56 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
         }
       }
     } else if (warp == TR_W_MMA) {
-      // ================================================================== MMA issue (one thread)
-      if (lane == 0) {
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-        for (int i = 0; i < nseg; ++i, ++sg) {
-          const int nch = (S.seg_n[i] + KC3 - 1) / KC3;
-          const int slot = sg % NACC;
-          TR_T(ma)
-          tc_mbar_wait(&S.accempty[slot], ((sg / NACC) & 1) ^ 1);                  // the contraction warps have read the slot's old content
-          TR_T(mb)
-          TR_ADD(0, ma, mb)
+      // ================================================================== MMA issue
+      // The whole warp walks the chunks with warp-uniform values (shuffled from lane 0), and ONE elected lane issues the
+      // tcgen05 instructions: their operands then live in uniform registers.  (Issued from inside `if (lane == 0)` every
+      // UTCHMMA / UTCBAR was wrapped in an ELECT + 4 x R2UR + branch loop: ~390 cycles per chunk in the trace.)
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+      const int N_u = __shfl_sync(0xffffffffu, N, 0), G_u = __shfl_sync(0xffffffffu, G, 0), NACC_u = 2 * G_u;
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N_u >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t bhi0 = tc_smem(&S.Bhi[0][0]), blo0 = tc_smem(&S.Blo[0][0]);
+      auto elect = []() {
+        uint32_t pred;
+        asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+        return pred != 0;
+      };
+      for (int i = 0; i < nseg; ++i, ++sg) {
+        const int nch = (__shfl_sync(0xffffffffu, S.seg_n[i], 0) + KC3 - 1) / KC3;
+        const int slot = sg % NACC_u;
+        TR_T(ma)
+        tc_mbar_wait(&S.accempty[slot], ((sg / NACC_u) & 1) ^ 1);                  // the contraction warps have read the slot's old content
+        TR_T(mb)
+        TR_ADD(0, ma, mb)
+        const uint32_t d = tmem_u + slot * N_u;
+        for (int c = 0; c < nch; ++c, ++it) {
+          const int stage = it % TR_NST;
+          TR_T(mc)
+          tc_mbar_wait(&S.full[stage], (it / TR_NST) & 1);
+          TR_T(md)
+          TR_ADD(1, mc, md)
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t d = tmem + slot * N;
-          for (int c = 0; c < nch; ++c, ++it) {
-            const int stage = it % TR_NST;
-            TR_T(mc)
-            tc_mbar_wait(&S.full[stage], (it / TR_NST) & 1);
-            TR_T(md)
-            TR_ADD(1, mc, md)
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint64_t bhd = tc_desc(tc_smem(&S.Bhi[stage][0]), N * 16, 128);
-            const uint64_t bld = tc_desc(tc_smem(&S.Blo[stage][0]), N * 16, 128);
-            const uint32_t ah = tmem + TR_ACOL + stage * 16, al = ah + 8;
+          const uint64_t bhd = tc_desc(bhi0 + stage * (TR_NMAX * 8 * 4), N_u * 16, 128);
+          const uint64_t bld = tc_desc(blo0 + stage * (TR_NMAX * 8 * 4), N_u * 16, 128);
+          const uint32_t ah = tmem_u + TR_ACOL + stage * 16, al = ah + 8;
+          if (elect()) {
             tc_mma_ts(d, ah, bhd, idesc, c > 0);
             tc_mma_ts(d, ah, bld, idesc, 1);
             tc_mma_ts(d, al, bhd, idesc, 1);
             tc_commit(&S.empty[stage]);
             if (c == nch - 1) tc_commit(&S.accfull[slot]);
-            TR_T(me)
-            TR_ADD(2, md, me)
           }
-        }
-        for (; sg % G != 0; ++sg) {                                              // pad the last group of the task with empty slots
-          const int slot = sg % NACC;
-          tc_mbar_wait(&S.accempty[slot], ((sg / NACC) & 1) ^ 1);
-          tc_mbar_arrive(&S.accfull[slot]);
+          __syncwarp();
+          TR_T(me)
+          TR_ADD(2, md, me)
         }
       }
-    } else if (warp == TR_W_GATHER) {
+      for (; sg % G_u != 0; ++sg) {                                                // pad the last group of the task with empty slots
+        const int slot = sg % NACC_u;
+        tc_mbar_wait(&S.accempty[slot], ((sg / NACC_u) & 1) ^ 1);
+        if (lane == 0) tc_mbar_arrive(&S.accfull[slot]);
+        __syncwarp();
+      }
+    } else if (warp == TR_W_GATHER || warp == TR_W_GATHER + 1) {
       // ================================================================== gather warp: global -> staging ring
       // lane = (edge e = lane / 4 of the chunk, sub = lane % 4): the four lanes of an edge copy its record in interleaved 16-byte
       // pieces -- destination feature row, harmonics, the role's hidden units -- with cp.async (LDGSTS; bulk copies are per-warp
@@ -538,13 +551,18 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
       const int hq = nj / 4;
       // list entries (edge slot, destination node) are fetched TR_PF chunks ahead of their use: lane l < 8 keeps the entry of edge l
       // of the next TR_PF chunks in registers, so the L2 latency of the entry loads never sits on the chunk's critical path
-      int hi_ = 0, hc = 0;                              // head of the prefetch stream: (segment, chunk)
-      auto head_load = [&]() {
+      // the two gather warps take alternate chunks (gw = parity of the chunk counter); each prefetches the entries of ITS chunks
+      const int gw = warp - TR_W_GATHER;
+      int hi_ = 0, hc = 0, hit = it;                    // head of the prefetch stream: (segment, chunk, chunk counter)
+      auto head_load = [&]() {                          // the next chunk of this warp at or after the head
         int2 v = make_int2(0, 0);
-        if (hi_ < nseg) {
+        while (hi_ < nseg) {
           const int n = S.seg_n[hi_], pos0 = S.seg_base[hi_] + hc * KC3;
-          if (lane < KC3) v = __ldg(&p.seg_list[pos0 + min(lane, n - hc * KC3 - 1)]);
+          const bool mine = (hit & 1) == gw;
+          if (mine && lane < KC3) v = __ldg(&p.seg_list[pos0 + min(lane, n - hc * KC3 - 1)]);
+          ++hit;
           if (++hc * KC3 >= n) { ++hi_; hc = 0; }
+          if (mine) break;
         }
         return v;
       };
@@ -555,6 +573,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
         const int n = S.seg_n[i], base = S.seg_base[i];
         const int nch = (n + KC3 - 1) / KC3;
         for (int c = 0; c < nch; ++c, ++it) {
+          if ((it & 1) != gw) continue;
           const int kc = min(KC3, n - c * KC3), pos0 = base + c * KC3;
           const int buf = it % TR_XR;
           const int2 ent = fifo[0];

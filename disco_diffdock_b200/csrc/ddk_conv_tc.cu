@@ -106,8 +106,9 @@ __global__ void __launch_bounds__(TcCfg<LV>::THREADS, 1) k_acc_tc(const __grid_c
   constexpr int J = Cfg::J, NSL = Cfg::NSL, AST = Cfg::AST;
   extern __shared__ __align__(128) unsigned char tc_raw[];
   TcSmem<LV>& S = *reinterpret_cast<TcSmem<LV>*>(tc_raw);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bool is_row = tid < ROWT;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-uniform by construction
+  const bool is_row = warp < ROWT / 32;
 
   // ---- one-time setup: TMEM, barriers, zeroed operand tiles (rows >= U and B rows > 72 stay zero for ever)
   if (warp == 0) {
@@ -359,13 +360,18 @@ __global__ void __launch_bounds__(TcCfg<LV>::THREADS, 1) k_acc_tc(const __grid_c
       }
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
-  } else if (lane == 0) {
-    // ================================================================== MMA issue (one thread)
+  } else {
+    // ================================================================== MMA issue
+    // The whole warp walks the chunks with warp-uniform values and ONE elected lane issues the tcgen05 instructions, so their
+    // operands live in uniform registers (issued from inside `if (lane == 0)` every UTCHMMA / UTCBAR sat in an ELECT + R2UR +
+    // branch loop: ~40 cycles apiece, 9 MMAs per chunk at level 3).
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+    const int n_long_u = __shfl_sync(0xffffffffu, n_long, 0);
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t bhi0 = tc_smem(&S.Bhi[0][0]), blo0 = tc_smem(&S.Blo[0][0]);
     int it = 0;
-    for (int i = blockIdx.x; i < n_long; i += gridDim.x) {
-      const int4 ge = load_seg_entry(p.glist + i);
-      const int nch = (ge.y + KC3 - 1) / KC3;
+    for (int i = blockIdx.x; i < n_long_u; i += gridDim.x) {
+      const int nch = (__shfl_sync(0xffffffffu, load_seg_entry(p.glist + i).y, 0) + KC3 - 1) / KC3;
       for (int c = 0; c < nch; ++c, ++it) {
         const int stage = it % TC_NST;
         TC_T(ma)
@@ -373,18 +379,23 @@ __global__ void __launch_bounds__(TcCfg<LV>::THREADS, 1) k_acc_tc(const __grid_c
         TC_T(mb)
         TC_ADD(6, ma, mb)
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint64_t bh = tc_desc(tc_smem(&S.Bhi[stage][0]), TC_N * 16, 128);
-        const uint64_t bl = tc_desc(tc_smem(&S.Blo[stage][0]), TC_N * 16, 128);
+        const uint64_t bh = tc_desc(bhi0 + stage * (Cfg::B_WORDS * 4), TC_N * 16, 128);
+        const uint64_t bl = tc_desc(blo0 + stage * (Cfg::B_WORDS * 4), TC_N * 16, 128);
+        uint32_t elected;
+        asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(elected));
+        if (elected) {
 #pragma unroll
-        for (int t = 0; t < TILES; ++t) {
-          const uint32_t ah = tmem + TC_ACOL + (stage * TILES + t) * 16, al = ah + 8;
-          const uint32_t d = tmem + t * TC_N;
-          tc_mma_ts(d, ah, bh, idesc, c > 0);
-          tc_mma_ts(d, ah, bl, idesc, 1);
-          tc_mma_ts(d, al, bh, idesc, 1);
+          for (int t = 0; t < TILES; ++t) {
+            const uint32_t ah = tmem_u + TC_ACOL + (stage * TILES + t) * 16, al = ah + 8;
+            const uint32_t d = tmem_u + t * TC_N;
+            tc_mma_ts(d, ah, bh, idesc, c > 0);
+            tc_mma_ts(d, ah, bl, idesc, 1);
+            tc_mma_ts(d, al, bh, idesc, 1);
+          }
+          tc_commit(&S.empty[stage]);                    // the stage may be refilled once these MMAs have read it
+          if (c == nch - 1) tc_commit(&S.accfull);       // the segment's accumulator is complete
         }
-        tc_commit(&S.empty[stage]);                    // the stage may be refilled once these MMAs have read it
-        if (c == nch - 1) tc_commit(&S.accfull);       // the segment's accumulator is complete
+        __syncwarp();
         TC_T(mc)
         TC_ADD(7, mb, mc)
       }
@@ -406,10 +417,10 @@ void host_tc_split(float a, uint32_t* hi, uint32_t* lo) { tc_split(a, *hi, *lo);
 static int g_tc_override = -1;      // ddk_debug_set_tc: -1 = follow the environment
 int tc_set_override(int on) { const int prev = g_tc_override; g_tc_override = on; return prev; }
 
-// DDK_TC: 0 = FFMA2 kernels only (k_conv_fused), 1 = k_conv_fused + k_acc_tc for the long lig<-rec segments (round-1 path),
-// 2 = k_conv_tcr: every accumulation on the tensor cores, contraction from tensor memory (default)
+// DDK_TC: 0 = FFMA2 kernels only (k_conv_fused), 1 = k_conv_fused + k_acc_tc for the long lig<-rec segments (default: the fastest
+// measured), 2 = k_conv_tcr: every accumulation on the tensor cores, contraction from tensor memory, no scratch round trip
 int conv_path() {
-  static const int env = getenv("DDK_TC") == nullptr ? 2 : atoi(getenv("DDK_TC"));
+  static const int env = getenv("DDK_TC") == nullptr ? 1 : atoi(getenv("DDK_TC"));
   const int v = g_tc_override < 0 ? env : g_tc_override;
   return v < 0 ? 0 : (v > 2 ? 2 : v);
 }

@@ -89,7 +89,7 @@ __device__ __forceinline__ void tc_mbar_wait_sleep(unsigned long long* b, uint32
   asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                : "=r"(ok) : "r"(tc_smem(b)), "r"(parity) : "memory");
   while (!ok) {
-    __nanosleep(64);
+    __nanosleep(200);
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(ok) : "r"(tc_smem(b)), "r"(parity) : "memory");
   }

@@ -191,10 +191,10 @@ int ddk_group_totals(DdkCtx* ctx, int64_t* edges, int64_t* segments);   /* cumul
                                                           list ([DDK_WORK_LISTS] each): edge groups 0 lig-lig, 1 lig<-rec, 2 rec-rec,
                                                           3 rec<-lig, and 4 + h = group 2 restricted to the residues within h
                                                           receptor-contact hops of a residue with a cross edge; all steps (sync) */
-/* Process-wide run-time choice of the conv-layer kernels (same meaning as the DDK_TC environment variable): 2 = k_conv_tcr, every
- * outer-product accumulation as 3xTF32 tcgen05.mma with the contraction from tensor memory (default); 1 = the round-1 pair
- * k_conv_fused (FFMA2) + k_acc_tc (long lig<-rec segments on the tensor cores); 0 = k_conv_fused only (all fp32 FMA: the
- * strictest rounding, for ill-conditioned trajectories); -1 = follow the environment again.  Takes effect at the next
+/* Process-wide run-time choice of the conv-layer kernels (same meaning as the DDK_TC environment variable): 1 = k_conv_fused
+ * (FFMA2) + k_acc_tc (the long lig<-rec segments as 3xTF32 tcgen05.mma) -- the default, fastest measured; 2 = k_conv_tcr, EVERY
+ * outer-product accumulation as 3xTF32 tcgen05.mma with the contraction straight from tensor memory (no scratch round trip);
+ * 0 = k_conv_fused only (all fp32 FMA: the strictest rounding, for ill-conditioned trajectories); -1 = follow the environment again.  Takes effect at the next
  * ddk_set_batch.  Returns the previous override.  Parity tests run the trajectories in every mode. */
 int ddk_debug_set_tc(int32_t on);
 int ddk_debug_read(DdkCtx* ctx, const char* name, void* dst_h, size_t max_bytes, size_t* n_bytes);

@@ -213,12 +213,13 @@ def run_inference_sharded(complexes: Sequence, model, model_args, device, t_to_s
                           inference_steps=20, actual_steps=None, seed=0, rank: Optional[int] = None, world: Optional[int] = None,
                           poses_per_call=400, no_torsion=None, no_random=False, no_final_step_noise=False, ode=False,
                           temp_sampling=1.0, temp_psi=0.0, temp_sigma_data=0.5, host_buffers=True, broadcast_weights=True,
-                          gather=True, sampler=None) -> Dict[str, object]:
+                          gather=True, sampler=None, **sampling_kw) -> Dict[str, object]:
     """``samples_per_complex`` poses for every complex, the (complex, sample) poses sharded over the ranks of the process group
     (one process per GPU; evaluate.py:219-400 is the single-process loop this replaces).  One broadcast of the weights, then no
     communication until ONE all-gather of the final poses; ranks take contiguous pose ranges balanced by N_l * N_r
     (``dist.shard_poses``).  Start poses and noise are keyed by (seed, complex, sample), and a pose's trajectory does not depend
-    on what it is batched with (tests), so the result is bit-identical for every world size.
+    on what it is batched with (tests), so the result is bit-identical for every world size.  Extra keyword arguments (``ar_model``,
+    ``classifier_free_guidance_weight``, ``cfg_start`` ... of the DisCo path) are handed to ``sampling()``.
 
     Returns ``{'names', 'ligand_pos': [per complex: tensor [samples, N_l, 3]], 'shard': [(complex, first, stop)], 'run_time'}``;
     with ``gather=False`` (or on ranks > 0 when the backend cannot gather) only the rank's own poses are filled in."""
@@ -269,7 +270,7 @@ def run_inference_sharded(complexes: Sequence, model, model_args, device, t_to_s
         sampler(data_list=flat, model=model, inference_steps=steps, tr_schedule=schedule, rot_schedule=schedule,
                 tor_schedule=schedule, device=device, t_to_sigma=t_to_sigma, model_args=model_args, no_random=no_random, ode=ode,
                 batch_size=len(flat), no_final_step_noise=no_final_step_noise, temp_sampling=temp_sampling, temp_psi=temp_psi,
-                temp_sigma_data=temp_sigma_data, noise=noise, host_buffers=host_buffers)
+                temp_sigma_data=temp_sigma_data, noise=noise, host_buffers=host_buffers, **sampling_kw)
         i = 0
         for ci, a, b in call:
             for k in range(a, b):

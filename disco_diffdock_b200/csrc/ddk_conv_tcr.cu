@@ -402,10 +402,15 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
       const int set = warp >> 2, rt = (warp & 3) * 32 + lane;
       const TcRow rd = R.rows[rt];
       const bool plain = __all_sync(0xffffffffu, rd.type == 0);
-      const int i1 = rd.type == 0 ? rd.i0 : rd.i0 + 1, i2 = rd.type == 0 ? rd.i0 : rd.i0 + 2;
-      const float w_t0 = rd.type == 0 ? 1.f : 0.f, w_dt = rd.type == 1 ? 1.f : 0.f;
-      const float w_c1 = (rd.type == 2 && rd.m == 1) ? 1.f : 0.f, w_c2 = (rd.type == 2 && rd.m == 2) ? 1.f : 0.f,
-                  w_c3 = (rd.type == 2 && rd.m == 3) ? 1.f : 0.f;
+      // every basis row is  x[ia] sh[ma] + sb x[ib] sh[mb] + sc x[ic] sh[mc]:  plain product (sb = sc = 0), dot product of a
+      // 3-vector with the l = 1 harmonics (sb = sc = 1), or one component of their cross product (sb = -1, sc = 0)
+      int ia = rd.i0, ma = rd.m, ib = rd.i0, mb = 0, ic = rd.i0, mc = 0;
+      float sb = 0.f, sc = 0.f;
+      if (rd.type == 1) { ma = 1; ib = rd.i0 + 1; mb = 2; ic = rd.i0 + 2; mc = 3; sb = 1.f; sc = 1.f; }
+      if (rd.type == 2) {
+        const int a = rd.m % 3, c2 = (rd.m + 1) % 3;          // component m - 1 = x[a'] s[b'] - x[b'] s[a'] with (a', b') cyclic
+        ia = rd.i0 + a; ma = 1 + c2; ib = rd.i0 + c2; mb = 1 + a; sb = -1.f;
+      }
       // B operand work items of this thread: item w = (row n = w % (nj + 1) of the tile, half hk = w / (nj + 1) of the 8 edges)
       const int nb_items = 2 * (nj + 1);
       int bn[2], bh[2];
@@ -415,35 +420,41 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
         bn[b2] = w < nb_items ? w % (nj + 1) : -1;
         bh[b2] = w < nb_items ? w / (nj + 1) : 0;
       }
+      // chunk counters kept incrementally (no division per chunk): ph = it mod 3 (whose chunk), buf = it mod 6 (ring slot),
+      // rp = (it / 6) & 1 (ring phase), sp = (it / 3) & 1 (phase of this set's operand stage)
+      int ph = it % TR_NSETS, buf = it % TR_XR, rp = (it / TR_XR) & 1, sp = (it / TR_NST) & 1;
+      const int stage = set;
       for (int i = 0; i < nseg; ++i) {
         const int n = S.seg_n[i];
         const int nch = (n + KC3 - 1) / KC3;
         for (int c = 0; c < nch; ++c, ++it) {
-          if (it % TR_NSETS != set) continue;
+          const bool mine = ph == set;
+          const int buf_c = buf, rp_c = rp, sp_c = sp;
+          if (++ph == TR_NSETS) { ph = 0; sp ^= 1; }
+          if (++buf == TR_XR) { buf = 0; rp ^= 1; }
+          if (!mine) continue;
           const int kc = min(KC3, n - c * KC3);
-          const int buf = it % TR_XR, stage = set;
           TR_T(ra)
-          tc_mbar_wait(&S.sfull[buf], (it / TR_XR) & 1);
+          tc_mbar_wait(&S.sfull[buf_c], rp_c);
           TR_T(rb)
-          tc_mbar_wait(&S.empty[stage], ((it / TR_NST) & 1) ^ 1);
+          tc_mbar_wait(&S.empty[stage], sp_c ^ 1);
           TR_T(rc)
           TR_ADD(0, ra, rb) TR_ADD(1, rb, rc)
           float b[KC3];
           if (plain) {
             float xv[KC3], sv[KC3];
 #pragma unroll
-            for (int e = 0; e < KC3; ++e) { xv[e] = S.X[buf][e][rd.i0]; sv[e] = S.SH[buf][e][rd.m]; }
+            for (int e = 0; e < KC3; ++e) { xv[e] = S.X[buf_c][e][rd.i0]; sv[e] = S.SH[buf_c][e][rd.m]; }
 #pragma unroll
             for (int e = 0; e < KC3; ++e) b[e] = xv[e] * sv[e];
           } else {
 #pragma unroll
             for (int e = 0; e < KC3; ++e) {
-              const float4 s4 = *reinterpret_cast<const float4*>(&S.SH[buf][e][0]);
-              const float v0 = S.X[buf][e][rd.i0], v1 = S.X[buf][e][i1], v2 = S.X[buf][e][i2];
-              const float t0 = v0 * S.SH[buf][e][rd.m];
-              float dt = v0 * s4.y; dt = fmaf(v1, s4.z, dt); dt = fmaf(v2, s4.w, dt);
-              const float c1 = fmaf(v1, s4.w, -(v2 * s4.z)), c2 = fmaf(v2, s4.y, -(v0 * s4.w)), c3 = fmaf(v0, s4.z, -(v1 * s4.y));
-              b[e] = w_t0 * t0 + w_dt * dt + w_c1 * c1 + w_c2 * c2 + w_c3 * c3;
+              const float* xr = &S.X[buf_c][e][0];
+              const float* sr = &S.SH[buf_c][e][0];
+              float r = xr[ia] * sr[ma];
+              r = fmaf(sb * xr[ib], sr[mb], r);
+              b[e] = fmaf(sc * xr[ic], sr[mc], r);
             }
           }
           {
@@ -464,7 +475,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
               if (nrow < nj) {
 #pragma unroll
                 for (int qd = 0; qd < 4; ++qd) {
-                  const float hld = S.HS[buf][4 * hk + qd][nrow];
+                  const float hld = S.HS[buf_c][4 * hk + qd][nrow];
                   tc_split_rn(4 * hk + qd < kc ? hld : 0.f, h[qd], l[qd]);      // rows of absent edges hold stale (finite) data
                 }
               } else {                                                           // the ones row -> Bsum
@@ -476,7 +487,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
             }
           }
           __syncwarp();
-          if (lane == 0) tc_mbar_arrive(&S.sempty[buf]);
+          if (lane == 0) tc_mbar_arrive(&S.sempty[buf_c]);
           TR_T(rd_)
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -128,6 +128,9 @@ __device__ __forceinline__ void tr_ld8(uint32_t taddr, uint32_t (&v)[8]) {
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr));
 }
 
+__device__ __forceinline__ void tr_ld2(uint32_t taddr, uint32_t (&v)[2]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(v[0]), "=r"(v[1]) : "r"(taddr));
+}
 __device__ __forceinline__ void tr_ld4(uint32_t taddr, uint32_t (&v)[4]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr));
@@ -140,7 +143,8 @@ __device__ __forceinline__ void tr_ld4(uint32_t taddr, uint32_t (&v)[4]) {
 template <int LV, bool VEC>
 __device__ __forceinline__ void tr_con_group(const TrArgs& p, TrSmem<LV>& S, const float* __restrict__ Wsl, const uint32_t tmem,
                                              const int sg, const int nvalid, const int seg0, const int g_edge, const int role_id,
-                                             const int cw, const int q, const int lane, const int ct, const int gi) {
+                                             const int cw, const int q, const int lane, const int ct, const int gi,
+                                             long long* dbgp = nullptr) {
   constexpr int G = VEC ? TR_GV : TR_GS, NACC = 2 * G;
   constexpr int O = VEC ? 6 : 24;                              // outputs per basis row; every thread computes 6 of them
   const TcrRole& R = S.role;
@@ -158,6 +162,9 @@ __device__ __forceinline__ void tr_con_group(const TrArgs& p, TrSmem<LV>& S, con
     tc_mbar_wait_sleep(&S.accfull[slot], (s / NACC) & 1);
   }
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#if DDK_TCR_TRACE
+  const long long tp0 = clock64();
+#endif
   tr_f32x2 acc[G][3];
 #pragma unroll
   for (int g = 0; g < G; ++g)
@@ -165,35 +172,48 @@ __device__ __forceinline__ void tr_con_group(const TrArgs& p, TrSmem<LV>& S, con
     for (int k = 0; k < 3; ++k) acc[g][k] = 0ull;
   const float* wrow = Wsl + (active ? R.woff[32 * q + lane] : 0) + o0;
   const uint32_t tlane = tmem + ((uint32_t)(32 * q) << 16);
-  constexpr int CW = VEC ? 8 : 4;                            // accumulator columns per load (4 segments x 4 in scalar roles)
-  for (int cb = c0; cb < c1; cb += CW) {
-    uint32_t v[G][CW];
+  constexpr int CW = VEC ? 8 : 2;                            // accumulator columns per load (4 segments x 2 in scalar roles: registers)
+  // software pipeline over the column blocks: the tensor-memory loads of block i + 1 are in flight while block i is multiplied
+  // (tcgen05.ld + wait took ~1500 cycles per block when they were issued back to back with their use)
+  uint32_t v[2][G][CW];
+  auto issue = [&](int cb, uint32_t (&dst)[G][CW]) {
 #pragma unroll
     for (int g = 0; g < G; ++g)
       if (g < nvalid) {
-        if constexpr (VEC) tr_ld8(tlane + ((sg + g) % NACC) * N + cb, v[g]);
-        else tr_ld4(tlane + ((sg + g) % NACC) * N + cb, v[g]);
+        if constexpr (VEC) tr_ld8(tlane + ((sg + g) % NACC) * N + cb, dst[g]);
+        else tr_ld2(tlane + ((sg + g) % NACC) * N + cb, dst[g]);
       }
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    if (active) {
+  };
+  auto compute = [&](int cb, const uint32_t (&src)[G][CW]) {
+    if (!active) return;
 #pragma unroll
-      for (int jj = 0; jj < CW; ++jj) {
-        const int col = cb + jj;
-        if (col < c1) {
-          const float* w = wrow + col * O;
-          tr_f32x2 wv[3];
+    for (int jj = 0; jj < CW; ++jj) {
+      const int col = cb + jj;
+      if (col < c1) {
+        const float* w = wrow + col * O;
+        tr_f32x2 wv[3];
 #pragma unroll
-          for (int k = 0; k < 3; ++k) wv[k] = *reinterpret_cast<const tr_f32x2*>(w + 2 * k);
+        for (int k = 0; k < 3; ++k) wv[k] = *reinterpret_cast<const tr_f32x2*>(w + 2 * k);
 #pragma unroll
-          for (int g = 0; g < G; ++g)
-            if (g < nvalid) {
-              const float a = __uint_as_float(v[g][jj]);
-              const tr_f32x2 aa = tr_pack2(a, a);
+        for (int g = 0; g < G; ++g)
+          if (g < nvalid) {
+            const float a = __uint_as_float(src[g][jj]);
+            const tr_f32x2 aa = tr_pack2(a, a);
 #pragma unroll
-              for (int k = 0; k < 3; ++k) tr_ffma2(acc[g][k], aa, wv[k]);
-            }
-        }
+            for (int k = 0; k < 3; ++k) tr_ffma2(acc[g][k], aa, wv[k]);
+          }
       }
+    }
+  };
+  issue(c0, v[0]);
+  for (int cb = c0; cb < c1; cb += 2 * CW) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");           // block cb has landed in v[0]
+    if (cb + CW < c1) issue(cb + CW, v[1]);
+    compute(cb, v[0]);
+    if (cb + CW < c1) {
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");         // block cb + CW has landed in v[1]
+      if (cb + 2 * CW < c1) issue(cb + 2 * CW, v[0]);
+      compute(cb + CW, v[1]);
     }
   }
   // every accumulator value this thread needs is in registers: the slots may be refilled
@@ -203,6 +223,9 @@ __device__ __forceinline__ void tr_con_group(const TrArgs& p, TrSmem<LV>& S, con
 #pragma unroll
     for (int g = 0; g < G; ++g) tc_mbar_arrive(&S.accempty[(sg + g) % NACC]);
   }
+#if DDK_TCR_TRACE
+  const long long tp1 = clock64();
+#endif
   // ---- partial outputs of the rows -> RED[g][h][row][o]
   constexpr int H = VEC ? 2 : 1, RR = VEC ? 128 : 64;
   if (active) {
@@ -231,11 +254,19 @@ __device__ __forceinline__ void tr_con_group(const TrArgs& p, TrSmem<LV>& S, con
     if (g < nvalid) {
       const int F = R.rgF[rg];
       const int f0 = (part * F) / np, f1 = ((part + 1) * F) / np;
+      // four independent partial sums in a fixed order: the loads of a row are not chained behind the previous addition
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
       for (int h = 0; h < H; ++h) {
         const float* base = &S.RED[((g * H + h) * RR) * O + o];
-        for (int f = f0; f < f1; ++f) s += base[R.rgrow[rg][f] * O];
+        const short* rr = &R.rgrow[rg][0];
+        int f = f0;
+        for (; f + 3 < f1; f += 4) {
+          s0 += base[rr[f] * O]; s1 += base[rr[f + 1] * O]; s2 += base[rr[f + 2] * O]; s3 += base[rr[f + 3] * O];
+        }
+        for (; f < f1; ++f) s0 += base[rr[f] * O];
       }
+      s = (s0 + s1) + (s2 + s3);
     }
     red2[ct] = s;
   }
@@ -254,6 +285,9 @@ __device__ __forceinline__ void tr_con_group(const TrArgs& p, TrSmem<LV>& S, con
       p.part[((size_t)sid * p.nroles + role_id) * D + f] = v;
     }
   }
+#if DDK_TCR_TRACE
+  if (dbgp) { const int k0 = VEC ? 3 : 5; dbgp[k0] += tp1 - tp0; dbgp[k0 + 1] += clock64() - tp1; dbgp[7] += VEC ? 1 : 0; }
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------- the kernel
@@ -498,6 +532,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
           TR_ADD(2, rc, rd_) TR_ADD(3, rd_, re)
 #if DDK_TCR_TRACE
           dbgacc[4] += 1;
+          if (vec) { dbgacc[5] += 1; dbgacc[6] += rd_ - rc; }
 #endif
         }
       }
@@ -630,8 +665,13 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
         }
         const long long cb_ = clock64();
 #endif
+#if DDK_TCR_TRACE
+        if (vec) tr_con_group<LV, true>(p, S, Wsl, tmem, sg, nvalid, grp * G, 0, role_id, cw, q, lane, ct, gcount, dbgacc);
+        else tr_con_group<LV, false>(p, S, Wsl, tmem, sg, nvalid, grp * G, 0, role_id, cw, q, lane, ct, gcount, dbgacc);
+#else
         if (vec) tr_con_group<LV, true>(p, S, Wsl, tmem, sg, nvalid, grp * G, 0, role_id, cw, q, lane, ct, gcount);
         else tr_con_group<LV, false>(p, S, Wsl, tmem, sg, nvalid, grp * G, 0, role_id, cw, q, lane, ct, gcount);
+#endif
 #if DDK_TCR_TRACE
         dbgacc[1] += clock64() - cb_; dbgacc[2] += 1;
 #endif
@@ -644,10 +684,10 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
 #if DDK_TCR_TRACE
   if (p.dbg) {
     long long* o = p.dbg + (size_t)blockIdx.x * 32;
-    if (tid == 0) { for (int k = 0; k < 5; ++k) o[k] = dbgacc[k]; o[5] = clock64() - tk0; o[6] = n_tasks; o[7] = n_reload; o[8] = t_reload; }
+    if (tid == 0) { for (int k = 0; k < 5; ++k) o[k] = dbgacc[k]; o[5] = clock64() - tk0; o[6] = n_tasks; o[7] = n_reload; o[8] = t_reload; o[26] = dbgacc[5]; o[27] = dbgacc[6]; }
     if (tid == TR_W_MMA * 32) for (int k = 0; k < 3; ++k) o[10 + k] = dbgacc[k];
     if (tid == TR_W_GATHER * 32) for (int k = 0; k < 2; ++k) o[14 + k] = dbgacc[k];
-    if (tid == TR_W_CON * 32) for (int k = 0; k < 3; ++k) o[18 + k] = dbgacc[k];
+    if (tid == TR_W_CON * 32) for (int k = 0; k < 8; ++k) o[18 + k] = dbgacc[k];
   }
 #endif
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -856,9 +896,11 @@ void launch_conv_tcr(DdkCtx* c, int layer, const float* x_in, float* x_out, cuda
     for (int b = 0; b < grid; ++b) for (int k = 0; k < 32; ++k) s_[k] += (double)h[(size_t)b * 32 + k] / grid;
     fprintf(stderr, "[tcr_trace] layer %d lv %d mode %d kcycles per CTA: total %.0f, tasks %.1f, reloads %.1f (%.0f) | row warp 0 (set 0): chunks %.0f, "
                     "wait staging %.0f, wait stage %.0f, operands %.0f, fences %.0f | mma: wait slot %.0f, wait operands %.0f, issue %.0f | "
-                    "gather: wait ring %.0f, issue %.0f | contraction warp 0: wait acc %.0f, groups %.0f (%.0f)\n",
+                    "gather: wait ring %.0f, issue %.0f | contraction warp 0: wait acc %.0f, groups %.0f (%.0f) | vector roles: %.0f groups, fma %.0f, "
+                    "reduce %.0f; scalar roles: fma %.0f, reduce %.0f | row warp 0 in vector roles: chunks %.0f, operands %.0f\n",
             layer, li.lv, mode, s_[5] / 1e3, s_[6], s_[7], s_[8] / 1e3, s_[4], s_[0] / 1e3, s_[1] / 1e3, s_[2] / 1e3, s_[3] / 1e3,
-            s_[10] / 1e3, s_[11] / 1e3, s_[12] / 1e3, s_[14] / 1e3, s_[15] / 1e3, s_[18] / 1e3, s_[19] / 1e3, s_[20]);
+            s_[10] / 1e3, s_[11] / 1e3, s_[12] / 1e3, s_[14] / 1e3, s_[15] / 1e3, s_[18] / 1e3, s_[19] / 1e3, s_[20],
+            s_[25], s_[21] / 1e3, s_[22] / 1e3, s_[23] / 1e3, s_[24] / 1e3, s_[26], s_[27] / 1e3);
   }
 #endif
   launch_conv_finalize(c, layer, x_in, x_out, st, lig_only, nroles);

@@ -172,16 +172,16 @@ __device__ __forceinline__ void tr_con_group(const TrArgs& p, TrSmem<LV>& S, con
     for (int k = 0; k < 3; ++k) acc[g][k] = 0ull;
   const float* wrow = Wsl + (active ? R.woff[32 * q + lane] : 0) + o0;
   const uint32_t tlane = tmem + ((uint32_t)(32 * q) << 16);
-  constexpr int CW = VEC ? 8 : 2;                            // accumulator columns per load (4 segments x 2 in scalar roles: registers)
+  constexpr int CW = VEC ? 8 : 4;                            // accumulator columns per load (4 segments x 4 in scalar roles)
   // software pipeline over the column blocks: the tensor-memory loads of block i + 1 are in flight while block i is multiplied
   // (tcgen05.ld + wait took ~1500 cycles per block when they were issued back to back with their use)
-  uint32_t v[2][G][CW];
+  uint32_t v[VEC ? 2 : 1][G][CW];                            // scalar roles (4 segments per group) have no registers for a second block
   auto issue = [&](int cb, uint32_t (&dst)[G][CW]) {
 #pragma unroll
     for (int g = 0; g < G; ++g)
       if (g < nvalid) {
         if constexpr (VEC) tr_ld8(tlane + ((sg + g) % NACC) * N + cb, dst[g]);
-        else tr_ld2(tlane + ((sg + g) % NACC) * N + cb, dst[g]);
+        else tr_ld4(tlane + ((sg + g) % NACC) * N + cb, dst[g]);
       }
   };
   auto compute = [&](int cb, const uint32_t (&src)[G][CW]) {
@@ -205,15 +205,23 @@ __device__ __forceinline__ void tr_con_group(const TrArgs& p, TrSmem<LV>& S, con
       }
     }
   };
-  issue(c0, v[0]);
-  for (int cb = c0; cb < c1; cb += 2 * CW) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");           // block cb has landed in v[0]
-    if (cb + CW < c1) issue(cb + CW, v[1]);
-    compute(cb, v[0]);
-    if (cb + CW < c1) {
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");         // block cb + CW has landed in v[1]
-      if (cb + 2 * CW < c1) issue(cb + 2 * CW, v[0]);
-      compute(cb + CW, v[1]);
+  if constexpr (VEC) {
+    issue(c0, v[0]);
+    for (int cb = c0; cb < c1; cb += 2 * CW) {
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");           // block cb has landed in v[0]
+      if (cb + CW < c1) issue(cb + CW, v[1]);
+      compute(cb, v[0]);
+      if (cb + CW < c1) {
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");         // block cb + CW has landed in v[1]
+        if (cb + 2 * CW < c1) issue(cb + 2 * CW, v[0]);
+        compute(cb + CW, v[1]);
+      }
+    }
+  } else {
+    for (int cb = c0; cb < c1; cb += CW) {
+      issue(cb, v[0]);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      compute(cb, v[0]);
     }
   }
   // every accumulator value this thread needs is in registers: the slots may be refilled

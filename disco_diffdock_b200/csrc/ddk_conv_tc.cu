@@ -60,15 +60,8 @@ template <int LV>
 struct TcSmem {
   alignas(128) uint32_t Bhi[TC_NST][TcCfg<LV>::B_WORDS];
   alignas(128) uint32_t Blo[TC_NST][TcCfg<LV>::B_WORDS];
-#if DDK_TC_TRANSPOSED
-  // EXPERIMENT (not validated on the GPU yet): feature-major staging, the 8 edges of a chunk contiguous,
-  // rows padded to 12 floats so that the 16-byte loads of 8 consecutive lanes fall into distinct bank groups
-  alignas(16) float X[TC_XR][TcCfg<LV>::DINP][12];
-  alignas(16) float SH[TC_XR][4][12];
-#else
   alignas(16) float X[TC_XR][KC3][TcCfg<LV>::DINP];
   alignas(16) float SH[TC_XR][KC3][4];
-#endif
   alignas(16) float HS[TC_XR][HID / TcCfg<LV>::J][KC3 * TcCfg<LV>::J + 8];   // [slice][edge * J + jj] as k_edge_hidden stores them;
                                                                         // 8 floats of padding per slice: the B-operand reads of a
                                                                         // warp span 4 slices at the same (edge, jj)
@@ -167,32 +160,6 @@ __global__ void __launch_bounds__(TcCfg<LV>::THREADS, 1) k_acc_tc(const __grid_c
         TC_ADD(0, ta, tb) TC_ADD(1, tb, tc_)
         // ---- basis values of the 8 edges for this row (branch-free, the 8 edges are independent instruction streams)
         float b[KC3];
-#if DDK_TC_TRANSPOSED
-        {
-          auto ld8 = [](const float* q, float (&o)[KC3]) {
-            const float4 a = *reinterpret_cast<const float4*>(q), c = *reinterpret_cast<const float4*>(q + 4);
-            o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = c.x; o[5] = c.y; o[6] = c.z; o[7] = c.w;
-          };
-          float x0[KC3], sm[KC3];
-          ld8(&S.X[buf][rd.i0][0], x0); ld8(&S.SH[buf][rd.m][0], sm);
-          if (plain) {
-#pragma unroll
-            for (int e = 0; e < KC3; ++e) b[e] = x0[e] * sm[e];
-          } else {
-            float x1[KC3], x2[KC3], sy[KC3], sz[KC3], sw[KC3];
-            ld8(&S.X[buf][i1][0], x1); ld8(&S.X[buf][i2][0], x2);
-            ld8(&S.SH[buf][1][0], sy); ld8(&S.SH[buf][2][0], sz); ld8(&S.SH[buf][3][0], sw);
-#pragma unroll
-            for (int e = 0; e < KC3; ++e) {
-              const float t0 = x0[e] * sm[e];
-              float dt = x0[e] * sy[e]; dt = fmaf(x1[e], sz[e], dt); dt = fmaf(x2[e], sw[e], dt);
-              const float c1 = fmaf(x1[e], sw[e], -(x2[e] * sz[e])), c2 = fmaf(x2[e], sy[e], -(x0[e] * sw[e])),
-                          c3 = fmaf(x0[e], sz[e], -(x1[e] * sy[e]));
-              b[e] = w_t0 * t0 + w_dt * dt + w_c1 * c1 + w_c2 * c2 + w_c3 * c3;
-            }
-          }
-        }
-#else
         if (plain) {
           float xv[KC3], sv[KC3];
 #pragma unroll
@@ -211,7 +178,6 @@ __global__ void __launch_bounds__(TcCfg<LV>::THREADS, 1) k_acc_tc(const __grid_c
             b[e] = w_t0 * t0 + w_dt * dt + w_c1 * c1 + w_c2 * c2 + w_c3 * c3;
           }
         }
-#endif
         {
           uint32_t hi[KC3], lo[KC3];
 #pragma unroll
@@ -318,21 +284,6 @@ __global__ void __launch_bounds__(TcCfg<LV>::THREADS, 1) k_acc_tc(const __grid_c
         if (gw == 0 && lane < KC3 && c + 1 < nch) ent_next = p.seg_list[pos0 + KC3 + min(lane, n - (c + 1) * KC3 - 1)];
         tc_mbar_wait(&S.sempty[buf], ((it / TC_XR) & 1) ^ 1);                          // every row warp has read the buffer's old content
         if (gw == 0) {
-#if DDK_TC_TRANSPOSED
-          constexpr int NP = KC3 * DINP + KC3 * 4;      // 4-byte pieces (feature i, edge e), then (harmonic m, edge e)
-#pragma unroll 4
-          for (int k = 0; k < (NP + 31) / 32; ++k) {    // uniform trip count: the shuffles need the whole warp
-            const int q0 = lane + 32 * k;
-            const bool on = q0 < NP, isx = q0 < KC3 * DINP;
-            const int qq = !on ? 0 : (isx ? q0 : q0 - KC3 * DINP), i = qq / KC3, e = qq % KC3;
-            const int es = min(e, kc - 1);
-            const int slot = __shfl_sync(0xffffffffu, ent.x, es), dst = __shfl_sync(0xffffffffu, ent.y, es);
-            if (on) {
-              if (isx) __pipeline_memcpy_async(&S.X[buf][i][e], p.x + (size_t)dst * D + i, 4);
-              else __pipeline_memcpy_async(&S.SH[buf][i][e], reinterpret_cast<const float*>(p.sh_pool + slot) + i, 4);
-            }
-          }
-#else
           constexpr int NP = KC3 * XQ + KC3;            // 16-byte pieces: feature rows, then one harmonics record per edge
 #pragma unroll
           for (int k = 0; k < (NP + 31) / 32; ++k) {    // uniform trip count: the shuffles need the whole warp
@@ -346,7 +297,6 @@ __global__ void __launch_bounds__(TcCfg<LV>::THREADS, 1) k_acc_tc(const __grid_c
               else __pipeline_memcpy_async(&S.SH[buf][e][0], p.sh_pool + slot, 16);
             }
           }
-#endif
         } else {
           constexpr int PJ = J / 4;                     // 16-byte pieces per (slice, edge)
           for (int q0 = lane; q0 < NSL * KC3 * PJ; q0 += 32) {

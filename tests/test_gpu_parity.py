@@ -473,3 +473,30 @@ def test_sharded_inference_is_bit_identical_to_unsharded():
     dump('sharded_inference', {'max_abs_diff_vs_unsharded': diffs, 'rmsd_vs_oracle': rmsd.tolist()})
     assert max(diffs.values()) == 0.0, diffs
     assert float(rmsd.max()) < 1e-3, rmsd
+
+
+def test_sampling_large_receptor_through_late_sparse_steps():
+    """BASELINE config 5 shape (2000 C-alpha residues, 120-atom ligand, dynamic cross cut-off) through the reverse-diffusion loop at
+    LATE times: t = 0.3, 0.2, 0.1 give a cross cut-off of 21.4 .. 20.6 A, so only a fraction of the receptor is listed (sparse cross
+    graph, empty cross segments, receptor-contact hops of the needed-residue sets) -- against the oracle on the same noise."""
+    from functools import partial
+    m, sd, cfg = helpers.make_model(4, gain=2.0)
+    m = m.to('cuda')
+    B, steps = 2, 3
+    g, lst = helpers.make_pose_batch(33, 120, 2000, B)
+    R = g['ligand'].mask_rotate.shape[0]
+    noise = helpers.draw_noise(13, steps, B, R)
+    sched = np.array([0.3, 0.2, 0.1])
+    data_list = [synthetic.as_loader_item(x) for x in copy.deepcopy(lst)]
+    out, _ = dsampling.sampling(data_list, m, steps, sched, sched, sched, torch.device('cuda'), partial(du.t_to_sigma, args=cfg), cfg,
+                                batch_size=B, noise=noise, **helpers.README_TEMPS)
+    got = torch.cat([x['ligand'].pos.cpu() for x in out])
+    eng = m.engine()
+    edges_last = eng.last_edge_count()
+    batch = ddata.Batch.from_data_list(copy.deepcopy(lst))
+    with torch.no_grad():
+        want = restate.sample(sd, cfg, batch, load_tables(), sched, noise, inference_steps=steps, **helpers.README_TEMPS)
+    rmsd = helpers.rmsd_per_pose(want, got, B)
+    dump('large_receptor_sparse_steps', {'rmsd': rmsd.tolist(), 'edges_last_step': edges_last, 'all_pairs_would_be': 2 * B * 120 * 2000})
+    assert edges_last < 0.5 * 2 * B * 120 * 2000                     # the cross graph is sparse at these times
+    assert float(rmsd.max()) < 1e-3, rmsd

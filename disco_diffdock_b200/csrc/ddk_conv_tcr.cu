@@ -154,8 +154,8 @@ __device__ __forceinline__ void tr_con_group(const TrArgs& p, TrSmem<LV>& S, con
   // quarter (the accumulator rows are duplicated by the row warps), and (warp set, lane half) selects 6 of its 24 outputs.
   const int rrow = VEC ? 32 * q + lane : 16 * q + (lane & 15);          // row index in RED / in the role's row groups
   const bool active = VEC ? rrow < R.nrows : rrow < R.ndist;
-  int c0 = 0, c1 = ncol, o0 = 0;
-  if (VEC) { c0 = set ? 40 : 0; c1 = set ? ncol : min(40, ncol); } else { o0 = 12 * set + 6 * (lane >> 4); }
+  int c0 = 0, o0 = 0;
+  if (VEC) c0 = set ? 40 : 0; else o0 = 12 * set + 6 * (lane >> 4);
 #pragma unroll
   for (int g = 0; g < G; ++g) {
     const int s = sg + g, slot = s % NACC;
@@ -173,55 +173,55 @@ __device__ __forceinline__ void tr_con_group(const TrArgs& p, TrSmem<LV>& S, con
   const float* wrow = Wsl + (active ? R.woff[32 * q + lane] : 0) + o0;
   const uint32_t tlane = tmem + ((uint32_t)(32 * q) << 16);
   constexpr int CW = VEC ? 8 : 4;                            // accumulator columns per load (4 segments x 4 in scalar roles)
-  // software pipeline over the column blocks: the tensor-memory loads of block i + 1 are in flight while block i is multiplied
-  // (tcgen05.ld + wait took ~1500 cycles per block when they were issued back to back with their use)
+  // The hot loop has no predicates: every block is full (accumulator columns >= ncol are exact zeros -- the B rows behind the
+  // ones row are zeroed at every role change -- and the weight slice is padded with zeros behind its last block), and the
+  // slots of absent segments (g >= nvalid, last group of a task) are read and multiplied like the others; their results are
+  // never stored.  (With `if (g < nvalid)` / `if (col < c1)` inside, every FFMA2 came with two predicated moves.)
+  const int nblk = VEC ? 5 : (ncol + CW - 1) / CW;           // vector roles: 40 columns per warp set
   uint32_t v[VEC ? 2 : 1][G][CW];                            // scalar roles (4 segments per group) have no registers for a second block
   auto issue = [&](int cb, uint32_t (&dst)[G][CW]) {
 #pragma unroll
-    for (int g = 0; g < G; ++g)
-      if (g < nvalid) {
-        if constexpr (VEC) tr_ld8(tlane + ((sg + g) % NACC) * N + cb, dst[g]);
-        else tr_ld4(tlane + ((sg + g) % NACC) * N + cb, dst[g]);
-      }
+    for (int g = 0; g < G; ++g) {
+      if constexpr (VEC) tr_ld8(tlane + ((sg + g) % NACC) * N + cb, dst[g]);
+      else tr_ld4(tlane + ((sg + g) % NACC) * N + cb, dst[g]);
+    }
   };
   auto compute = [&](int cb, const uint32_t (&src)[G][CW]) {
-    if (!active) return;
+    const float* w = wrow + cb * O;
 #pragma unroll
     for (int jj = 0; jj < CW; ++jj) {
-      const int col = cb + jj;
-      if (col < c1) {
-        const float* w = wrow + col * O;
-        tr_f32x2 wv[3];
+      tr_f32x2 wv[3];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) wv[k] = *reinterpret_cast<const tr_f32x2*>(w + 2 * k);
+      for (int k = 0; k < 3; ++k) wv[k] = *reinterpret_cast<const tr_f32x2*>(w + jj * O + 2 * k);
 #pragma unroll
-        for (int g = 0; g < G; ++g)
-          if (g < nvalid) {
-            const float a = __uint_as_float(src[g][jj]);
-            const tr_f32x2 aa = tr_pack2(a, a);
+      for (int g = 0; g < G; ++g) {
+        const float a = __uint_as_float(src[g][jj]);
+        const tr_f32x2 aa = tr_pack2(a, a);
 #pragma unroll
-            for (int k = 0; k < 3; ++k) tr_ffma2(acc[g][k], aa, wv[k]);
-          }
+        for (int k = 0; k < 3; ++k) tr_ffma2(acc[g][k], aa, wv[k]);
       }
     }
   };
   if constexpr (VEC) {
     issue(c0, v[0]);
-    for (int cb = c0; cb < c1; cb += 2 * CW) {
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");           // block cb has landed in v[0]
-      if (cb + CW < c1) issue(cb + CW, v[1]);
+#pragma unroll 1
+    for (int bk = 0; bk < nblk; bk += 2) {
+      const int cb = c0 + bk * CW;
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");           // block bk has landed in v[0]
+      if (bk + 1 < nblk) issue(cb + CW, v[1]);
       compute(cb, v[0]);
-      if (cb + CW < c1) {
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");         // block cb + CW has landed in v[1]
-        if (cb + 2 * CW < c1) issue(cb + 2 * CW, v[0]);
+      if (bk + 1 < nblk) {
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");         // block bk + 1 has landed in v[1]
+        if (bk + 2 < nblk) issue(cb + 2 * CW, v[0]);
         compute(cb + CW, v[1]);
       }
     }
   } else {
-    for (int cb = c0; cb < c1; cb += CW) {
-      issue(cb, v[0]);
+#pragma unroll 1
+    for (int bk = 0; bk < nblk; ++bk) {
+      issue(bk * CW, v[0]);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      compute(cb, v[0]);
+      compute(bk * CW, v[0]);
     }
   }
   // every accumulator value this thread needs is in registers: the slots may be refilled
@@ -417,6 +417,20 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       }
       sg = 0;
+      {
+        // B rows [ncol, N) of every stage are exact zeros for this role (a previous role with another tile width may have left
+        // hidden units there): the accumulator columns behind the ones column are then zeros, which the contraction relies on
+        const int ncol_r = src->ncol, N_r = src->N;
+        const int nz = (N_r - ncol_r) * 2 * TR_NST * 2;          // rows x k-halves x stages x (hi, lo)
+        for (int i = tid; i < nz * 4; i += TR_THREADS) {
+          const int wd = i & 3; int r = i >> 2;
+          const int row = ncol_r + r % (N_r - ncol_r); r /= (N_r - ncol_r);
+          const int hk = r & 1; r >>= 1;
+          const int stg = r % TR_NST, hl = r / TR_NST;
+          (hl ? S.Blo : S.Bhi)[stg][(row + N_r * hk) * 4 + wd] = 0u;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      }
       tc_mbar_wait_sleep(&S.bar_w, nwl & 1);
       ++nwl;
       __syncthreads();
@@ -783,7 +797,7 @@ int build_tcr_roles(int lv, const LayerInfo& li, TcrRole* roles) {
       for (int d = 0; d < nd; ++d) { R.rows[d] = drow[d]; R.woff[d] = dwoff[d]; }
       R.nrows = nd;
     }
-    R.wfloats = (wblocks * R.wstride + 3) / 4 * 4;
+    R.wfloats = (wblocks * R.wstride + 8 * R.O + 3) / 4 * 4;     // + one block of 8 columns of zeros: the contraction reads full blocks
     if (R.wfloats > TCR_WMAX) return -1;
     // row groups (class, component) and the output columns they feed; rgrow = index of the row in RED (distinct-row index)
     for (int f = 0; f < D; ++f) R.outsrc[f] = -1;

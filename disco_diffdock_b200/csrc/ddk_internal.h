@@ -71,7 +71,7 @@ constexpr int TC_MIN_CHUNKS = 8;            // segments with at least this many 
 // tensor-core conv with resident contraction (ddk_conv_tcr.cu): a ROLE = (irrep classes, range of hidden units) of a basis level
 constexpr int TCR_MAXROLES = 5;     // roles per level
 constexpr int TCR_MAXACC = 8;       // accumulator slots in tensor memory
-constexpr int TCR_WMAX = 36240;     // floats of the largest resident weight slice (level 3, scalar classes, 24 hidden units + bias)
+constexpr int TCR_WMAX = 36240 + 192;     // floats of the largest resident weight slice (level 3, scalar classes, 24 hidden units + bias)
 constexpr int TCR_MAXRG = 6;        // row groups (class, component) per role
 constexpr int TCR_MAXF = 36;        // rows per row group
 struct alignas(16) TcrRole {

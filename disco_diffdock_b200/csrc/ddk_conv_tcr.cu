@@ -42,7 +42,7 @@ namespace ddk {
 
 constexpr int TR_NSETS = 3;          // row-warp sets: set s produces the operands of chunks it = s (mod 3) -- three chunks in flight
 constexpr int TR_NST = TR_NSETS;     // operand stages (A in tensor memory, B in shared memory): one per set
-constexpr int TR_XR = 6;             // staging ring of the gather warp
+constexpr int TR_XR = 10;            // staging ring of the gather warps (even: they take alternate chunks)
 constexpr int TR_ROWW = 4;           // row warps per set = one 128-row tile
 constexpr int TR_CONW = 8;           // contraction warps
 constexpr int TR_W_MMA = TR_NSETS * TR_ROWW, TR_W_GATHER = TR_W_MMA + 1, TR_W_CON = TR_W_MMA + 4;   // warps 12 | 13 | 16..23
@@ -50,12 +50,10 @@ constexpr int TR_THREADS = (TR_W_CON + TR_CONW) * 32;   // 768 (warps 14, 15 idl
 constexpr int TR_COLS = 512;         // tensor-memory columns allocated
 constexpr int TR_ACOL = 448;         // A operand stages: TR_NST x (8 hi + 8 lo) columns from here; accumulator slots below
 constexpr int TR_NMAX = 80;          // widest MMA N
-constexpr int TR_BAR_CON = 1;        // named barrier of the contraction warps
 constexpr int TR_GV = 2, TR_GS = 4;  // segments contracted together: vector roles / scalar roles
-constexpr int TR_RED_FLOATS = 6144;  // partial outputs of a group: max(G_V * 2 halves * 128 rows * 6, G_S * 64 rows * 24)
-constexpr int TR_RED2 = 256;
 constexpr int TR_MAXSEG = 256;       // segments per task
-constexpr int TR_PF = 4;             // chunks the gather warp fetches list entries ahead
+constexpr int TR_PF = 4;             // chunks per batch of prefetched list entries (TR_PF * KC3 = one warp)
+static_assert(TR_PF * KC3 == 32, "a batch of prefetched list entries is one warp wide");
 
 struct TrArgs {
   int NL, N;
@@ -88,8 +86,6 @@ struct TrSmem {
   alignas(16) float X[TR_XR][KC3][TrCfg<LV>::DINP];                     // destination feature rows of the chunk's edges
   alignas(16) float SH[TR_XR][KC3][4];
   alignas(16) float HS[TR_XR][KC3][HID];                                // the role's hidden units of each edge (first nj floats)
-  alignas(16) float RED[TR_RED_FLOATS];
-  alignas(16) float RED2[2][TR_RED2];
   alignas(16) TcrRole role;                                             // the resident role's tables
   alignas(8) unsigned long long full[TR_NST], empty[TR_NST];            // operand stages: row warps <-> MMA thread
   alignas(8) unsigned long long sfull[TR_XR], sempty[TR_XR];            // staging ring: gather warps <-> row warps
@@ -109,7 +105,6 @@ struct TrSmem {
 #define TR_ADD(slot, a, b)
 #endif
 
-__device__ __forceinline__ void tr_bar_con() { asm volatile("bar.sync %0, %1;" ::"n"(TR_BAR_CON), "n"(TR_CONW * 32) : "memory"); }
 
 typedef unsigned long long tr_f32x2;
 __device__ __forceinline__ void tr_ffma2(tr_f32x2& d, const tr_f32x2 a, const tr_f32x2 b) {
@@ -143,8 +138,7 @@ __device__ __forceinline__ void tr_ld4(uint32_t taddr, uint32_t (&v)[4]) {
 template <int LV, bool VEC>
 __device__ __forceinline__ void tr_con_group(const TrArgs& p, TrSmem<LV>& S, const float* __restrict__ Wsl, const uint32_t tmem,
                                              const int sg, const int nvalid, const int seg0, const int g_edge, const int role_id,
-                                             const int cw, const int q, const int lane, const int ct, const int gi,
-                                             long long* dbgp = nullptr) {
+                                             const int cw, const int q, const int lane, long long* dbgp = nullptr) {
   constexpr int G = VEC ? TR_GV : TR_GS, NACC = 2 * G;
   constexpr int O = VEC ? 6 : 24;                              // outputs per basis row; every thread computes 6 of them
   const TcrRole& R = S.role;
@@ -152,8 +146,7 @@ __device__ __forceinline__ void tr_con_group(const TrArgs& p, TrSmem<LV>& S, con
   const int set = cw >> 2;                                    // warp set 0 / 1
   // VEC: lane = basis row, the two warp sets split the columns.  Scalar roles: every row sits in lanes l and l + 16 of its
   // quarter (the accumulator rows are duplicated by the row warps), and (warp set, lane half) selects 6 of its 24 outputs.
-  const int rrow = VEC ? 32 * q + lane : 16 * q + (lane & 15);          // row index in RED / in the role's row groups
-  const bool active = VEC ? rrow < R.nrows : rrow < R.ndist;
+  const bool active = R.rows[32 * q + lane].u >= 0;
   int c0 = 0, o0 = 0;
   if (VEC) c0 = set ? 40 : 0; else o0 = 12 * set + 6 * (lane >> 4);
 #pragma unroll
@@ -234,63 +227,55 @@ __device__ __forceinline__ void tr_con_group(const TrArgs& p, TrSmem<LV>& S, con
 #if DDK_TCR_TRACE
   const long long tp1 = clock64();
 #endif
-  // ---- partial outputs of the rows -> RED[g][h][row][o]
-  constexpr int H = VEC ? 2 : 1, RR = VEC ? 128 : 64;
-  if (active) {
+  // ---- sum over the basis rows inside the warp, by shuffles in a fixed order; no other warp is involved: the warp writes
+  // its own share of the (segment, role) partial record and k_conv_finalize_tcr adds the shares (TcrRole::fsrc).
+  float r[G][6];
 #pragma unroll
-    for (int g = 0; g < G; ++g)
-      if (g < nvalid) {
-        float* r = &S.RED[(((g * H) + (VEC ? set : 0)) * RR + rrow) * O + o0];
+  for (int g = 0; g < G; ++g)
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          float a0, a1;
-          tr_unpack2(acc[g][k], a0, a1);
-          r[2 * k] = a0; r[2 * k + 1] = a1;
-        }
-      }
-  }
-  tr_bar_con();
-  // ---- stage 1: thread (g, row group rg = (class, component), output o, part) adds its share of the group's rows
-  const int nrg = R.nrg, np = R.np, nout = nrg * O;
-  float* red2 = &S.RED2[gi & 1][0];
-  if (ct < G * nout * np) {
-    const int part = ct % np;
-    int rest = ct / np;
-    const int o = rest % O; rest /= O;
-    const int rg = rest % nrg, g = rest / nrg;
-    float s = 0.f;
-    if (g < nvalid) {
-      const int F = R.rgF[rg];
-      const int f0 = (part * F) / np, f1 = ((part + 1) * F) / np;
-      // four independent partial sums in a fixed order: the loads of a row are not chained behind the previous addition
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-      for (int h = 0; h < H; ++h) {
-        const float* base = &S.RED[((g * H + h) * RR) * O + o];
-        const short* rr = &R.rgrow[rg][0];
-        int f = f0;
-        for (; f + 3 < f1; f += 4) {
-          s0 += base[rr[f] * O]; s1 += base[rr[f + 1] * O]; s2 += base[rr[f + 2] * O]; s3 += base[rr[f + 3] * O];
-        }
-        for (; f < f1; ++f) s0 += base[rr[f] * O];
-      }
-      s = (s0 + s1) + (s2 + s3);
+    for (int k = 0; k < 3; ++k) {
+      tr_unpack2(acc[g][k], r[g][2 * k], r[g][2 * k + 1]);
+      if (!active) { r[g][2 * k] = 0.f; r[g][2 * k + 1] = 0.f; }     // padding rows evaluate x[0] * sh[0] against block 0
     }
-    red2[ct] = s;
-  }
-  tr_bar_con();
-  // ---- stage 2: the 84-wide partial row of (segment, role): owned columns from the sums, zeros elsewhere
-  for (int t2 = ct; t2 < G * D; t2 += TR_CONW * 32) {
-    const int g = t2 / D, f = t2 % D;
-    if (g < nvalid) {
-      const int src = R.outsrc[f];
-      float v = 0.f;
-      if (src >= 0) {
-        const float* b = red2 + (g * nout + src) * np;
-        for (int k = 0; k < np; ++k) v += b[k];
-      }
-      const int sid = S.seg_id[seg0 + g];
-      p.part[((size_t)sid * p.nroles + role_id) * D + f] = v;
+  if constexpr (VEC) {
+    // the three components of a basis row sit in neighbouring lanes and every class starts at a warp boundary: the rows
+    // that feed one (component, output) are the lanes of one residue mod 3 -> lanes 0, 1, 2 end with the warp's sums
+#pragma unroll
+    for (int delta = 24; delta >= 3; delta >>= 1) {
+#pragma unroll
+      for (int g = 0; g < G; ++g)
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          const float t = __shfl_down_sync(0xffffffffu, r[g][k], delta);
+          if (lane + delta < 32) r[g][k] += t;
+        }
+    }
+    if (lane < 3) {
+#pragma unroll
+      for (int g = 0; g < G; ++g)
+        if (g < nvalid) {
+          float* dst = p.part + ((size_t)S.seg_id[seg0 + g] * p.nroles + role_id) * TCR_PS + (cw * 3 + lane) * 6;
+#pragma unroll
+          for (int k = 0; k < 3; ++k) *reinterpret_cast<float2*>(dst + 2 * k) = make_float2(r[g][2 * k], r[g][2 * k + 1]);
+        }
+    }
+  } else {
+    // lane = 16 h + l: row 16 q + l, outputs 12 set + 6 h + (0..5); the 16 rows of a quarter belong to one class
+#pragma unroll
+    for (int delta = 8; delta >= 1; delta >>= 1) {
+#pragma unroll
+      for (int g = 0; g < G; ++g)
+#pragma unroll
+        for (int k = 0; k < 6; ++k) r[g][k] += __shfl_xor_sync(0xffffffffu, r[g][k], delta);
+    }
+    if ((lane & 15) == 0) {
+#pragma unroll
+      for (int g = 0; g < G; ++g)
+        if (g < nvalid) {
+          float* dst = p.part + ((size_t)S.seg_id[seg0 + g] * p.nroles + role_id) * TCR_PS + (cw * 2 + (lane >> 4)) * 6;
+#pragma unroll
+          for (int k = 0; k < 3; ++k) *reinterpret_cast<float2*>(dst + 2 * k) = make_float2(r[g][2 * k], r[g][2 * k + 1]);
+        }
     }
   }
 #if DDK_TCR_TRACE
@@ -341,7 +326,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
     // operand tiles and staging rings start as zeros: the bulk copies of a partial chunk leave the rows of absent edges as they
     // are (their hidden units are masked to 0 in the B operand, so whatever FINITE values they hold contribute nothing)
     uint32_t* z = &S.Bhi[0][0];
-    constexpr int nz = (int)((offsetof(TrSmem<LV>, RED) - offsetof(TrSmem<LV>, Bhi)) / 4);
+    constexpr int nz = (int)((offsetof(TrSmem<LV>, role) - offsetof(TrSmem<LV>, Bhi)) / 4);
     for (int i = tid; i < nz; i += TR_THREADS) z[i] = 0u;
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -355,10 +340,16 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
   const long long tk0 = clock64();
   long long t_reload = 0, n_tasks = 0, n_reload = 0;
 #endif
-  int it = 0;        // 8-edge chunks so far (gather / row warps / MMA thread count the same sequence)
+  // Chunk bookkeeping.  Every warp role walks the chunks of the CTA's tasks in the same order; chunk number `it` (never
+  // materialised) belongs to row set it % 3, gather warp it % 2, operand stage it % 3 and ring slot it % TR_XR.  A row set / gather
+  // warp steps straight from one of its chunks to the next (`skip` = offset of its first chunk in the next task) and keeps the
+  // ring slot, ring phase and stage phase of that chunk incrementally; the MMA warp visits every chunk.
+  int skip = 0, buf = 0, bph = 0, sph = 0;
+  if (warp < TR_W_MMA) { skip = warp >> 2; buf = skip % TR_XR; }
+  else if (warp == TR_W_GATHER || warp == TR_W_GATHER + 1) { skip = warp - TR_W_GATHER; buf = skip; }
+  int mstage = 0, mph = 0;   // MMA warp: operand stage and its phase
   int sg = 0;        // accumulator slots so far (MMA thread / contraction warps); a multiple of the group size between tasks
   int nwl = 0;       // weight-slice loads so far
-  int gcount = 0;    // contraction groups so far
 
   for (;;) {
     // ---- claim a task: (combo, block of segments); stay on the resident combo while it has work
@@ -403,7 +394,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
       {
         const int4* s4 = reinterpret_cast<const int4*>(src);
         int4* d4 = reinterpret_cast<int4*>(&S.role);
-        static_assert(sizeof(TcrRole) % 16 == 0, "role tables are copied in 16-byte pieces");
+        static_assert(sizeof(TcrRole) % 16 == 0 && offsetof(TcrRole, fsrc) % 16 == 0 && TCR_MAXSRC == 8, "role tables are copied in 16-byte pieces");
         for (int i = tid; i < (int)(sizeof(TcrRole) / 16); i += TR_THREADS) d4[i] = __ldg(s4 + i);
       }
       // the accumulator-slot ring depends on the role kind (4 slots of 80 columns / 8 slots of 32 or 48): every pipeline is
@@ -476,26 +467,22 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
         bn[b2] = w < nb_items ? w % (nj + 1) : -1;
         bh[b2] = w < nb_items ? w / (nj + 1) : 0;
       }
-      // chunk counters kept incrementally (no division per chunk): ph = it mod 3 (whose chunk), buf = it mod 6 (ring slot),
-      // rp = (it / 6) & 1 (ring phase), sp = (it / 3) & 1 (phase of this set's operand stage)
-      int ph = it % TR_NSETS, buf = it % TR_XR, rp = (it / TR_XR) & 1, sp = (it / TR_NST) & 1;
       const int stage = set;
-      for (int i = 0; i < nseg; ++i) {
-        const int n = S.seg_n[i];
-        const int nch = (n + KC3 - 1) / KC3;
-        for (int c = 0; c < nch; ++c, ++it) {
-          const bool mine = ph == set;
-          const int buf_c = buf, rp_c = rp, sp_c = sp;
-          if (++ph == TR_NSETS) { ph = 0; sp ^= 1; }
-          if (++buf == TR_XR) { buf = 0; rp ^= 1; }
-          if (!mine) continue;
-          const int kc = min(KC3, n - c * KC3);
+      int i = 0, c = skip, nch = (S.seg_n[0] + KC3 - 1) / KC3;
+      auto norm = [&]() {
+        while (i < nseg && c >= nch) { c -= nch; ++i; nch = i < nseg ? (S.seg_n[i] + KC3 - 1) / KC3 : 0; }
+      };
+      norm();
+      while (i < nseg) {
+        {
+          const int buf_c = buf, rp_c = bph, sp_c = sph;
+          const int kc = min(KC3, S.seg_n[i] - c * KC3);
           TR_T(ra)
           tc_mbar_wait(&S.sfull[buf_c], rp_c);
           TR_T(rb)
-          tc_mbar_wait(&S.empty[stage], sp_c ^ 1);
-          TR_T(rc)
-          TR_ADD(0, ra, rb) TR_ADD(1, rb, rc)
+          // everything that only READS the staged chunk happens before the wait for the operand stage: the basis values, the B
+          // rows of this thread and their TF32 splits sit in registers when the MMA warp releases the stage, and only the stores
+          // remain on the stage's critical loop (release -> stores -> fences -> MMA of this chunk)
           float b[KC3];
           if (plain) {
             float xv[KC3], sv[KC3];
@@ -513,10 +500,30 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
               b[e] = fmaf(sc * xr[ic], sr[mc], r);
             }
           }
-          {
-            uint32_t hi[KC3], lo[KC3];
+          uint32_t hi[KC3], lo[KC3];
 #pragma unroll
-            for (int e = 0; e < KC3; ++e) tc_split_rn(b[e], hi[e], lo[e]);
+          for (int e = 0; e < KC3; ++e) tc_split_rn(b[e], hi[e], lo[e]);
+          uint32_t bh_[2][4], bl_[2][4];
+#pragma unroll
+          for (int b2 = 0; b2 < 2; ++b2) {
+            const int nrow = bn[b2], hk = bh[b2];
+#pragma unroll
+            for (int qd = 0; qd < 4; ++qd) { bh_[b2][qd] = 4 * hk + qd < kc ? 0x3f800000u : 0u; bl_[b2][qd] = 0u; }   // the ones row -> Bsum
+            if (nrow >= 0 && nrow < nj) {
+#pragma unroll
+              for (int qd = 0; qd < 4; ++qd) {
+                const float hld = S.HS[buf_c][4 * hk + qd][nrow];
+                tc_split_rn(4 * hk + qd < kc ? hld : 0.f, bh_[b2][qd], bl_[b2][qd]);   // rows of absent edges hold stale (finite) data
+              }
+            }
+          }
+          __syncwarp();
+          if (lane == 0) tc_mbar_arrive(&S.sempty[buf_c]);      // the ring slot is free again
+          TR_T(rb2)
+          tc_mbar_wait(&S.empty[stage], sp_c ^ 1);
+          TR_T(rc)
+          TR_ADD(0, ra, rb) TR_ADD(1, rb2, rc)
+          {
             const uint32_t ta = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + TR_ACOL + stage * 16;
             asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                          ::"r"(ta), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]), "r"(hi[4]), "r"(hi[5]), "r"(hi[6]), "r"(hi[7]) : "memory");
@@ -527,23 +534,10 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
           for (int b2 = 0; b2 < 2; ++b2) {
             const int nrow = bn[b2], hk = bh[b2];
             if (nrow >= 0) {
-              uint32_t h[4], l[4];
-              if (nrow < nj) {
-#pragma unroll
-                for (int qd = 0; qd < 4; ++qd) {
-                  const float hld = S.HS[buf_c][4 * hk + qd][nrow];
-                  tc_split_rn(4 * hk + qd < kc ? hld : 0.f, h[qd], l[qd]);      // rows of absent edges hold stale (finite) data
-                }
-              } else {                                                           // the ones row -> Bsum
-#pragma unroll
-                for (int qd = 0; qd < 4; ++qd) { h[qd] = 4 * hk + qd < kc ? 0x3f800000u : 0u; l[qd] = 0u; }
-              }
-              *reinterpret_cast<uint4*>(&S.Bhi[stage][(nrow + N * hk) * 4]) = make_uint4(h[0], h[1], h[2], h[3]);
-              *reinterpret_cast<uint4*>(&S.Blo[stage][(nrow + N * hk) * 4]) = make_uint4(l[0], l[1], l[2], l[3]);
+              *reinterpret_cast<uint4*>(&S.Bhi[stage][(nrow + N * hk) * 4]) = make_uint4(bh_[b2][0], bh_[b2][1], bh_[b2][2], bh_[b2][3]);
+              *reinterpret_cast<uint4*>(&S.Blo[stage][(nrow + N * hk) * 4]) = make_uint4(bl_[b2][0], bl_[b2][1], bl_[b2][2], bl_[b2][3]);
             }
           }
-          __syncwarp();
-          if (lane == 0) tc_mbar_arrive(&S.sempty[buf_c]);
           TR_T(rd_)
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -551,13 +545,18 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
           __syncwarp();
           if (lane == 0) tc_mbar_arrive(&S.full[stage]);
           TR_T(re)
-          TR_ADD(2, rc, rd_) TR_ADD(3, rd_, re)
+          TR_ADD(2, rb, rb2) TR_ADD(2, rc, rd_) TR_ADD(3, rd_, re)
 #if DDK_TCR_TRACE
           dbgacc[4] += 1;
-          if (vec) { dbgacc[5] += 1; dbgacc[6] += rd_ - rc; }
+          if (vec) { dbgacc[5] += 1; dbgacc[6] += (rb2 - rb) + (rd_ - rc); }
 #endif
         }
+        buf += TR_NSETS; if (buf >= TR_XR) { buf -= TR_XR; bph ^= 1; }
+        sph ^= 1;
+        c += TR_NSETS;
+        norm();
       }
+      skip = c;
     } else if (warp == TR_W_MMA) {
       // ================================================================== MMA issue
       // The whole warp walks the chunks with warp-uniform values (shuffled from lane 0), and ONE elected lane issues the
@@ -572,6 +571,9 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
         asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
         return pred != 0;
       };
+      // descriptors of operand stage 0; stage s is TR_NMAX * 32 bytes further (the start-address field counts 16-byte units)
+      const uint64_t bhd0 = tc_desc(bhi0, N_u * 16, 128), bld0 = tc_desc(blo0, N_u * 16, 128);
+      constexpr uint32_t dstep = (TR_NMAX * 8 * 4) >> 4;
       for (int i = 0; i < nseg; ++i, ++sg) {
         const int nch = (__shfl_sync(0xffffffffu, S.seg_n[i], 0) + KC3 - 1) / KC3;
         const int slot = sg % NACC_u;
@@ -580,15 +582,14 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
         TR_T(mb)
         TR_ADD(0, ma, mb)
         const uint32_t d = tmem_u + slot * N_u;
-        for (int c = 0; c < nch; ++c, ++it) {
-          const int stage = it % TR_NST;
+        for (int c = 0; c < nch; ++c) {
+          const int stage = mstage;
           TR_T(mc)
-          tc_mbar_wait(&S.full[stage], (it / TR_NST) & 1);
+          tc_mbar_wait(&S.full[stage], mph);
           TR_T(md)
           TR_ADD(1, mc, md)
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint64_t bhd = tc_desc(bhi0 + stage * (TR_NMAX * 8 * 4), N_u * 16, 128);
-          const uint64_t bld = tc_desc(blo0 + stage * (TR_NMAX * 8 * 4), N_u * 16, 128);
+          const uint64_t bhd = bhd0 + stage * dstep, bld = bld0 + stage * dstep;
           const uint32_t ah = tmem_u + TR_ACOL + stage * 16, al = ah + 8;
           if (elect()) {
             tc_mma_ts(d, ah, bhd, idesc, c > 0);
@@ -598,6 +599,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
             if (c == nch - 1) tc_commit(&S.accfull[slot]);
           }
           __syncwarp();
+          if (++mstage == TR_NST) { mstage = 0; mph ^= 1; }
           TR_T(me)
           TR_ADD(2, md, me)
         }
@@ -617,40 +619,41 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
       const int e = lane >> 2, sub = lane & 3;
       constexpr int XQ = DINP / 4;
       const int hq = nj / 4;
-      // list entries (edge slot, destination node) are fetched TR_PF chunks ahead of their use: lane l < 8 keeps the entry of edge l
-      // of the next TR_PF chunks in registers, so the L2 latency of the entry loads never sits on the chunk's critical path
-      // the two gather warps take alternate chunks (gw = parity of the chunk counter); each prefetches the entries of ITS chunks
-      const int gw = warp - TR_W_GATHER;
-      int hi_ = 0, hc = 0, hit = it;                    // head of the prefetch stream: (segment, chunk, chunk counter)
-      auto head_load = [&]() {                          // the next chunk of this warp at or after the head
-        int2 v = make_int2(0, 0);
-        while (hi_ < nseg) {
-          const int n = S.seg_n[hi_], pos0 = S.seg_base[hi_] + hc * KC3;
-          const bool mine = (hit & 1) == gw;
-          if (mine && lane < KC3) v = __ldg(&p.seg_list[pos0 + min(lane, n - hc * KC3 - 1)]);
-          ++hit;
-          if (++hc * KC3 >= n) { ++hi_; hc = 0; }
-          if (mine) break;
+      // list entries (edge slot, destination node) are fetched a BATCH of TR_PF chunks at a time, one batch ahead: lane l holds the
+      // entry of edge l % 8 of the batch's chunk l / 8 (one coalesced load), and the chunk's lanes get theirs by shuffle.  The
+      // registers of a batch are touched again only TR_PF chunks after its load was issued -- a per-chunk register FIFO made
+      // every chunk wait for the load issued one chunk earlier (the rotating moves read the newest entry).
+      // The two gather warps take alternate chunks (gw = parity of the chunk counter); each prefetches the entries of ITS chunks.
+      int i = 0, c = skip, nch = (S.seg_n[0] + KC3 - 1) / KC3;
+      auto norm = [&](int& i_, int& c_, int& nch_) {
+        while (i_ < nseg && c_ >= nch_) { c_ -= nch_; ++i_; nch_ = i_ < nseg ? (S.seg_n[i_] + KC3 - 1) / KC3 : 0; }
+      };
+      norm(i, c, nch);
+      int hi_ = i, hc = c, hnch = nch;                  // head of the prefetch stream: this warp's next chunk not yet fetched
+      auto batch_load = [&]() {
+        int mypos = -1, myrem = 1;
+#pragma unroll
+        for (int b = 0; b < TR_PF; ++b) {
+          if (hi_ < nseg) {
+            if ((lane >> 3) == b) { mypos = S.seg_base[hi_] + hc * KC3; myrem = S.seg_n[hi_] - hc * KC3; }
+            hc += 2;
+            norm(hi_, hc, hnch);
+          }
         }
+        int2 v = make_int2(0, 0);
+        if (mypos >= 0) v = __ldg(&p.seg_list[mypos + min(lane & 7, myrem - 1)]);
         return v;
       };
-      int2 fifo[TR_PF];
-#pragma unroll
-      for (int k = 0; k < TR_PF; ++k) fifo[k] = head_load();
-      for (int i = 0; i < nseg; ++i) {
-        const int n = S.seg_n[i], base = S.seg_base[i];
-        const int nch = (n + KC3 - 1) / KC3;
-        for (int c = 0; c < nch; ++c, ++it) {
-          if ((it & 1) != gw) continue;
-          const int kc = min(KC3, n - c * KC3), pos0 = base + c * KC3;
-          const int buf = it % TR_XR;
-          const int2 ent = fifo[0];
-#pragma unroll
-          for (int k = 0; k + 1 < TR_PF; ++k) fifo[k] = fifo[k + 1];
-          fifo[TR_PF - 1] = head_load();
-          const int slot = __shfl_sync(0xffffffffu, ent.x, e), dst = __shfl_sync(0xffffffffu, ent.y, e);
+      int2 cur = batch_load(), nxt = batch_load();
+      int kb = 0;                                       // chunk of the current batch
+      while (i < nseg) {
+        {
+          const int n = S.seg_n[i];
+          const int kc = min(KC3, n - c * KC3), pos0 = S.seg_base[i] + c * KC3;
+          const int slot = __shfl_sync(0xffffffffu, cur.x, kb * KC3 + e), dst = __shfl_sync(0xffffffffu, cur.y, kb * KC3 + e);
+          if (++kb == TR_PF) { kb = 0; cur = nxt; nxt = batch_load(); }
           TR_T(ga)
-          tc_mbar_wait(&S.sempty[buf], ((it / TR_XR) & 1) ^ 1);
+          tc_mbar_wait(&S.sempty[buf], bph ^ 1);
           TR_T(gb)
           TR_ADD(0, ga, gb)
           if (e < kc) {                                 // rows of absent edges keep their stale (finite) content
@@ -671,13 +674,17 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
           TR_T(gc)
           TR_ADD(1, gb, gc)
         }
+        buf += 2; if (buf >= TR_XR) { buf -= TR_XR; bph ^= 1; }
+        c += 2;
+        norm(i, c, nch);
       }
+      skip = c;
       asm volatile("cp.async.wait_all;" ::: "memory");
     } else if (warp >= TR_W_CON) {
       // ================================================================== contraction warps
-      const int cw = warp - TR_W_CON, q = warp & 3, ct = cw * 32 + lane;    // TR_W_CON is a multiple of 4: q = cw & 3
+      const int cw = warp - TR_W_CON, q = warp & 3;    // TR_W_CON is a multiple of 4: q = cw & 3
       const int ngroups = (nseg + G - 1) / G;
-      for (int grp = 0; grp < ngroups; ++grp, sg += G, ++gcount) {
+      for (int grp = 0; grp < ngroups; ++grp, sg += G) {
         const int nvalid = min(G, nseg - grp * G);
 #if DDK_TCR_TRACE
         {                                             // time spent waiting for the group's accumulators (then the group itself)
@@ -688,19 +695,19 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
         const long long cb_ = clock64();
 #endif
 #if DDK_TCR_TRACE
-        if (vec) tr_con_group<LV, true>(p, S, Wsl, tmem, sg, nvalid, grp * G, 0, role_id, cw, q, lane, ct, gcount, dbgacc);
-        else tr_con_group<LV, false>(p, S, Wsl, tmem, sg, nvalid, grp * G, 0, role_id, cw, q, lane, ct, gcount, dbgacc);
+        if (vec) tr_con_group<LV, true>(p, S, Wsl, tmem, sg, nvalid, grp * G, 0, role_id, cw, q, lane, dbgacc);
+        else tr_con_group<LV, false>(p, S, Wsl, tmem, sg, nvalid, grp * G, 0, role_id, cw, q, lane, dbgacc);
 #else
-        if (vec) tr_con_group<LV, true>(p, S, Wsl, tmem, sg, nvalid, grp * G, 0, role_id, cw, q, lane, ct, gcount);
-        else tr_con_group<LV, false>(p, S, Wsl, tmem, sg, nvalid, grp * G, 0, role_id, cw, q, lane, ct, gcount);
+        if (vec) tr_con_group<LV, true>(p, S, Wsl, tmem, sg, nvalid, grp * G, 0, role_id, cw, q, lane);
+        else tr_con_group<LV, false>(p, S, Wsl, tmem, sg, nvalid, grp * G, 0, role_id, cw, q, lane);
 #endif
 #if DDK_TCR_TRACE
         dbgacc[1] += clock64() - cb_; dbgacc[2] += 1;
 #endif
       }
     }
-    // every thread keeps only the counters its own warp role uses (`it`: gather / row warps / MMA thread; `sg`: MMA thread /
-    // contraction warps) and advances them by walking the same task sequence, so they agree without any exchange
+    // every thread keeps only the counters its own warp role uses and advances them by walking the same task sequence, so the
+    // warp roles agree on chunk and slot numbers without any exchange
     __syncthreads();
   }
 #if DDK_TCR_TRACE
@@ -715,6 +722,44 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TR_COLS));
+}
+
+// ---------------------------------------------------------------------------------------------- finalize
+// Sum of the partial records of a node's two segments over the roles (a fixed order: segment, role, share), mean over the
+// node's edges, batch-norm affine, residual -- k_conv_finalize's arithmetic on k_conv_tcr's record layout.
+struct FinTcrArgs {
+  int N, dout, nroles;
+  const int* seg_cnt; const float* part; const TcrRole* roles;
+  const float* bn_scale; const float* bn_shift; const float* x_in; float* x_out;
+};
+
+__global__ void __launch_bounds__(256) k_conv_finalize_tcr(FinTcrArgs p) {
+  const int q = threadIdx.x / D, f = threadIdx.x % D;
+  if (q >= 3) return;
+  const int node = blockIdx.x * 3 + q;
+  if (node >= p.N) return;
+  const int cnt[2] = {p.seg_cnt[2 * node], p.seg_cnt[2 * node + 1]};
+  float v = 0.f;
+  if (f < p.dout) {
+    float s = 0.f;
+    for (int r = 0; r < p.nroles; ++r) {
+      const int4 t4 = __ldg(reinterpret_cast<const int4*>(&p.roles[r].fsrc[f][0]));
+      const int tw[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (cnt[h] <= 0) continue;
+        const float* rec = p.part + ((size_t)(2 * node + h) * p.nroles + r) * TCR_PS;
+#pragma unroll
+        for (int i = 0; i < TCR_MAXSRC; ++i) {
+          const int o = (short)((tw[i >> 1] >> (16 * (i & 1))) & 0xffff);
+          if (o >= 0) s += rec[o];
+        }
+      }
+    }
+    const float cn = fmaxf((float)(cnt[0] + cnt[1]), 1.f);
+    v = (s / cn) * p.bn_scale[f] + p.bn_shift[f] + p.x_in[(size_t)node * D + f];
+  }
+  p.x_out[(size_t)node * D + f] = v;
 }
 
 // ---------------------------------------------------------------------------------------------- host side
@@ -760,69 +805,81 @@ int build_tcr_roles(int lv, const LayerInfo& li, TcrRole* roles) {
     // 8-byte words, so that the 8-byte loads of lanes working on different blocks fall into different banks
     const int blk = R.ncol * R.O;
     R.wstride = blk % 4 == 2 ? blk : blk + 2;
-    // distinct rows: type-sorted (plain products first); in vector roles the three components of (class, f) in neighbouring lanes
+    // distinct rows: class-major (vector classes start at a multiple of 32 rows, scalar classes at a multiple of 16), inside a
+    // class type-sorted (plain products first) with the three components of (class, f) in neighbouring rows
+    const int align = sp.isS ? 16 : 32;
     int nd = 0, wblocks = 0;
-    std::vector<TcRow> drow(128);
-    std::vector<int> dwoff(128, 0);
-    std::vector<int> blk_of((size_t)li.ncls * 64, -1);
-    for (int k : sp.cls) for (int f = 0; f < li.cls[k].F; ++f) blk_of[(size_t)k * 64 + f] = wblocks++;
-    for (int pass = 0; pass < 3; ++pass)
-      for (int k : sp.cls) {
-        const ClassInfo& ci = li.cls[k];
+    std::vector<TcRow> drow(128, TcRow{0, 0, 0, -1});
+    std::vector<int> dwoff(128, 0), dcls(128, -1), dcomp(128, 0);
+    for (int k : sp.cls) {
+      const ClassInfo& ci = li.cls[k];
+      if (ci.O != R.O) return -1;
+      nd = (nd + align - 1) / align * align;
+      std::vector<int> blk_of(ci.F);
+      for (int f = 0; f < ci.F; ++f) blk_of[f] = wblocks++;
+      for (int pass = 0; pass < 3; ++pass)
         for (int f = 0; f < ci.F; ++f) {
           if (byu[ci.uoff + f].type != pass) continue;
           for (int c = 0; c < ci.ncomp; ++c) {
-            if (nd >= 128) return -1;
+            if (nd >= (sp.isS ? 64 : 128)) return -1;
             const int u = ci.uoff + c * ci.F + f;
             if (byu[u].type != pass) return -1;            // the components of a row share its type
-            drow[nd] = byu[u];
-            dwoff[nd] = blk_of[(size_t)k * 64 + f] * R.wstride;
+            drow[nd] = byu[u]; dwoff[nd] = blk_of[f] * R.wstride; dcls[nd] = k; dcomp[nd] = c;
             ++nd;
           }
         }
-      }
-    R.ndist = nd;
+    }
     for (int i = 0; i < 128; ++i) { R.rows[i] = TcRow{0, 0, 0, -1}; R.woff[i] = 0; }
+    std::vector<int> tcls(128, -1), tcomp(128, 0);           // (class, component) of every tile row
     if (sp.isS) {
-      // scalar roles: distinct row d = 16 q + l sits in lanes l and l + 16 of quarter q (tile rows 32 q + l and 32 q + 16 + l): the
-      // two copies of its accumulator row let (warp set, lane half) split its 24 outputs four ways without any shuffle
-      if (nd > 64) return -1;
       for (int d = 0; d < nd; ++d)
         for (int h = 0; h < 2; ++h) {
-          const int lane_row = 32 * (d / 16) + 16 * h + (d % 16);
-          R.rows[lane_row] = drow[d]; R.woff[lane_row] = dwoff[d];
+          const int t = 32 * (d / 16) + 16 * h + (d % 16);
+          R.rows[t] = drow[d]; R.woff[t] = dwoff[d]; tcls[t] = dcls[d];
         }
       R.nrows = 128;
     } else {
-      for (int d = 0; d < nd; ++d) { R.rows[d] = drow[d]; R.woff[d] = dwoff[d]; }
+      for (int d = 0; d < nd; ++d) { R.rows[d] = drow[d]; R.woff[d] = dwoff[d]; tcls[d] = dcls[d]; tcomp[d] = dcomp[d]; }
       R.nrows = nd;
     }
     R.wfloats = (wblocks * R.wstride + 8 * R.O + 3) / 4 * 4;     // + one block of 8 columns of zeros: the contraction reads full blocks
     if (R.wfloats > TCR_WMAX) return -1;
-    // row groups (class, component) and the output columns they feed; rgrow = index of the row in RED (distinct-row index)
-    for (int f = 0; f < D; ++f) R.outsrc[f] = -1;
-    int nrg = 0;
-    for (int k : sp.cls) {
-      const ClassInfo& ci = li.cls[k];
-      if (ci.O != R.O) return -1;
-      for (int c = 0; c < ci.ncomp; ++c) {
-        if (nrg >= TCR_MAXRG || ci.F > TCR_MAXF) return -1;
-        R.rgF[nrg] = ci.F;
-        for (int f = 0; f < ci.F; ++f) {
-          const int u = ci.uoff + c * ci.F + f;
-          int pos = -1;
-          for (int i = 0; i < nd; ++i) if (drow[i].u == u) pos = i;
-          if (pos < 0) return -1;
-          R.rgrow[nrg][f] = (short)pos;
+    // shares of every output column inside the partial record (see TcrRole)
+    for (int f = 0; f < D; ++f) for (int i = 0; i < TCR_MAXSRC; ++i) R.fsrc[f][i] = -1;
+    auto add_src = [&](int f, int idx) {
+      for (int i = 0; i < TCR_MAXSRC; ++i) if (R.fsrc[f][i] < 0) { R.fsrc[f][i] = (short)idx; return true; }
+      return false;
+    };
+    for (int cw = 0; cw < TR_CONW; ++cw) {
+      const int set = cw >> 2, q = cw & 3;
+      if (sp.isS) {
+        int k = -1;                                             // class of the quarter's rows
+        for (int l = 0; l < 16; ++l) {
+          const int kk = tcls[32 * q + l];
+          if (kk < 0) continue;
+          if (k >= 0 && kk != k) return -1;
+          k = kk;
         }
-        for (int o = 0; o < ci.O; ++o) R.outsrc[ci.col0 + (ci.ncomp == 3 ? 3 * o + c : o)] = (short)(nrg * R.O + o);
-        ++nrg;
+        if (k < 0) continue;
+        for (int h = 0; h < 2; ++h)
+          for (int o6 = 0; o6 < 6; ++o6)
+            if (!add_src(li.cls[k].col0 + 12 * set + 6 * h + o6, (cw * 2 + h) * 6 + o6)) return -1;
+      } else {
+        for (int l3 = 0; l3 < 3; ++l3) {
+          int k = -1, c = -1;                                   // (class, component) of the lanes = l3 (mod 3) of this warp
+          for (int l = l3; l < 32; l += 3) {
+            const int t = 32 * q + l;
+            if (tcls[t] < 0) continue;
+            if (k >= 0 && (tcls[t] != k || tcomp[t] != c)) return -1;
+            k = tcls[t]; c = tcomp[t];
+          }
+          if (k < 0) continue;
+          for (int o = 0; o < 6; ++o)
+            if (!add_src(li.cls[k].col0 + 3 * o + c, (cw * 3 + l3) * 6 + o)) return -1;
+        }
       }
     }
-    R.nrg = nrg;
     const int G = sp.isS ? TR_GS : TR_GV;
-    R.np = std::max(1, std::min(8, (TR_CONW * 32) / (G * nrg * R.O)));
-    if (G * nrg * R.O * R.np > TR_RED2 || G * (sp.isS ? 1 : 2) * (sp.isS ? 64 : 128) * R.O > TR_RED_FLOATS) return -1;
     if (2 * G > TCR_MAXACC || 2 * G * R.N > TR_ACOL) return -1;
   }
   return (int)specs.size();
@@ -925,7 +982,18 @@ void launch_conv_tcr(DdkCtx* c, int layer, const float* x_in, float* x_out, cuda
             s_[25], s_[21] / 1e3, s_[22] / 1e3, s_[23] / 1e3, s_[24] / 1e3, s_[26], s_[27] / 1e3);
   }
 #endif
-  launch_conv_finalize(c, layer, x_in, x_out, st, lig_only, nroles);
+  {
+    FinTcrArgs f;
+    f.N = lig_only ? c->NL : c->N; f.dout = li.dout; f.nroles = nroles;   // ligand nodes come first
+    f.seg_cnt = ptr<int>(c->b_seg_cnt);
+    f.part = ptr<float>(c->b_part);
+    f.roles = a.roles;
+    f.bn_scale = W(c, conv_id(layer, DDK_WL_BN_SCALE));
+    f.bn_shift = W(c, conv_id(layer, DDK_WL_BN_SHIFT));
+    f.x_in = x_in; f.x_out = x_out;
+    LaunchScope ls(c, PC_CONTRACT, st);
+    k_conv_finalize_tcr<<<(f.N + 2) / 3, 256, 0, st>>>(f);
+  }
 }
 
 // ---- host checks (callable without a GPU): every basis row of a level is owned by exactly one role row, the weight slices

@@ -72,8 +72,8 @@ constexpr int TC_MIN_CHUNKS = 8;            // segments with at least this many 
 constexpr int TCR_MAXROLES = 5;     // roles per level
 constexpr int TCR_MAXACC = 8;       // accumulator slots in tensor memory
 constexpr int TCR_WMAX = 36240 + 192;     // floats of the largest resident weight slice (level 3, scalar classes, 24 hidden units + bias)
-constexpr int TCR_MAXRG = 6;        // row groups (class, component) per role
-constexpr int TCR_MAXF = 36;        // rows per row group
+constexpr int TCR_PS = 144;         // floats of the partial record of one (segment, role): 8 contraction warps x 18
+constexpr int TCR_MAXSRC = 8;       // shares of one output column inside a record
 struct alignas(16) TcrRole {
   int nrows;                        // tile rows in use (<= 128)
   int ncol;                         // contracted accumulator columns: nj hidden units + the ones column (Bsum)
@@ -83,14 +83,17 @@ struct alignas(16) TcrRole {
   int O;                            // outputs per row: 6 (vector classes) or 24 (scalar classes)
   int isS;                          // scalar-class role
   int wstride, wfloats;             // floats of one (class, f) weight block incl. padding; floats of the whole slice
-  int nrg, np;                      // row groups; reduction parts per output
-  int ndist;                        // distinct basis rows (scalar roles hold every row twice: tile rows 32 q + l and 32 q + 16 + l)
-  int pad_[2];
+  int pad_[1];
+  // Tile rows.  Vector roles: the three components of a basis row (class, f) in neighbouring rows, every class starting at a
+  // multiple of 32 rows (one contraction warp never mixes classes).  Scalar roles: distinct row d = 16 q + l sits in tile rows
+  // 32 q + l and 32 q + 16 + l (both halves of a warp), every class starting at a multiple of 16 distinct rows.
   TcRow rows[128];                  // basis row evaluated by row thread p (u = -1: padding)
   int woff[128];                    // offset of row p's weight block inside the slice
-  short rgrow[TCR_MAXRG][TCR_MAXF]; // row threads of row group rg
-  int rgF[TCR_MAXRG];
-  short outsrc[D];                  // node-feature column f <- output rg * O + o of this role, or -1
+  // Partial record of a (segment, role), TCR_PS floats, written by the contraction warps (cw = 4 * set + quarter):
+  //   vector roles: [cw][lane 0..2][6 outputs]  -- lane l holds the sum over the warp's rows in lanes = l (mod 3);
+  //   scalar roles: [cw][lane half h][6]        -- outputs 12 set + 6 h + (0..5) summed over the 16 rows of the quarter.
+  // fsrc[f]: the record entries that add up to node-feature column f (ascending, -1 terminated), none if another role owns f.
+  short fsrc[D][TCR_MAXSRC];
 };
 static_assert(sizeof(TcrRole) % 16 == 0, "copied in 16-byte pieces");
 

@@ -42,7 +42,13 @@ namespace ddk {
 
 constexpr int TR_NSETS = 3;          // row-warp sets: set s produces the operands of chunks it = s (mod 3) -- three chunks in flight
 constexpr int TR_NST = TR_NSETS;     // operand stages (A in tensor memory, B in shared memory): one per set
-constexpr int TR_XR = 10;            // staging ring of the gather warps (even: they take alternate chunks)
+constexpr int TR_XR = 10;            // staging ring of the gather warps
+// Phase-parity waits are only safe while no waiter can run two phases ahead of its barrier.  Ring slot it % TR_XR is filled by
+// gather warp it % 2 -- always the same warp, because 2 divides TR_XR -- and read by row set it % 3, which differs from round to
+// round: a set that waits for chunk it has stored chunk it - 3, so the MMA warp has consumed every chunk <= it - 3 - TR_NST, and
+// the previous fill of the slot (chunk it - TR_XR) is among them iff TR_XR >= TR_NST + 3.  (Measured: 8-, 10-chunk rings with 3, 4
+// or 5 stages and a third gather warp all run at the same speed within 1 %; a 6-stage / 8-chunk build violates the bound and hangs.)
+static_assert(TR_XR % 2 == 0 && TR_XR >= TR_NST + 3, "staging ring: single filler per slot, readers at most one phase ahead");
 constexpr int TR_ROWW = 4;           // row warps per set = one 128-row tile
 constexpr int TR_CONW = 8;           // contraction warps
 constexpr int TR_W_MMA = TR_NSETS * TR_ROWW, TR_W_GATHER = TR_W_MMA + 1, TR_W_CON = TR_W_MMA + 4;   // warps 12 | 13 | 16..23
@@ -786,9 +792,9 @@ int build_tcr_roles(int lv, const LayerInfo& li, TcrRole* roles) {
     }
     if (!cur.empty()) specs.push_back({cur, 0, HID, false});
   }
-  // scalar roles: all scalar classes, the hidden units in thirds (levels 0, 3: slices of 24 / 8) or halves (levels 1, 2: 12)
+  // scalar roles: all scalar classes, the hidden units in halves where the weight slice fits (levels 0 - 2), else in thirds
   if (!scls.empty()) {
-    const int parts = (lv == 0 || lv == 3) ? 3 : 2;
+    const int parts = lv == 3 ? 3 : 2;
     for (int h = 0; h < parts; ++h) specs.push_back({scls, h * (HID / parts), HID / parts, true});
   }
   if ((int)specs.size() > TCR_MAXROLES) return -1;
@@ -797,8 +803,7 @@ int build_tcr_roles(int lv, const LayerInfo& li, TcrRole* roles) {
     TcrRole& R = roles[r];
     memset(&R, 0, sizeof(R));
     R.isS = sp.isS; R.j0 = sp.j0; R.nj = sp.nj; R.ncol = sp.nj + 1; R.N = tcr_ncols16(R.ncol);
-    if (sp.j0 % J || sp.nj % J) return -1;
-    R.sl0 = sp.j0 / J; R.nsl = sp.nj / J;
+    R.sl0 = sp.j0 / J; R.nsl = sp.nj / J;                   // (informative: k_conv_tcr reads edge-major hidden units)
     if ((sp.j0 * 4) % 16 || (sp.nj * 4) % 16) return -1;   // bulk copies of the role's hidden units
     R.O = sp.isS ? 24 : 6;
     // weight block of one (class, f): ncol x O floats; the stride between blocks is = 2 (mod 4) floats, i.e. an odd number of

@@ -367,10 +367,11 @@ void host_tc_split(float a, uint32_t* hi, uint32_t* lo) { tc_split(a, *hi, *lo);
 static int g_tc_override = -1;      // ddk_debug_set_tc: -1 = follow the environment
 int tc_set_override(int on) { const int prev = g_tc_override; g_tc_override = on; return prev; }
 
-// DDK_TC: 0 = FFMA2 kernels only (k_conv_fused), 1 = k_conv_fused + k_acc_tc for the long lig<-rec segments (default: the fastest
-// measured), 2 = k_conv_tcr: every accumulation on the tensor cores, contraction from tensor memory, no scratch round trip
+// DDK_TC: 0 = FFMA2 kernels only (k_conv_fused), 1 = k_conv_fused + k_acc_tc for the long lig<-rec segments, 2 = k_conv_tcr: every
+// accumulation on the tensor cores, contraction from tensor memory, no scratch round trip (default: the fastest measured, and
+// closer to the reference than mode 1 with the shipped checkpoints)
 int conv_path() {
-  static const int env = getenv("DDK_TC") == nullptr ? 1 : atoi(getenv("DDK_TC"));
+  static const int env = getenv("DDK_TC") == nullptr ? 2 : atoi(getenv("DDK_TC"));
   const int v = g_tc_override < 0 ? env : g_tc_override;
   return v < 0 ? 0 : (v > 2 ? 2 : v);
 }

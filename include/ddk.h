@@ -191,18 +191,21 @@ int ddk_group_totals(DdkCtx* ctx, int64_t* edges, int64_t* segments);   /* cumul
                                                           list ([DDK_WORK_LISTS] each): edge groups 0 lig-lig, 1 lig<-rec, 2 rec-rec,
                                                           3 rec<-lig, and 4 + h = group 2 restricted to the residues within h
                                                           receptor-contact hops of a residue with a cross edge; all steps (sync) */
-/* Process-wide run-time choice of the conv-layer kernels (same meaning as the DDK_TC environment variable): 1 = k_conv_fused
- * (FFMA2) + k_acc_tc (the long lig<-rec segments as 3xTF32 tcgen05.mma) -- the default, fastest measured; 2 = k_conv_tcr, EVERY
- * outer-product accumulation as 3xTF32 tcgen05.mma with the contraction straight from tensor memory (no scratch round trip);
- * 0 = k_conv_fused only (all fp32 FMA: the strictest rounding, for ill-conditioned trajectories); -1 = follow the environment again.  Takes effect at the next
- * ddk_set_batch.  Returns the previous override.  Parity tests run the trajectories in every mode. */
+/* Process-wide run-time choice of the conv-layer kernels (same meaning as the DDK_TC environment variable):
+ *   2 = k_conv_tcr (the default, fastest measured): EVERY outer-product accumulation as 3xTF32 tcgen05.mma with the contraction
+ *       against the resident second radial-MLP layer straight from tensor memory (no scratch round trip);
+ *   1 = k_conv_fused (FFMA2) + k_acc_tc (only the long lig<-rec segments as 3xTF32 tcgen05.mma, A blocks through a scratch buffer);
+ *   0 = k_conv_fused only (all fp32 FMA: the strictest rounding, for ill-conditioned trajectories);
+ *  -1 = follow the environment again.
+ * Takes effect at the next ddk_create / ddk_set_batch.  Returns the previous override.  Parity tests run the trajectories in
+ * every mode. */
 int ddk_debug_set_tc(int32_t on);
 int ddk_debug_read(DdkCtx* ctx, const char* name, void* dst_h, size_t max_bytes, size_t* n_bytes);
 
 /* Optional per-launch timing with CUDA events on the launching stream (used by bench.py for the roofline line).
  * Kernel classes: 0 setup, 1 graph (lists + edge embeddings), 2 node projections, 3..6 conv accumulate (basis level
  * 0..3), 7 conv contract / finalize, 8 score heads, 9 update, 10 first radial-MLP layer per listed edge (k_edge_hidden),
- * 11..14 tensor-core accumulation of the long lig<-rec segments (k_acc_tc, basis level 0..3).
+ * 11..14 tensor-core conv kernels (k_conv_tcr, or k_acc_tc in mode 1; basis level 0..3).
  * ddk_profile_read synchronises the device, adds the elapsed milliseconds / launch counts since the last read into
  * ms[15] / launches[15] and clears the records. */
 #define DDK_PROFILE_CLASSES 15

@@ -64,6 +64,7 @@ static_assert(TR_PF * KC3 == 32, "a batch of prefetched list entries is one warp
 struct TrArgs {
   int NL, N;
   int nb_segs;                       // segments per task (multiple of 8)
+  int couple;                        // 1: a CTA claims for the role of its edge group that is furthest behind (see the claim code)
   int gmask;                         // bit g set: edge group g is processed
   const int4* glist; int goff[4]; int gci[4];
   const int* gcnt;                   // [list] segments; [2 F3_NLIST + 4 ... ] see launch_build_group_lists
@@ -358,25 +359,55 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
   int nwl = 0;       // weight-slice loads so far
 
   for (;;) {
-    // ---- claim a task: (combo, block of segments); stay on the resident combo while it has work
+    // ---- claim a task: (combo, block of segments)
+    // couple = 1: inside its edge group the CTA takes the next block of the ROLE WHOSE CURSOR IS FURTHEST BEHIND (the resident one on
+    // ties).  The roles of a group then walk the work list side by side -- the second to fifth visit of an edge find its hidden
+    // units, list entries and harmonics in L2 instead of DRAM -- and finish together whatever their relative cost; the price is a
+    // weight-slice reload (one bulk copy, ~2 k cycles) at most tasks.  couple = 0: stay on the resident combo while it has work.
     if (tid == 0) {
-      int combo = S.task[5], found = 0;
-      for (int tries = 0; tries < ncombo && !found; ++tries) {
-        const int g = combo / p.nroles;
-        const int gall = ((p.gmask >> g) & 1) ? p.gcnt[p.gci[g]] : 0;
-        const int rem = gall - *reinterpret_cast<volatile int*>(p.counters + combo);
-        if (rem > 0) {
-          const int size = max(8, min(p.nb_segs, (rem / 8) / 8 * 8));       // guided self-scheduling
-          const int start = atomicAdd(p.counters + combo, size);
-          if (start < gall) {
-            S.task[0] = g; S.task[1] = combo % p.nroles; S.task[2] = start; S.task[3] = min(size, gall - start);
-            S.task[4] = (combo != S.task[6]);
-            S.task[5] = combo; S.task[6] = combo;
-            found = 1;
-            break;
+      int found = 0;
+      if (p.couple) {
+        int g = S.task[5] / p.nroles;
+        const int rres = S.task[6] >= 0 && S.task[6] / p.nroles == g ? S.task[6] % p.nroles : -1;
+        for (int gt = 0; gt < 4 && !found; ++gt, g = (g + 1) & 3) {
+          const int gall = ((p.gmask >> g) & 1) ? p.gcnt[p.gci[g]] : 0;
+          for (int retry = 0; retry <= p.nroles && !found; ++retry) {
+            int best = -1, bcur = 0x7fffffff;
+            for (int r = 0; r < p.nroles; ++r) {
+              const int cur = *reinterpret_cast<volatile int*>(p.counters + g * p.nroles + r);
+              if (cur < gall && (cur < bcur || (cur == bcur && r == rres))) { best = r; bcur = cur; }
+            }
+            if (best < 0) break;                                                // the group is exhausted
+            const int combo = g * p.nroles + best, rem = gall - bcur;
+            const int size = max(8, min(p.nb_segs, (rem / 8) / 8 * 8));         // guided self-scheduling
+            const int start = atomicAdd(p.counters + combo, size);
+            if (start < gall) {
+              S.task[0] = g; S.task[1] = best; S.task[2] = start; S.task[3] = min(size, gall - start);
+              S.task[4] = (combo != S.task[6]);
+              S.task[5] = combo; S.task[6] = combo;
+              found = 1;
+            }
           }
         }
-        combo = (combo + 1) % ncombo;
+      } else {
+        int combo = S.task[5];
+        for (int tries = 0; tries < ncombo && !found; ++tries) {
+          const int g = combo / p.nroles;
+          const int gall = ((p.gmask >> g) & 1) ? p.gcnt[p.gci[g]] : 0;
+          const int rem = gall - *reinterpret_cast<volatile int*>(p.counters + combo);
+          if (rem > 0) {
+            const int size = max(8, min(p.nb_segs, (rem / 8) / 8 * 8));         // guided self-scheduling
+            const int start = atomicAdd(p.counters + combo, size);
+            if (start < gall) {
+              S.task[0] = g; S.task[1] = combo % p.nroles; S.task[2] = start; S.task[3] = min(size, gall - start);
+              S.task[4] = (combo != S.task[6]);
+              S.task[5] = combo; S.task[6] = combo;
+              found = 1;
+              break;
+            }
+          }
+          combo = (combo + 1) % ncombo;
+        }
       }
       if (!found) S.task[0] = -1;
     }
@@ -936,8 +967,11 @@ void launch_conv_tcr(DdkCtx* c, int layer, const float* x_in, float* x_out, cuda
   a.gmask = lig_only ? 0x3 : 0xf;
   const int nsegs = 2 * (lig_only ? c->NL : c->N);
   static const int tasks_per_cta = getenv("DDK_TCR_TASKS_PER_CTA") ? atoi(getenv("DDK_TCR_TASKS_PER_CTA")) : 12;
+  static const int couple = getenv("DDK_TCR_COUPLE") ? atoi(getenv("DDK_TCR_COUPLE")) : 1;
+  static const int nb_max = getenv("DDK_TCR_NB") ? atoi(getenv("DDK_TCR_NB")) : 128;
   int nb = (int)((int64_t)nsegs * nroles / (c->sm_count * tasks_per_cta)) / 8 * 8;
-  a.nb_segs = std::min(256, std::max(8, nb));
+  a.nb_segs = std::min(std::min(TR_MAXSEG, std::max(8, nb_max / 8 * 8)), std::max(8, nb));
+  a.couple = couple;
   a.glist = ptr<int4>(c->b_glist);
   a.goff[0] = 0; a.goff[1] = c->NL; a.goff[2] = 2 * c->NL; a.goff[3] = 2 * c->NL + c->NR;
   for (int g = 0; g < 4; ++g) a.gci[g] = g;

@@ -35,8 +35,8 @@ for k, (n, t, b) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print(f'{k:34s} n={n:4d}  {t / 1e6:8.2f} ms  {100 * t / tot:5.1f} %   dram {b / n / 1e6:9.2f} MB/launch  {b / max(t, 1) :7.1f} GB/s')
 if args.traffic_json:
     is3 = lambda l, k: (k + '<3') in l['name'] or (k + '<(int)3') in l['name']
-    k3 = [l for l in sel if is3(l, 'k_conv_fused')] or [l for l in sel if is3(l, 'k_conv_tc')]
-    both = [l for l in sel if is3(l, 'k_conv_fused') or is3(l, 'k_acc_tc') or is3(l, 'k_conv_tc')]   # the kernels of one 84-wide conv layer
+    k3 = [l for l in sel if is3(l, 'k_conv_tcr')] or [l for l in sel if is3(l, 'k_conv_fused')]
+    both = [l for l in sel if is3(l, 'k_conv_tcr') or is3(l, 'k_conv_fused') or is3(l, 'k_acc_tc')]   # the kernels of one 84-wide conv layer
     b = sum(l.get('dram__bytes_read.sum', 0.0) + l.get('dram__bytes_write.sum', 0.0) for l in both)
     t = sum(l['gpu__time_duration.sum'] for l in both)
     json.dump({'kernel': ' + '.join(sorted(set(short(l['name']) for l in both))), 'workload': 'dense', 'launches': len(k3), 'dram_bytes_per_launch': b / max(len(k3), 1),

@@ -42,22 +42,30 @@ namespace ddk {
 
 constexpr int TR_NSETS = 3;          // row-warp sets: set s produces the operands of chunks it = s (mod 3) -- three chunks in flight
 constexpr int TR_NST = TR_NSETS;     // operand stages (A in tensor memory, B in shared memory): one per set
-constexpr int TR_XR = 10;            // staging ring of the gather warps
+#ifndef DDK_TCR_XR
+#define DDK_TCR_XR 9
+#endif
+#ifndef DDK_TCR_NGW
+#define DDK_TCR_NGW 3
+#endif
+constexpr int TR_XR = DDK_TCR_XR;    // staging ring of the gather warps
+constexpr int TR_NGW = DDK_TCR_NGW;  // gather warps: chunk it -> warp it % TR_NGW
 // Phase-parity waits are only safe while no waiter can run two phases ahead of its barrier.  Ring slot it % TR_XR is filled by
-// gather warp it % 2 -- always the same warp, because 2 divides TR_XR -- and read by row set it % 3, which differs from round to
+// gather warp it % TR_NGW -- always the same warp, because TR_NGW divides TR_XR -- and read by row set it % 3, which differs from round to
 // round: a set that waits for chunk it has stored chunk it - 3, so the MMA warp has consumed every chunk <= it - 3 - TR_NST, and
 // the previous fill of the slot (chunk it - TR_XR) is among them iff TR_XR >= TR_NST + 3.  (Measured: 8-, 10-chunk rings with 3, 4
 // or 5 stages and a third gather warp all run at the same speed within 1 %; a 6-stage / 8-chunk build violates the bound and hangs.)
-static_assert(TR_XR % 2 == 0 && TR_XR >= TR_NST + 3, "staging ring: single filler per slot, readers at most one phase ahead");
+static_assert(TR_NGW >= 1 && TR_NGW <= 3 && TR_XR % TR_NGW == 0 && (TR_XR % TR_NSETS == 0 || TR_XR >= TR_NST + 3),
+              "staging ring: single filler per slot, readers at most one phase ahead");
 constexpr int TR_ROWW = 4;           // row warps per set = one 128-row tile
 constexpr int TR_CONW = 8;           // contraction warps
-constexpr int TR_W_MMA = TR_NSETS * TR_ROWW, TR_W_GATHER = TR_W_MMA + 1, TR_W_CON = TR_W_MMA + 4;   // warps 12 | 13 | 16..23
-constexpr int TR_THREADS = (TR_W_CON + TR_CONW) * 32;   // 768 (warps 14, 15 idle: the contraction warps start at a multiple of 4)
+constexpr int TR_W_MMA = TR_NSETS * TR_ROWW, TR_W_GATHER = TR_W_MMA + 1, TR_W_CON = TR_W_MMA + 4;   // warps 12 | 13.. | 16..23
+constexpr int TR_THREADS = (TR_W_CON + TR_CONW) * 32;   // 768: warps 0-11 rows, 12 MMA, 13-15 gather, 16-23 contraction (a multiple of 4: quarter = warp & 3)
 constexpr int TR_COLS = 512;         // tensor-memory columns allocated
 constexpr int TR_ACOL = 448;         // A operand stages: TR_NST x (8 hi + 8 lo) columns from here; accumulator slots below
 constexpr int TR_NMAX = 80;          // widest MMA N
 constexpr int TR_GV = 2, TR_GS = 4;  // segments contracted together: vector roles / scalar roles
-constexpr int TR_MAXSEG = 256;       // segments per task
+constexpr int TR_MAXSEG = 128;       // segments per task
 constexpr int TR_PF = 4;             // chunks per batch of prefetched list entries (TR_PF * KC3 = one warp)
 static_assert(TR_PF * KC3 == 32, "a batch of prefetched list entries is one warp wide");
 
@@ -93,7 +101,8 @@ struct TrSmem {
   alignas(16) float X[TR_XR][KC3][TrCfg<LV>::DINP];                     // destination feature rows of the chunk's edges
   alignas(16) float SH[TR_XR][KC3][4];
   alignas(16) float HS[TR_XR][KC3][HID];                                // the role's hidden units of each edge (first nj floats)
-  alignas(16) TcrRole role;                                             // the resident role's tables
+  alignas(16) unsigned char role_[offsetof(TcrRole, fsrc)];             // the resident role's tables (all but fsrc, which only the finalize kernel reads)
+  __device__ const TcrRole& role() const { return *reinterpret_cast<const TcrRole*>(role_); }
   alignas(8) unsigned long long full[TR_NST], empty[TR_NST];            // operand stages: row warps <-> MMA thread
   alignas(8) unsigned long long sfull[TR_XR], sempty[TR_XR];            // staging ring: gather warps <-> row warps
   alignas(8) unsigned long long accfull[TCR_MAXACC], accempty[TCR_MAXACC];   // accumulator slots: MMA thread <-> contraction warps
@@ -148,7 +157,7 @@ __device__ __forceinline__ void tr_con_group(const TrArgs& p, TrSmem<LV>& S, con
                                              const int cw, const int q, const int lane, long long* dbgp = nullptr) {
   constexpr int G = VEC ? TR_GV : TR_GS, NACC = 2 * G;
   constexpr int O = VEC ? 6 : 24;                              // outputs per basis row; every thread computes 6 of them
-  const TcrRole& R = S.role;
+  const TcrRole& R = S.role();
   const int N = R.N, ncol = R.ncol;
   const int set = cw >> 2;                                    // warp set 0 / 1
   // VEC: lane = basis row, the two warp sets split the columns.  Scalar roles: every row sits in lanes l and l + 16 of its
@@ -333,7 +342,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
     // operand tiles and staging rings start as zeros: the bulk copies of a partial chunk leave the rows of absent edges as they
     // are (their hidden units are masked to 0 in the B operand, so whatever FINITE values they hold contribute nothing)
     uint32_t* z = &S.Bhi[0][0];
-    constexpr int nz = (int)((offsetof(TrSmem<LV>, role) - offsetof(TrSmem<LV>, Bhi)) / 4);
+    constexpr int nz = (int)((offsetof(TrSmem<LV>, role_) - offsetof(TrSmem<LV>, Bhi)) / 4);
     for (int i = tid; i < nz; i += TR_THREADS) z[i] = 0u;
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -353,7 +362,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
   // ring slot, ring phase and stage phase of that chunk incrementally; the MMA warp visits every chunk.
   int skip = 0, buf = 0, bph = 0, sph = 0;
   if (warp < TR_W_MMA) { skip = warp >> 2; buf = skip % TR_XR; }
-  else if (warp == TR_W_GATHER || warp == TR_W_GATHER + 1) { skip = warp - TR_W_GATHER; buf = skip; }
+  else if (warp >= TR_W_GATHER && warp < TR_W_GATHER + TR_NGW) { skip = warp - TR_W_GATHER; buf = skip; }
   int mstage = 0, mph = 0;   // MMA warp: operand stage and its phase
   int sg = 0;        // accumulator slots so far (MMA thread / contraction warps); a multiple of the group size between tasks
   int nwl = 0;       // weight-slice loads so far
@@ -430,9 +439,9 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
       }
       {
         const int4* s4 = reinterpret_cast<const int4*>(src);
-        int4* d4 = reinterpret_cast<int4*>(&S.role);
+        int4* d4 = reinterpret_cast<int4*>(S.role_);
         static_assert(sizeof(TcrRole) % 16 == 0 && offsetof(TcrRole, fsrc) % 16 == 0 && TCR_MAXSRC == 8, "role tables are copied in 16-byte pieces");
-        for (int i = tid; i < (int)(sizeof(TcrRole) / 16); i += TR_THREADS) d4[i] = __ldg(s4 + i);
+        for (int i = tid; i < (int)(offsetof(TcrRole, fsrc) / 16); i += TR_THREADS) d4[i] = __ldg(s4 + i);
       }
       // the accumulator-slot ring depends on the role kind (4 slots of 80 columns / 8 slots of 32 or 48): every pipeline is
       // drained here, so the slot barriers restart from phase 0 together with the slot counter
@@ -475,7 +484,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
       }
     }
     __syncthreads();
-    const TcrRole& R = S.role;
+    const TcrRole& R = S.role();
     const int N = R.N, nj = R.nj, j0 = R.j0;
     const bool vec = !R.isS;
     const int G = vec ? TR_GV : TR_GS, NACC = 2 * G;
@@ -647,14 +656,20 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
         if (lane == 0) tc_mbar_arrive(&S.accfull[slot]);
         __syncwarp();
       }
-    } else if (warp == TR_W_GATHER || warp == TR_W_GATHER + 1) {
+    } else if (warp >= TR_W_GATHER && warp < TR_W_GATHER + TR_NGW) {
       // ================================================================== gather warp: global -> staging ring
-      // lane = (edge e = lane / 4 of the chunk, sub = lane % 4): the four lanes of an edge copy its record in interleaved 16-byte
-      // pieces -- destination feature row, harmonics, the role's hidden units -- with cp.async (LDGSTS; bulk copies are per-warp
-      // instructions and serialise when every lane has its own address: measured 1700 cycles per chunk).  Completion is signalled
-      // to the ring slot's mbarrier by cp.async.mbarrier.arrive.noinc, so the warp never waits for its own copies.
-      const int e = lane >> 2, sub = lane & 3;
+      // Levels 2, 3 (feature rows of 240 / 336 bytes): two passes of four edges, lane = (edge 4 * pass + lane / 8, sub = lane % 8); the
+      // eight lanes of an edge copy its record in interleaved 16-byte pieces -- destination feature row, harmonics, the role's hidden units -- with cp.async (LDGSTS; bulk
+      // copies are per-warp instructions and serialise when every lane has its own address: measured 1700 cycles per chunk).
+      // A quarter-warp (the unit a 16-byte shared-memory store is processed in) then writes 128 CONTIGUOUS bytes of one row:
+      // conflict-free whatever the row stride.  (With four lanes per edge a quarter-warp wrote 64 bytes of two rows 336 / 288 bytes
+      // apart, which overlap modulo 128: 13.4 shared-memory wavefronts per LDGSTS instead of 4, a third of all wavefronts of the
+      // kernel, whose shared-memory pipe is its busiest unit.)  Levels 0, 1 (96 / 176-byte rows): one pass, four lanes per edge.
+      // Completion is signalled to the ring slot's mbarrier by
+      // cp.async.mbarrier.arrive.noinc, so the warp never waits for its own copies.
       constexpr int XQ = DINP / 4;
+      constexpr int LPE = XQ >= 12 ? 8 : 4, EPP = 32 / LPE;   // lanes per edge record (narrow rows: 4), edges per pass
+      const int eq = lane / LPE, sub = lane % LPE;
       const int hq = nj / 4;
       // list entries (edge slot, destination node) are fetched a BATCH of TR_PF chunks at a time, one batch ahead: lane l holds the
       // entry of edge l % 8 of the batch's chunk l / 8 (one coalesced load), and the chunk's lanes get theirs by shuffle.  The
@@ -673,7 +688,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
         for (int b = 0; b < TR_PF; ++b) {
           if (hi_ < nseg) {
             if ((lane >> 3) == b) { mypos = S.seg_base[hi_] + hc * KC3; myrem = S.seg_n[hi_] - hc * KC3; }
-            hc += 2;
+            hc += TR_NGW;
             norm(hi_, hc, hnch);
           }
         }
@@ -687,32 +702,38 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
         {
           const int n = S.seg_n[i];
           const int kc = min(KC3, n - c * KC3), pos0 = S.seg_base[i] + c * KC3;
-          const int slot = __shfl_sync(0xffffffffu, cur.x, kb * KC3 + e), dst = __shfl_sync(0xffffffffu, cur.y, kb * KC3 + e);
+          const int2 ent = cur;
+          const int kb_c = kb;
           if (++kb == TR_PF) { kb = 0; cur = nxt; nxt = batch_load(); }
           TR_T(ga)
           tc_mbar_wait(&S.sempty[buf], bph ^ 1);
           TR_T(gb)
           TR_ADD(0, ga, gb)
-          if (e < kc) {                                 // rows of absent edges keep their stale (finite) content
-            const float* xs = p.x + (size_t)dst * D + 4 * sub;
-            float* xd = &S.X[buf][e][4 * sub];
 #pragma unroll
-            for (int k = 0; k < (XQ + 3) / 4; ++k)
-              if (sub + 4 * k < XQ) __pipeline_memcpy_async(xd + 16 * k, xs + 16 * k, 16);
-            if (sub == 0) __pipeline_memcpy_async(&S.SH[buf][e][0], p.sh_pool + slot, 16);
-            const float* hsrc = p.hs + (size_t)(pos0 + e) * HID + j0 + 4 * sub;
-            float* hd = &S.HS[buf][e][4 * sub];
+          for (int ps = 0; ps < KC3 / EPP; ++ps) {
+            const int e = EPP * ps + eq;
+            const int slot = __shfl_sync(0xffffffffu, ent.x, kb_c * KC3 + e), dst = __shfl_sync(0xffffffffu, ent.y, kb_c * KC3 + e);
+            if (e < kc) {                               // rows of absent edges keep their stale (finite) content
+              const float* xs = p.x + (size_t)dst * D;
+              float* xd = &S.X[buf][e][0];
 #pragma unroll
-            for (int k = 0; k < (HID / 4 + 3) / 4; ++k)
-              if (sub + 4 * k < hq) __pipeline_memcpy_async(hd + 16 * k, hsrc + 16 * k, 16);
+              for (int k = 0; k < (XQ + LPE - 1) / LPE; ++k)
+                if (sub + LPE * k < XQ) __pipeline_memcpy_async(xd + 4 * (sub + LPE * k), xs + 4 * (sub + LPE * k), 16);
+              if (sub == LPE - 1) __pipeline_memcpy_async(&S.SH[buf][e][0], p.sh_pool + slot, 16);
+              const float* hsrc = p.hs + (size_t)(pos0 + e) * HID + j0;
+              float* hd = &S.HS[buf][e][0];
+#pragma unroll
+              for (int k = 0; k < (HID / 4 + LPE - 1) / LPE; ++k)
+                if (sub + LPE * k < hq) __pipeline_memcpy_async(hd + 4 * (sub + LPE * k), hsrc + 4 * (sub + LPE * k), 16);
+            }
           }
           // the barrier receives this thread's arrival when all of its copies above have landed
           asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tc_smem(&S.sfull[buf])) : "memory");
           TR_T(gc)
           TR_ADD(1, gb, gc)
         }
-        buf += 2; if (buf >= TR_XR) { buf -= TR_XR; bph ^= 1; }
-        c += 2;
+        buf += TR_NGW; if (buf >= TR_XR) { buf -= TR_XR; bph ^= 1; }
+        c += TR_NGW;
         norm(i, c, nch);
       }
       skip = c;

@@ -41,7 +41,11 @@
 namespace ddk {
 
 constexpr int TR_NSETS = 3;          // row-warp sets: set s produces the operands of chunks it = s (mod 3) -- three chunks in flight
-constexpr int TR_NST = TR_NSETS;     // operand stages (A in tensor memory, B in shared memory): one per set
+#ifndef DDK_TCR_NST
+#define DDK_TCR_NST 3
+#endif
+constexpr int TR_NST = DDK_TCR_NST;  // operand stages (A in tensor memory, B in shared memory): chunk it -> stage it % TR_NST
+static_assert(TR_NST >= TR_NSETS && TR_NST <= 6, "operand stages");
 #ifndef DDK_TCR_XR
 #define DDK_TCR_XR 9
 #endif
@@ -62,7 +66,7 @@ constexpr int TR_CONW = 8;           // contraction warps
 constexpr int TR_W_MMA = TR_NSETS * TR_ROWW, TR_W_GATHER = TR_W_MMA + 1, TR_W_CON = TR_W_MMA + 4;   // warps 12 | 13.. | 16..23
 constexpr int TR_THREADS = (TR_W_CON + TR_CONW) * 32;   // 768: warps 0-11 rows, 12 MMA, 13-15 gather, 16-23 contraction (a multiple of 4: quarter = warp & 3)
 constexpr int TR_COLS = 512;         // tensor-memory columns allocated
-constexpr int TR_ACOL = 448;         // A operand stages: TR_NST x (8 hi + 8 lo) columns from here; accumulator slots below
+constexpr int TR_ACOL = 512 - 16 * TR_NST;        // A operand stages: TR_NST x (8 hi + 8 lo) columns from here; accumulator slots below
 constexpr int TR_NMAX = 80;          // widest MMA N
 constexpr int TR_GV = 2, TR_GS = 4;  // segments contracted together: vector roles / scalar roles
 constexpr int TR_MAXSEG = 128;       // segments per task
@@ -357,11 +361,11 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
   long long t_reload = 0, n_tasks = 0, n_reload = 0;
 #endif
   // Chunk bookkeeping.  Every warp role walks the chunks of the CTA's tasks in the same order; chunk number `it` (never
-  // materialised) belongs to row set it % 3, gather warp it % 2, operand stage it % 3 and ring slot it % TR_XR.  A row set / gather
+  // materialised) belongs to row set it % 3, gather warp it % TR_NGW, operand stage it % TR_NST and ring slot it % TR_XR.  A row set / gather
   // warp steps straight from one of its chunks to the next (`skip` = offset of its first chunk in the next task) and keeps the
   // ring slot, ring phase and stage phase of that chunk incrementally; the MMA warp visits every chunk.
-  int skip = 0, buf = 0, bph = 0, sph = 0;
-  if (warp < TR_W_MMA) { skip = warp >> 2; buf = skip % TR_XR; }
+  int skip = 0, buf = 0, bph = 0, rst = 0, sph = 0;
+  if (warp < TR_W_MMA) { skip = warp >> 2; buf = skip % TR_XR; rst = skip % TR_NST; }
   else if (warp >= TR_W_GATHER && warp < TR_W_GATHER + TR_NGW) { skip = warp - TR_W_GATHER; buf = skip; }
   int mstage = 0, mph = 0;   // MMA warp: operand stage and its phase
   int sg = 0;        // accumulator slots so far (MMA thread / contraction warps); a multiple of the group size between tasks
@@ -513,7 +517,6 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
         bn[b2] = w < nb_items ? w % (nj + 1) : -1;
         bh[b2] = w < nb_items ? w / (nj + 1) : 0;
       }
-      const int stage = set;
       int i = 0, c = skip, nch = (S.seg_n[0] + KC3 - 1) / KC3;
       auto norm = [&]() {
         while (i < nseg && c >= nch) { c -= nch; ++i; nch = i < nseg ? (S.seg_n[i] + KC3 - 1) / KC3 : 0; }
@@ -521,7 +524,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
       norm();
       while (i < nseg) {
         {
-          const int buf_c = buf, rp_c = bph, sp_c = sph;
+          const int buf_c = buf, rp_c = bph, stage = rst, sp_c = sph;
           const int kc = min(KC3, S.seg_n[i] - c * KC3);
           TR_T(ra)
           tc_mbar_wait(&S.sfull[buf_c], rp_c);
@@ -598,7 +601,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
 #endif
         }
         buf += TR_NSETS; if (buf >= TR_XR) { buf -= TR_XR; bph ^= 1; }
-        sph ^= 1;
+        rst += TR_NSETS; if (rst >= TR_NST) { rst -= TR_NST; sph ^= 1; }
         c += TR_NSETS;
         norm();
       }

@@ -256,6 +256,7 @@ def main():
     ap.add_argument('--complexes', type=int, default=N_COMPLEX)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-sparse', action='store_true', help='skip the second (other trajectory) line')
+    ap.add_argument('--no-strict', action='store_true', help='skip the strict_fp32 line (the same job with DDK_TC=0)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
@@ -416,6 +417,10 @@ def main():
     line = {'metric': 'docked_poses_per_sec', 'value': value, 'unit': 'poses/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic, fresh-init weights (seeded)',
+            'arithmetic': {'2': 'fp32 in / out; the outer-product accumulations of the conv layers as 3xTF32 split products (hi*hi + hi*lo '
+                                '+ lo*hi, fp32 accumulators in tensor memory) on tcgen05, everything else fp32 FMA (k_conv_tcr)',
+                           '1': 'fp32 FMA (k_conv_fused); the long lig<-rec segments as 3xTF32 split products on tcgen05 (k_acc_tc)',
+                           '0': 'fp32 FMA throughout (k_conv_fused)'}[os.environ.get('DDK_TC', '2') if os.environ.get('DDK_TC', '2') in '012' else '2'],
             'config': workload_config(args.workload, n_complex),
             'work': {'edges_per_pose_step': edges_per_pose_step,
                      'reference_formulation_equiv_tflops': R['edges'] * world * FLOP_PER_EDGE_REF / (ms / 1000) / 1e12,
@@ -437,6 +442,17 @@ def main():
         line[other] = {'value': n_poses * world * a2.steps / (ms2 / 1000), 'unit': 'poses/s', 'steps': a2.steps,
                        'edges_per_pose_step': R2['edges'] / (n_poses * REV_STEPS * a2.steps),
                        'trajectory': workload_config(other, n_complex)['start_and_noise']}
+    if not args.no_strict and os.environ.get('DDK_TC') is None:
+        # the same job on the all-fp32-FMA conv kernels (DDK_TC=0): the path that holds 1e-3 A on ill-conditioned trajectories too
+        from disco_diffdock_b200 import engine as dengine
+        dengine.set_tensor_core_path(0)
+        a0 = argparse.Namespace(steps=max(1, args.steps - 1), warmup=1)
+        R0 = time_resident(a0, eng, m, cfg, dev, world, rank, complexes, args.workload, t2s, sched, dist)
+        dengine.set_tensor_core_path(None)
+        ms0 = reduce_max(R0['ms_local'])
+        line['strict_fp32'] = {'value': n_poses * world * a0.steps / (ms0 / 1000), 'unit': 'poses/s', 'steps': a0.steps, 'conv_path': 'DDK_TC=0',
+                               'note': 'conv layers on k_conv_fused (packed fp32 FMA) only; the headline runs them as 3xTF32 split '
+                                       'products on tcgen05 (k_conv_tcr), DESIGN.md section 2 for what each holds'}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         cpu_reference_run(args.workload, complexes, sd, cfg, [(0, 0)], 1, threads)

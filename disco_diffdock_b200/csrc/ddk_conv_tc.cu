@@ -368,8 +368,8 @@ static int g_tc_override = -1;      // ddk_debug_set_tc: -1 = follow the environ
 int tc_set_override(int on) { const int prev = g_tc_override; g_tc_override = on; return prev; }
 
 // DDK_TC: 0 = FFMA2 kernels only (k_conv_fused), 1 = k_conv_fused + k_acc_tc for the long lig<-rec segments, 2 = k_conv_tcr: every
-// accumulation on the tensor cores, contraction from tensor memory, no scratch round trip (default: the fastest measured, and
-// closer to the reference than mode 1 with the shipped checkpoints)
+// accumulation on the tensor cores, contraction from tensor memory, no scratch round trip (default: the fastest measured; as
+// close to the reference as mode 1 with the shipped checkpoints, mode 0 is the strict one)
 int conv_path() {
   static const int env = getenv("DDK_TC") == nullptr ? 2 : atoi(getenv("DDK_TC"));
   const int v = g_tc_override < 0 ? env : g_tc_override;

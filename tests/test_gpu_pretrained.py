@@ -15,7 +15,8 @@ k_acc_tc, 2 = k_conv_tcr (default, everything on the tensor cores).  What was me
     mode                         forward scores    teacher-forced scores / pose after one step    free-running 20-step ODE
     0  fp32 FMA                  3.9e-6            1.8e-5 / 5.1e-5 A                              2.5e-4 A
     1  + k_acc_tc (3xTF32)       5.7e-5            7.0e-5 / 3.1e-4 A                              9.6e-3 A
-    2  k_conv_tcr (3xTF32)       6.0e-5            8.2e-5 / 3.0e-4 A                              2.6e-3 A
+    2  k_conv_tcr (3xTF32)       5.9e-5            7.6e-5 / 3.1e-4 A                              9.6e-3 A (2.6e-3 A with an
+                                                                                                  earlier summation order of the same kernel)
 
 i.e. with these weights (cancellation: activations of 3e2 .. 8e2 produce scores of 0.1) the 3xTF32 accumulation -- two TF32 words
 hold 22 of the 24 mantissa bits of an operand, and the tensor core accumulates with truncation -- is about 15x noisier than the
@@ -57,7 +58,7 @@ def _need_cuda():
 # per mode: forward scores (truly relative), teacher-forced scores, pose after one teacher-forced step [A], free-running ODE [A]
 TOL = {0: dict(fwd=2e-5, teacher=5e-5, step=1e-4, free=1e-3),
        1: dict(fwd=2e-4, teacher=2e-4, step=1e-3, free=3e-2),
-       2: dict(fwd=2e-4, teacher=2e-4, step=1e-3, free=1e-2)}
+       2: dict(fwd=2e-4, teacher=2e-4, step=1e-3, free=3e-2)}
 
 
 def true_rel(got, want):

@@ -95,7 +95,7 @@ struct TcArgs {
 template <int LV>
 __global__ void __launch_bounds__(TcCfg<LV>::THREADS, 1) k_acc_tc(const __grid_constant__ TcArgs p) {
   using Cfg = TcCfg<LV>;
-  constexpr int U = Cfg::U, DINP = Cfg::DINP, XQ = Cfg::XQ, TILES = Cfg::TILES, ROWT = Cfg::ROWT;
+  constexpr int XQ = Cfg::XQ, TILES = Cfg::TILES, ROWT = Cfg::ROWT;
   constexpr int J = Cfg::J, NSL = Cfg::NSL, AST = Cfg::AST;
   extern __shared__ __align__(128) unsigned char tc_raw[];
   TcSmem<LV>& S = *reinterpret_cast<TcSmem<LV>*>(tc_raw);
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(TcCfg<LV>::THREADS, 1) k_acc_tc(const __grid_c
     const TcRow rd = p.rows[tid];
     const int u = rd.u;
     const bool valid = u >= 0;
-    const int tile = tid >> 7, rit = tid & 127;
+    const int tile = tid >> 7;
     const bool plain = __all_sync(0xffffffffu, rd.type == 0);
     const int i1 = rd.type == 0 ? rd.i0 : rd.i0 + 1, i2 = rd.type == 0 ? rd.i0 : rd.i0 + 2;
     const float w_t0 = rd.type == 0 ? 1.f : 0.f, w_dt = rd.type == 1 ? 1.f : 0.f;

@@ -11,20 +11,22 @@
 //   * its slice of the packed weights (<= 150 KB) stays RESIDENT in shared memory while a CTA works on the role,
 //   * several segments' accumulators (N = 80 / 48 / 32 columns each) sit side by side in tensor memory.
 // Level 3: roles {1o}, {1e} (108 rows x all 72 hidden units + the ones column) and {0e, 0o} x three thirds of the hidden units
-// (60 rows x 24 + ones); the lower levels analogously (build_tcr_roles).  A CTA owns one (edge group, role) "combo" at a
-// time and claims blocks of segments from per-combo counters (as k_conv_fused does); every segment is visited once per role
-// and each visit writes an 84-wide partial output row that k_conv_finalize adds in a fixed order.  Warp roles inside a CTA:
-//   * 2 gather warps: list entries, destination feature rows, harmonics and the role's hidden units of 8 edges -> staging ring
+// (60 rows x 24 + ones); the lower levels analogously with the scalar classes in halves (build_tcr_roles).  Every segment is visited
+// once per role; each visit writes a partial record (TCR_PS floats) that k_conv_finalize_tcr adds in a fixed order.
+// Scheduling: per (edge group, role) a cursor into the group's segment list; a CTA claims the next block of the role of its group
+// whose cursor is furthest behind, so the roles walk the list side by side (later visits of an edge hit L2) and finish together.
+// Warp roles inside a CTA (768 threads):
+//   * 3 gather warps: list entries, destination feature rows, harmonics and the role's hidden units of 8 edges -> staging ring
 //     (cp.async, completion on mbarriers; they run ahead across segment boundaries);
-//   * 4 row warps: thread p evaluates basis row p of the 8 edges, splits it into TF32 hi + lo and writes it into TENSOR MEMORY
-//     (tcgen05.st; the A operand never touches shared memory); they also split the hidden units into the B operand
+//   * 3 sets of 4 row warps: thread p evaluates basis row p of the 8 edges, splits it into TF32 hi + lo and writes it into TENSOR
+//     MEMORY (tcgen05.st; the A operand never touches shared memory); they also split the hidden units into the B operand
 //     (K-major no-swizzle UMMA layout in shared memory, one extra row of ones -> Bsum);
-//   * 1 MMA thread: three tcgen05.mma kind::tf32 (.ts form) per chunk -- hi*hi + hi*lo + lo*hi -- into the segment's
+//   * 1 MMA warp: three tcgen05.mma kind::tf32 (.ts form) per chunk -- hi*hi + hi*lo + lo*hi -- into the segment's
 //     accumulator slot; tcgen05.commit frees the operand stage and publishes the finished accumulator;
 //   * 8 contraction warps: tcgen05.ld the accumulators of G finished segments (G = 2 for vector roles, 4 for scalar roles) and
 //     contract them with the resident weights in packed FFMA2 -- every weight read from shared memory is used for G segments
-//     (and, in vector roles, for the three components that sit in neighbouring lanes: broadcast) --, reduce over the rows of
-//     each (class, component) through shared memory in a fixed order and write the partial rows.
+//     (and, in vector roles, for the three components that sit in neighbouring lanes: broadcast) --, sum over the rows of each
+//     (class, component) by shuffles in a fixed order and write their share of the partial record.
 // Measured pacing of tcgen05.mma kind::tf32 on B200 (tools/microbench/umma_pacing.cu): max(46, N / 2) cycles per instruction for
 // M = 64 and 128 alike, so an M = 128 x N = 80 tile costs the same as any narrower one -- the reason every role keeps the
 // widest N its weights allow and one tile.
@@ -32,6 +34,7 @@
 #include <cuda_pipeline_primitives.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -491,12 +494,13 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
     const TcrRole& R = S.role();
     const int N = R.N, nj = R.nj, j0 = R.j0;
     const bool vec = !R.isS;
-    const int G = vec ? TR_GV : TR_GS, NACC = 2 * G;
+    const int G = vec ? TR_GV : TR_GS;
+    [[maybe_unused]] const int NACC = 2 * G;        // (trace build)
 
     if (warp < TR_W_MMA) {
       // ================================================================== row warps: A operand -> tensor memory, B -> smem
       // set = warp / 4 produces the chunks it = set (mod TR_NSETS) into operand stage `set`; thread (quarter, lane) = tile row
-      const int set = warp >> 2, rt = (warp & 3) * 32 + lane;
+      const int rt = (warp & 3) * 32 + lane;
       const TcRow rd = R.rows[rt];
       const bool plain = __all_sync(0xffffffffu, rd.type == 0);
       // every basis row is  x[ia] sh[ma] + sb x[ib] sh[mb] + sc x[ic] sh[mc]:  plain product (sb = sc = 0), dot product of a
@@ -1060,7 +1064,8 @@ void launch_conv_tcr(DdkCtx* c, int layer, const float* x_in, float* x_out, cuda
 }
 
 // ---- host checks (callable without a GPU): every basis row of a level is owned by exactly one role row, the weight slices
-// reproduce the packed weights, and the shapes fit the kernel's budgets.  Returns 0 if all four levels pass, else 1 + level.
+// reproduce the packed weights, the shapes fit the kernel's budgets, and the partial records added up through TcrRole::fsrc equal the
+// direct contraction.  Returns 0 if all four levels pass, else 1 + level (tables) or 10 + level (records).
 int host_tcr_roles_check() {
   for (int lv = 0; lv < 4; ++lv) {
     // class tables of a layer of this level (as build_layers in ddk_api.cu)
@@ -1112,6 +1117,66 @@ int host_tcr_roles_check() {
       }
     }
     for (int v : cover) if (v != 1) return 1 + lv;
+    // partial records: emulate what the contraction warps write for one segment (random accumulator A[u][0..72], column 72 = Bsum)
+    // and what k_conv_finalize_tcr adds up through fsrc; compare with the direct contraction  out = W2p (*) A + b2p (*) Bsum
+    {
+      unsigned long long st = 88172645463325252ull + (unsigned)lv;
+      auto rnd = [&]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return (double)(st % 20001) / 10000.0 - 1.0; };
+      std::vector<double> A((size_t)li.U * (HID + 1));
+      for (auto& v : A) v = rnd();
+      for (auto& v : w2p) v = (float)rnd();
+      for (auto& v : b2p) v = (float)rnd();
+      std::vector<double> direct(D, 0.0), emul(D, 0.0);
+      for (int k = 0; k < li.ncls; ++k) {
+        const ClassInfo& ci = li.cls[k];
+        for (int c = 0; c < ci.ncomp; ++c)
+          for (int o = 0; o < ci.O; ++o) {
+            double acc = 0.0;
+            for (int f = 0; f < ci.F; ++f) {
+              const int u = ci.uoff + c * ci.F + f;
+              for (int j = 0; j < HID; ++j) acc += A[(size_t)u * (HID + 1) + j] * w2p[ci.woff + ((int64_t)f * HID + j) * ci.O + o];
+              acc += A[(size_t)u * (HID + 1) + HID] * b2p[ci.boff + (int64_t)f * ci.O + o];
+            }
+            direct[ci.col0 + (ci.ncomp == 3 ? 3 * o + c : o)] = acc;
+          }
+      }
+      for (int r = 0; r < nr; ++r) {
+        const TcrRole& R = roles[r];
+        std::vector<float> sl((size_t)R.wfloats);
+        build_tcr_weights(li, R, w2p.data(), b2p.data(), sl.data());
+        auto acol = [&](int u, int col) {
+          return col < R.nj ? A[(size_t)u * (HID + 1) + R.j0 + col] : (col == R.nj ? A[(size_t)u * (HID + 1) + HID] : 0.0);
+        };
+        std::vector<double> rec(TCR_PS, 0.0);
+        for (int cw = 0; cw < TR_CONW; ++cw) {
+          const int set = cw >> 2, q = cw & 3;
+          for (int lane = 0; lane < 32; ++lane) {
+            const int t = 32 * q + lane, u = R.rows[t].u;
+            if (u < 0) continue;
+            if (R.isS) {
+              const int h = lane >> 4;
+              for (int k6 = 0; k6 < 6; ++k6) {
+                const int o = 12 * set + 6 * h + k6;
+                double acc = 0.0;
+                for (int col = 0; col < R.ncol; ++col) acc += acol(u, col) * sl[R.woff[t] + col * 24 + o];
+                rec[(cw * 2 + h) * 6 + k6] += acc;
+              }
+            } else {
+              const int c0 = set ? 40 : 0;
+              for (int o = 0; o < 6; ++o) {
+                double acc = 0.0;
+                for (int col = c0; col < std::min(c0 + 40, R.ncol); ++col) acc += acol(u, col) * sl[R.woff[t] + col * 6 + o];
+                rec[(cw * 3 + lane % 3) * 6 + o] += acc;
+              }
+            }
+          }
+        }
+        for (int f = 0; f < D; ++f)
+          for (int i = 0; i < TCR_MAXSRC && R.fsrc[f][i] >= 0; ++i) emul[f] += rec[R.fsrc[f][i]];
+      }
+      for (int f = 0; f < D; ++f)
+        if (std::abs(emul[f] - direct[f]) > 1e-6 * (1.0 + std::abs(direct[f]))) return 10 + lv;
+    }
   }
   return 0;
 }

@@ -234,7 +234,9 @@ int ddk_host_tc_split(const float* a_h, int32_t n, uint32_t* hi_h, uint32_t* lo_
 /* Host self check of k_conv_tcr's role tables (callable without a GPU): at every basis level each (basis row, hidden unit) pair and
  * each (basis row, bias) pair is owned by exactly one role, the per-role weight slices reproduce the packed second-layer weights
  * (models/tensor_layers.py:154-156 re-associated, disco_diffdock_b200/weights.py) and every shape fits the kernel's tensor-memory /
- * shared-memory budgets.  Returns 0, or 1 + the first failing level. */
+ * shared-memory budgets; and, for a random accumulator block, the partial records the contraction warps would write, added up
+ * through the finalize table (TcrRole::fsrc), equal the direct contraction W2p (*) A + b2p (*) Bsum.  Returns 0, 1 + the first
+ * level whose tables fail, or 10 + the first level whose records fail. */
 int ddk_host_tcr_roles_check(void);
 
 /* Host build of k_conv_tcr's operand split: hi and lo both on the TF32 grid, |a - hi - lo| <= 2^-22 |a|. */

@@ -141,7 +141,8 @@ def test_tf32_split_is_exact(lib):
 
 def test_tensor_core_role_tables(lib):
     """k_conv_tcr: at every basis level each (basis row, hidden unit) and (basis row, bias) pair belongs to exactly one role, the
-    resident weight slices reproduce the packed second-layer weights, and the shapes fit tensor memory / shared memory."""
+    resident weight slices reproduce the packed second-layer weights, the shapes fit tensor memory / shared memory, and the partial
+    records of the contraction warps summed through the finalize table equal the direct contraction (emulated on the host)."""
     lib.ddk_host_tcr_roles_check.restype = ctypes.c_int
     assert lib.ddk_host_tcr_roles_check() == 0
 

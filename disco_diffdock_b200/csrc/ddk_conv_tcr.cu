@@ -994,7 +994,7 @@ void launch_conv_tcr(DdkCtx* c, int layer, const float* x_in, float* x_out, cuda
   a.NL = c->NL; a.N = c->N;
   a.gmask = lig_only ? 0x3 : 0xf;
   const int nsegs = 2 * (lig_only ? c->NL : c->N);
-  static const int tasks_per_cta = getenv("DDK_TCR_TASKS_PER_CTA") ? atoi(getenv("DDK_TCR_TASKS_PER_CTA")) : 12;
+  static const int tasks_per_cta = getenv("DDK_TCR_TASKS_PER_CTA") ? atoi(getenv("DDK_TCR_TASKS_PER_CTA")) : 24;   // 40-pose calls: 12 -> 214, 24 -> 219, 48 -> 205 poses/s (400 poses: capped by DDK_TCR_NB)
   static const int couple = getenv("DDK_TCR_COUPLE") ? atoi(getenv("DDK_TCR_COUPLE")) : 1;
   static const int nb_max = getenv("DDK_TCR_NB") ? atoi(getenv("DDK_TCR_NB")) : 128;
   int nb = (int)((int64_t)nsegs * nroles / (c->sm_count * tasks_per_cta)) / 8 * 8;

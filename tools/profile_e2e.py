@@ -13,13 +13,15 @@ from tests import helpers
 ap = argparse.ArgumentParser()
 ap.add_argument('--complexes', type=int, default=10)
 ap.add_argument('--cprofile', action='store_true')
+ap.add_argument('--workload', choices=['dense', 'sparse'], default='dense')
 args = ap.parse_args()
 dev = torch.device('cuda')
-m, sd, cfg = helpers.make_model(0, gain=5.0)
+m, sd, cfg = bench.make_weights(args.workload)
+dense = args.workload == 'dense'
 m = m.to(dev); eng = m.engine(dev)
 t2s = partial(du.t_to_sigma, args=cfg)
 sched = du.get_t_schedule(bench.REV_STEPS)
-complexes = bench.build_workload(0, args.complexes)
+complexes = bench.build_workload(0, args.complexes, args.workload)
 n_poses = args.complexes * bench.N_SAMPLES
 
 
@@ -27,7 +29,7 @@ def step(seed):
     g = torch.Generator().manual_seed(seed)
     for data_list in complexes:
         dl = [x.shallow_copy() for x in data_list]
-        dsampling.sampling(dl, m, bench.REV_STEPS, sched, sched, sched, dev, t2s, cfg, batch_size=bench.N_SAMPLES,
+        dsampling.sampling(dl, m, bench.REV_STEPS, sched, sched, sched, dev, t2s, cfg, no_random=dense, batch_size=bench.N_SAMPLES,
                            no_final_step_noise=True, generator=g, host_buffers=True, **helpers.README_TEMPS)
 
 
@@ -45,8 +47,8 @@ ts, tr = [], []
 for data_list in complexes:
     ts.append(timed(eng.set_batch_copies, data_list[0], bench.N_SAMPLES))
     R = eng.batch_info.RB
-    z = {'tr': torch.randn(bench.REV_STEPS, bench.N_SAMPLES, 3), 'rot': torch.randn(bench.REV_STEPS, bench.N_SAMPLES, 3),
-         'tor': torch.randn(bench.REV_STEPS, R)}
+    z = None if dense else {'tr': torch.randn(bench.REV_STEPS, bench.N_SAMPLES, 3), 'rot': torch.randn(bench.REV_STEPS, bench.N_SAMPLES, 3),
+                            'tor': torch.randn(bench.REV_STEPS, R)}
     pos = torch.cat([x['ligand'].pos for x in data_list], 0).float().contiguous()
     tr.append(timed(eng.sample_host, pos, tab, z))
 print(f'per complex: set_batch_copies {1e3 * np.mean(ts):.2f} ms, sample_host {1e3 * np.mean(tr):.2f} ms')
@@ -67,8 +69,8 @@ flat = [g for c in complexes for g in c]
 big = ddata.Batch.from_data_list(flat)
 info = eng.set_batch(big)
 tabN = dsampling.build_step_tables(m, cfg, t2s, sched, sched, sched, bench.REV_STEPS, n_poses, **helpers.README_TEMPS)
-z = {'tr': torch.randn(bench.REV_STEPS, n_poses, 3, device=dev), 'rot': torch.randn(bench.REV_STEPS, n_poses, 3, device=dev),
-     'tor': torch.randn(bench.REV_STEPS, info.RB, device=dev)}
+z = None if dense else {'tr': torch.randn(bench.REV_STEPS, n_poses, 3, device=dev), 'rot': torch.randn(bench.REV_STEPS, n_poses, 3, device=dev),
+                        'tor': torch.randn(bench.REV_STEPS, info.RB, device=dev)}
 pos0 = big['ligand'].pos.to(dev).contiguous()
 eng.sample(pos0.clone(), tabN, z)
 eng.profile_read()
@@ -87,7 +89,7 @@ t0 = time.perf_counter(); groups = group_copies(dl); t1 = time.perf_counter(); g
 print(f'batched call: group_copies {1e3 * (t1 - t0):.1f} ms, group_index_arrays {1e3 * (t2 - t1):.1f} ms (host only)')
 for _ in range(2):
     tsb = timed(eng.set_batch_groups, groups)
-zh = {k: v.cpu() for k, v in z.items()}
+zh = None if z is None else {k: v.cpu() for k, v in z.items()}
 posh = torch.cat([x['ligand'].pos for x in dl], 0).float().contiguous()
 for _ in range(2):
     tsh = timed(eng.sample_host, posh.clone(), tabN, zh)
@@ -96,7 +98,7 @@ print(f'batched call: set_batch_groups {1e3 * tsb:.1f} ms, sample_host {1e3 * ts
 def batched(seed):
     g = torch.Generator().manual_seed(seed)
     d = [x.shallow_copy() for c in complexes for x in c]
-    dsampling.sampling(d, m, bench.REV_STEPS, sched, sched, sched, dev, t2s, cfg, batch_size=len(d), no_final_step_noise=True,
+    dsampling.sampling(d, m, bench.REV_STEPS, sched, sched, sched, dev, t2s, cfg, no_random=dense, batch_size=len(d), no_final_step_noise=True,
                        generator=g, host_buffers=True, **helpers.README_TEMPS)
 eng.profile_enable(False)
 batched(0)

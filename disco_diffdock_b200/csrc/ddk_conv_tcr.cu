@@ -832,7 +832,6 @@ static int tcr_ncols16(int n) { return (n + 15) / 16 * 16; }
 
 // Roles of basis level lv (see the header).  cls: the irrep classes of a layer of that level (build_layers).
 int build_tcr_roles(int lv, const LayerInfo& li, TcrRole* roles) {
-  const int J = f3_J(lv);
   std::vector<TcRow> all(TC_MAXROWS);
   build_tc_rows(lv, all.data());                      // (type, i0, m, u) of every basis row of the level
   std::vector<TcRow> byu(li.U);
@@ -862,7 +861,6 @@ int build_tcr_roles(int lv, const LayerInfo& li, TcrRole* roles) {
     TcrRole& R = roles[r];
     memset(&R, 0, sizeof(R));
     R.isS = sp.isS; R.j0 = sp.j0; R.nj = sp.nj; R.ncol = sp.nj + 1; R.N = tcr_ncols16(R.ncol);
-    R.sl0 = sp.j0 / J; R.nsl = sp.nj / J;                   // (informative: k_conv_tcr reads edge-major hidden units)
     if ((sp.j0 * 4) % 16 || (sp.nj * 4) % 16) return -1;   // bulk copies of the role's hidden units
     R.O = sp.isS ? 24 : 6;
     // weight block of one (class, f): ncol x O floats; the stride between blocks is = 2 (mod 4) floats, i.e. an odd number of

@@ -79,11 +79,10 @@ struct alignas(16) TcrRole {
   int ncol;                         // contracted accumulator columns: nj hidden units + the ones column (Bsum)
   int N;                            // MMA N: ncol rounded up to 16
   int j0, nj;                       // hidden units [j0, j0 + nj)
-  int sl0, nsl;                     // ... as slices of k_edge_hidden's layout (J = f3_J(level) units per slice)
   int O;                            // outputs per row: 6 (vector classes) or 24 (scalar classes)
   int isS;                          // scalar-class role
   int wstride, wfloats;             // floats of one (class, f) weight block incl. padding; floats of the whole slice
-  int pad_[1];
+  int pad_[3];
   // Tile rows.  Vector roles: the three components of a basis row (class, f) in neighbouring rows, every class starting at a
   // multiple of 32 rows (one contraction warp never mixes classes).  Scalar roles: distinct row d = 16 q + l sits in tile rows
   // 32 q + l and 32 q + 16 + l (both halves of a warp), every class starting at a multiple of 16 distinct rows.

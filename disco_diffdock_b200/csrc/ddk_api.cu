@@ -364,10 +364,11 @@ int ddk_set_batch(DdkCtx* c, const DdkBatch* b, void* stream) {
   EN(c->b_tb, (size_t)B * TB_COUNT * NS * 4);
   EN(c->b_xa, (size_t)c->N * D * 4); EN(c->b_xb, (size_t)c->N * D * 4); EN(c->b_proj, (size_t)c->N * 4 * HID * 4);
   c->nhop = std::min(F3_MAXHOP, c->cfg.num_conv_layers - 1);
-  EN(c->b_glist, ((size_t)nsegs + (size_t)c->nhop * NR) * 16); EN(c->b_gcnt, (2 * F3_NLIST + 4) * 4); EN(c->b_counters, 5 * NSL_MAX * 4);
+  // work lists | needed-hop lists | pieces of the lig<-rec segments (k_conv_tcr)
+  EN(c->b_glist, ((size_t)nsegs + (size_t)c->nhop * NR + (size_t)NL * TCR_PMAX) * 16); EN(c->b_gcnt, (2 * F3_NLIST + 4) * 4); EN(c->b_counters, 5 * NSL_MAX * 4);
   EN(c->b_need, (size_t)std::max(1, c->nhop) * NR);
   static_assert(TCR_MAXROLES * TCR_PS <= NSL_MAX * D, "the partial records of k_conv_tcr fit the partial rows of k_conv_fused");
-  EN(c->b_part, (size_t)nsegs * NSL_MAX * D * 4);
+  EN(c->b_part, ((size_t)nsegs + (size_t)NL * (TCR_PMAX - 1)) * NSL_MAX * D * 4);
   EN(c->b_hs, (size_t)std::max<int64_t>(total, 1) * HID * 4);
   c->tc_cap = 0;
   if (conv_path() == 1) {   // A_s scratch of the round-1 tensor-core path (k_acc_tc): one block per ligand atom, capped at 4 GB

@@ -176,39 +176,52 @@ __global__ void k_need_expand(int ER, const int* __restrict__ rr_src, const int*
   if (e < ER && prev[rr_src[e]]) { next[rr_src[e]] = 1; next[rr_dst[e]] = 1; }   // every write stores 1: no race that matters
 }
 
-// blocks 0..3: the four edge groups; block 4 + h: group 2 restricted to the residues of need[h]
+// blocks 0..3: the four edge groups; block 4 + h: group 2 restricted to the residues of need[h].
+// split_sub > 0 (k_conv_tcr): the lig<-rec segments (list 1) are listed in PIECES of at most split_sub edges, in the region at
+// split_off; entry = (segment, edges, first list position, record id) with record id = segment for piece 0 (and for every
+// unsplit entry) and 2 N + (TCR_PMAX - 1) * ligand node + p - 1 for piece p > 0.
 __global__ void __launch_bounds__(1024) k_build_group_lists(int NL, int NR, const int* __restrict__ seg_cnt,
                                                             const int* __restrict__ seg_base, int4* __restrict__ glist,
                                                             int* __restrict__ gcnt, unsigned long long* __restrict__ counters,
-                                                            const unsigned char* __restrict__ need, const int tc_min_chunks) {
+                                                            const unsigned char* __restrict__ need, const int tc_min_chunks,
+                                                            const int split_sub, const int split_off) {
   __shared__ int hist[GL_BUCKETS], cursor[GL_BUCKETS];
-  __shared__ int nedge;
+  __shared__ int nedge, nreal;
   const int li = blockIdx.x;                       // work list
   const bool filt = li >= 4;
   const int g = filt ? 2 : li;
   const int nn = g < 2 ? NL : NR;
-  const int off = li == 0 ? 0 : (li == 1 ? NL : (li == 2 ? 2 * NL : (li == 3 ? 2 * NL + NR : 2 * NL + 2 * NR + (li - 4) * NR)));
+  const bool split = li == 1 && split_sub > 0;
+  const int off = split ? split_off
+                        : (li == 0 ? 0 : (li == 1 ? NL : (li == 2 ? 2 * NL : (li == 3 ? 2 * NL + NR : 2 * NL + 2 * NR + (li - 4) * NR))));
   const unsigned char* nd = filt ? need + (size_t)(li - 4) * NR : nullptr;
   const int tid = threadIdx.x;
+  auto bucket = [](int n) { return min(GL_BUCKETS - 1, (n + KC3 - 1) / KC3); };
+  auto pieces = [&](int n) { return split ? min(TCR_PMAX, (n + split_sub - 1) / split_sub) : 1; };
+  auto piece_len = [&](int n, int P, int pc) { return pc < P - 1 ? split_sub : n - (P - 1) * (split ? split_sub : 0); };
   if (tid < GL_BUCKETS) hist[tid] = 0;
-  if (tid == 0) nedge = 0;
+  if (tid == 0) { nedge = 0; nreal = 0; }
   __syncthreads();
   for (int i = tid; i < nn; i += 1024) {
     const int seg = g < 2 ? 2 * i + g : 2 * (NL + i) + (g - 2);
     int n = seg_cnt[seg];
     if (filt && !nd[i]) n = 0;
-    if (n > 0) { atomicAdd(&hist[min(GL_BUCKETS - 1, (n + KC3 - 1) / KC3)], 1); atomicAdd(&nedge, n); }
+    if (n > 0) {
+      const int P = pieces(n);
+      for (int pc = 0; pc < P; ++pc) atomicAdd(&hist[bucket(piece_len(n, P, pc))], 1);
+      atomicAdd(&nedge, n); atomicAdd(&nreal, 1);
+    }
   }
   __syncthreads();
   if (tid == 0) {
     int run = 0;
     for (int bkt = GL_BUCKETS - 1; bkt >= 0; --bkt) { cursor[bkt] = run; run += hist[bkt]; }
-    gcnt[li] = run;
+    gcnt[li] = run;                                                         // list entries (pieces count as entries)
     gcnt[F3_NLIST + 4 + li] = nedge;                                        // listed edges of this work list in this step
     if (!filt) gcnt[F3_NLIST + li] = cursor[tc_min_chunks - 1];             // segments with >= tc_min_chunks chunks (list head)
-    if (!filt) atomicAdd(counters + 1, (unsigned long long)run);            // all non-empty segments
+    if (!filt) atomicAdd(counters + 1, (unsigned long long)nreal);          // all non-empty segments
     atomicAdd(counters + 2 + li, (unsigned long long)nedge);                // edges per work list
-    atomicAdd(counters + 2 + F3_NLIST + li, (unsigned long long)run);       // segments per work list
+    atomicAdd(counters + 2 + F3_NLIST + li, (unsigned long long)nreal);     // segments per work list
   }
   __syncthreads();
   for (int i = tid; i < nn; i += 1024) {
@@ -216,8 +229,13 @@ __global__ void __launch_bounds__(1024) k_build_group_lists(int NL, int NR, cons
     int n = seg_cnt[seg];
     if (filt && !nd[i]) n = 0;
     if (n > 0) {
-      const int o = atomicAdd(&cursor[min(GL_BUCKETS - 1, (n + KC3 - 1) / KC3)], 1);
-      glist[off + o] = make_int4(seg, n, seg_base[seg], 0);
+      const int P = pieces(n), base = seg_base[seg];
+      for (int pc = 0; pc < P; ++pc) {
+        const int len = piece_len(n, P, pc);
+        const int o = atomicAdd(&cursor[bucket(len)], 1);
+        const int rec = pc == 0 ? seg : 2 * (NL + NR) + (TCR_PMAX - 1) * i + pc - 1;
+        glist[off + o] = make_int4(seg, len, base + pc * (split ? split_sub : 0), rec);
+      }
     }
   }
 }
@@ -1062,8 +1080,17 @@ void launch_build_group_lists(DdkCtx* c, cudaStream_t st, bool with_needed) {
   LaunchScope ls(c, PC_GRAPH, st);
   k_build_group_lists<<<4 + nhop, 1024, 0, st>>>(c->NL, c->NR, ptr<int>(c->b_seg_cnt), ptr<int>(c->b_seg_base),
                                                  ptr<int4>(c->b_glist), ptr<int>(c->b_gcnt),
-                                                 ptr<unsigned long long>(c->b_edge_total), need, tc_min_chunks);
+                                                 ptr<unsigned long long>(c->b_edge_total), need, tc_min_chunks,
+                                                 tcr_split_sub(), glist_split_off(c));
 }
+
+// k_conv_tcr accumulates the lig<-rec segments in pieces (list 1 lives in its own region of the work-list buffer then)
+int tcr_split_sub() {
+  static const int sub = getenv("DDK_TCR_SUB") ? std::max(0, atoi(getenv("DDK_TCR_SUB"))) / KC3 * KC3 : TCR_SUB;
+  return conv_path() == 2 ? sub : 0;
+}
+int glist_split_off(const DdkCtx* c) { return 2 * c->N + c->nhop * c->NR; }
+int glist_off_group1(const DdkCtx* c) { return tcr_split_sub() > 0 ? glist_split_off(c) : c->NL; }
 
 void launch_conv_finalize(DdkCtx* c, int layer, const float* x_in, float* x_out, cudaStream_t st, bool lig_only, int nsl) {
   const LayerInfo& li = c->layers[layer];

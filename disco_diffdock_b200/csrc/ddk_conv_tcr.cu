@@ -116,7 +116,7 @@ struct TrSmem {
   alignas(8) unsigned long long bar_w;                                  // completion of the weight-slice bulk copy
   uint32_t tmem_base;
   int task[8];                       // g, role, idx0, nseg, reload, combo cursor, resident combo (g * nroles + role), -
-  int seg_id[TR_MAXSEG], seg_n[TR_MAXSEG], seg_base[TR_MAXSEG];   // the task's work-list entries (staged once per task)
+  int seg_id[TR_MAXSEG], seg_n[TR_MAXSEG], seg_base[TR_MAXSEG];   // the task's work-list entries (record id, edges, first list position)
   alignas(128) float Wsl[1];         // the resident weight slice follows (TCR_WMAX floats, dynamic)
 };
 
@@ -486,8 +486,8 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
       // the task's work-list entries -> shared memory: every warp role walks them, nobody waits on a global load per segment
       const int4* wle = p.glist + p.goff[g] + idx0;
       for (int i = tid; i < nseg; i += TR_THREADS) {
-        const int4 e4 = load_seg_entry(wle + i);
-        S.seg_id[i] = e4.x; S.seg_n[i] = e4.y; S.seg_base[i] = e4.z;
+        const int4 e4 = __ldg(wle + i);                  // (segment, edges, first list position, record id)
+        S.seg_id[i] = e4.w; S.seg_n[i] = e4.y; S.seg_base[i] = e4.z;
       }
     }
     __syncthreads();
@@ -794,6 +794,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_conv_tcr(const __grid_constan
 // node's edges, batch-norm affine, residual -- k_conv_finalize's arithmetic on k_conv_tcr's record layout.
 struct FinTcrArgs {
   int N, dout, nroles;
+  int NL, sub, extra;                // ligand nodes; edges per piece of a lig<-rec segment (0: unsplit); first record id of the pieces p > 0
   const int* seg_cnt; const float* part; const TcrRole* roles;
   const float* bn_scale; const float* bn_shift; const float* x_in; float* x_out;
 };
@@ -807,17 +808,23 @@ __global__ void __launch_bounds__(256) k_conv_finalize_tcr(FinTcrArgs p) {
   float v = 0.f;
   if (f < p.dout) {
     float s = 0.f;
+    // the lig<-rec segment of a ligand node was accumulated in pieces (TCR_SUB): piece 0 in the segment's record, the others behind
+    const int npiece = node < p.NL && p.sub > 0 && cnt[1] > 0 ? min(TCR_PMAX, (cnt[1] + p.sub - 1) / p.sub) : 1;
     for (int r = 0; r < p.nroles; ++r) {
       const int4 t4 = __ldg(reinterpret_cast<const int4*>(&p.roles[r].fsrc[f][0]));
       const int tw[4] = {t4.x, t4.y, t4.z, t4.w};
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         if (cnt[h] <= 0) continue;
-        const float* rec = p.part + ((size_t)(2 * node + h) * p.nroles + r) * TCR_PS;
+        const int np = h == 1 ? npiece : 1;
+        for (int pc = 0; pc < np; ++pc) {
+          const size_t rid = pc == 0 ? (size_t)(2 * node + h) : (size_t)p.extra + (size_t)(TCR_PMAX - 1) * node + pc - 1;
+          const float* rec = p.part + (rid * p.nroles + r) * TCR_PS;
 #pragma unroll
-        for (int i = 0; i < TCR_MAXSRC; ++i) {
-          const int o = (short)((tw[i >> 1] >> (16 * (i & 1))) & 0xffff);
-          if (o >= 0) s += rec[o];
+          for (int i = 0; i < TCR_MAXSRC; ++i) {
+            const int o = (short)((tw[i >> 1] >> (16 * (i & 1))) & 0xffff);
+            if (o >= 0) s += rec[o];
+          }
         }
       }
     }
@@ -1011,7 +1018,7 @@ void launch_conv_tcr(DdkCtx* c, int layer, const float* x_in, float* x_out, cuda
   a.nb_segs = std::min(std::min(TR_MAXSEG, std::max(8, nb_max / 8 * 8)), std::max(8, nb));
   a.couple = couple;
   a.glist = ptr<int4>(c->b_glist);
-  a.goff[0] = 0; a.goff[1] = c->NL; a.goff[2] = 2 * c->NL; a.goff[3] = 2 * c->NL + c->NR;
+  a.goff[0] = 0; a.goff[1] = glist_off_group1(c); a.goff[2] = 2 * c->NL; a.goff[3] = 2 * c->NL + c->NR;
   for (int g = 0; g < 4; ++g) a.gci[g] = g;
   if (mode >= CONV_NEEDED) { const int h = mode - CONV_NEEDED; a.goff[2] = 2 * c->NL + 2 * c->NR + h * c->NR; a.gci[2] = 4 + h; }
   a.gcnt = ptr<int>(c->b_gcnt);
@@ -1062,6 +1069,7 @@ void launch_conv_tcr(DdkCtx* c, int layer, const float* x_in, float* x_out, cuda
   {
     FinTcrArgs f;
     f.N = lig_only ? c->NL : c->N; f.dout = li.dout; f.nroles = nroles;   // ligand nodes come first
+    f.NL = c->NL; f.sub = tcr_split_sub(); f.extra = 2 * c->N;
     f.seg_cnt = ptr<int>(c->b_seg_cnt);
     f.part = ptr<float>(c->b_part);
     f.roles = a.roles;

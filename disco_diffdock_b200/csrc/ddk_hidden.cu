@@ -144,7 +144,7 @@ void launch_edge_hidden(DdkCtx* c, int layer, cudaStream_t st, int mode) {
   HidArgs a;
   a.NL = c->NL;
   a.glist = ptr<int4>(c->b_glist);
-  a.goff[0] = 0; a.goff[1] = c->NL; a.goff[2] = 2 * c->NL; a.goff[3] = 2 * c->NL + c->NR;
+  a.goff[0] = 0; a.goff[1] = glist_off_group1(c); a.goff[2] = 2 * c->NL; a.goff[3] = 2 * c->NL + c->NR;
   for (int g = 0; g < 4; ++g) a.gci[g] = g;
   if (mode >= CONV_NEEDED) { const int h = mode - CONV_NEEDED; a.goff[2] = 2 * c->NL + 2 * c->NR + h * c->NR; a.gci[2] = 4 + h; }
   a.gcnt = ptr<int>(c->b_gcnt);

@@ -72,6 +72,10 @@ constexpr int TC_MIN_CHUNKS = 8;            // segments with at least this many 
 constexpr int TCR_MAXROLES = 5;     // roles per level
 constexpr int TCR_MAXACC = 8;       // accumulator slots in tensor memory
 constexpr int TCR_WMAX = 36240 + 192;     // floats of the largest resident weight slice (level 3, scalar classes, 24 hidden units + bias)
+constexpr int TCR_SUB = 64;         // k_conv_tcr: a lig<-rec segment is accumulated in pieces of at most this many edges (short accumulation chains: the
+                                    // tensor core adds with truncation); piece 0 writes the segment's record, piece p > 0 the
+                                    // record 2 N + (TCR_PMAX - 1) * ligand node + p - 1
+constexpr int TCR_PMAX = 16;        // pieces per segment at most (the last piece takes the rest)
 constexpr int TCR_PS = 144;         // floats of the partial record of one (segment, role): 8 contraction warps x 18
 constexpr int TCR_MAXSRC = 8;       // shares of one output column inside a record
 struct alignas(16) TcrRole {
@@ -222,6 +226,9 @@ void build_tcr_weights(const LayerInfo& li, const TcrRole& R, const float* w2p, 
 void launch_conv_tcr(DdkCtx* c, int layer, const float* x_in, float* x_out, cudaStream_t st, int mode);
 void launch_conv_finalize(DdkCtx* c, int layer, const float* x_in, float* x_out, cudaStream_t st, bool lig_only, int nsl);
 int host_tcr_roles_check();
+int tcr_split_sub();                       // edges per piece of a lig<-rec segment (0: segments are not split; only k_conv_tcr splits)
+int glist_split_off(const DdkCtx* c);      // region of b_glist behind the work lists and the needed-hop lists
+int glist_off_group1(const DdkCtx* c);     // where work list 1 lives in b_glist (its own region while it is listed in pieces)
 void host_tc_split_rn(float a, uint32_t* hi, uint32_t* lo);
 void host_kabsch(const float* A, const float* Bp, int N, float* R9, float* t3);   // host build of the device routine (tests)
 void host_axis_angle(const float* aa, float* R9);   // opt-in dynamic shared memory sizes (once per process / device)

@@ -12,18 +12,18 @@ we found and ANGSTROMS apart with noise on.  Hence three kinds of checks:
 Every check runs with the three conv-kernel choices (DDK_TC / ddk_debug_set_tc): 0 = fp32 FFMA2 kernels only, 1 = FFMA2 +
 k_acc_tc, 2 = k_conv_tcr (default, everything on the tensor cores).  What was measured on the B200 (gpurun_out/diag_pre_*.json):
 
-    mode                         forward scores    teacher-forced scores / pose after one step    free-running 20-step ODE
-    0  fp32 FMA                  3.9e-6            1.8e-5 / 5.1e-5 A                              2.5e-4 A
-    1  + k_acc_tc (3xTF32)       5.7e-5            7.0e-5 / 3.1e-4 A                              9.6e-3 A
-    2  k_conv_tcr (3xTF32)       5.9e-5            7.6e-5 / 3.1e-4 A                              9.6e-3 A (2.6e-3 A with an
-                                                                                                  earlier summation order of the same kernel)
+    mode                                        forward scores    teacher-forced scores / pose after one step    free-running 20-step ODE
+    0  fp32 FMA                                 3.9e-6            1.8e-5 / 5.1e-5 A                              2.5e-4 A
+    1  + k_acc_tc (3xTF32, whole segments)      5.7e-5            7.0e-5 / 3.1e-4 A                              9.6e-3 A
+    2  k_conv_tcr (3xTF32, pieces of 64 edges)  1.1e-5            1.9e-5 / 6.9e-5 A                              6.9e-4 A
+       k_conv_tcr with whole segments           5.9e-5            7.7e-5 / 3.1e-4 A                              9.6e-3 A   (DDK_TCR_SUB=0)
 
-i.e. with these weights (cancellation: activations of 3e2 .. 8e2 produce scores of 0.1) the 3xTF32 accumulation -- two TF32 words
-hold 22 of the 24 mantissa bits of an operand, and the tensor core accumulates with truncation -- is about 15x noisier than the
-fp32 FMA chain, and this trajectory amplifies any noise ~100x (the oracle's own spread).  The north_star tolerance (1e-3 A) is
-asserted for mode 0, which is the path to select (DDK_TC=0) when bit-level agreement on ill-conditioned trajectories matters; the
-tensor-core modes are held to the stated looser bounds here and to 1e-3 A in the well-conditioned fresh-weight regime
-(tests/test_gpu_parity.py).
+The tensor core adds into its fp32 accumulator with truncation: a 230-edge lig<-rec segment is a chain of 87 truncating updates,
+whose bias -- not the 22-bit operand split -- is what made the 3xTF32 paths 15x noisier than the fp32 FMA chain with these weights
+(cancellation: activations of 3e2 .. 8e2 produce scores of 0.1; this trajectory amplifies any noise ~100x, the oracle's own spread).
+k_conv_tcr therefore accumulates those segments in pieces of 64 edges (24 updates each) whose contracted outputs are added in fp32:
+it holds the north_star tolerance (1e-3 A) here like the all-fp32 mode 0; mode 1 (whole segments through k_acc_tc) is held to the
+stated looser bound, and every mode to 1e-3 A in the well-conditioned fresh-weight regime (tests/test_gpu_parity.py).
 """
 import copy
 import os
@@ -58,7 +58,7 @@ def _need_cuda():
 # per mode: forward scores (truly relative), teacher-forced scores, pose after one teacher-forced step [A], free-running ODE [A]
 TOL = {0: dict(fwd=2e-5, teacher=5e-5, step=1e-4, free=1e-3),
        1: dict(fwd=2e-4, teacher=2e-4, step=1e-3, free=3e-2),
-       2: dict(fwd=2e-4, teacher=2e-4, step=1e-3, free=3e-2)}
+       2: dict(fwd=2e-5, teacher=5e-5, step=1e-4, free=1e-3)}
 
 
 def true_rel(got, want):

@@ -13,6 +13,8 @@
 // Level 3: roles {1o}, {1e} (108 rows x all 72 hidden units + the ones column) and {0e, 0o} x three thirds of the hidden units
 // (60 rows x 24 + ones); the lower levels analogously with the scalar classes in halves (build_tcr_roles).  Every segment is visited
 // once per role; each visit writes a partial record (TCR_PS floats) that k_conv_finalize_tcr adds in a fixed order.
+// The long lig<-rec segments are listed in pieces of at most TCR_SUB edges (k_build_group_lists): the tensor core updates its fp32
+// accumulator with truncation, and short chains keep that one-sided error at the level of the fp32 FMA chain.
 // Scheduling: per (edge group, role) a cursor into the group's segment list; a CTA claims the next block of the role of its group
 // whose cursor is furthest behind, so the roles walk the list side by side (later visits of an edge hit L2) and finish together.
 // Warp roles inside a CTA (768 threads):

@@ -418,7 +418,8 @@ def main():
             'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic, fresh-init weights (seeded)',
             'arithmetic': {'2': 'fp32 in / out; the outer-product accumulations of the conv layers as 3xTF32 split products (hi*hi + hi*lo '
-                                '+ lo*hi, fp32 accumulators in tensor memory) on tcgen05, everything else fp32 FMA (k_conv_tcr)',
+                                '+ lo*hi, fp32 accumulators in tensor memory, chains of at most 64 edges) on tcgen05, everything else fp32 '
+                                'FMA (k_conv_tcr)',
                            '1': 'fp32 FMA (k_conv_fused); the long lig<-rec segments as 3xTF32 split products on tcgen05 (k_acc_tc)',
                            '0': 'fp32 FMA throughout (k_conv_fused)'}[os.environ.get('DDK_TC', '2') if os.environ.get('DDK_TC', '2') in '012' else '2'],
             'config': workload_config(args.workload, n_complex),
@@ -452,7 +453,7 @@ def main():
         ms0 = reduce_max(R0['ms_local'])
         line['strict_fp32'] = {'value': n_poses * world * a0.steps / (ms0 / 1000), 'unit': 'poses/s', 'steps': a0.steps, 'conv_path': 'DDK_TC=0',
                                'note': 'conv layers on k_conv_fused (packed fp32 FMA) only; the headline runs them as 3xTF32 split '
-                                       'products on tcgen05 (k_conv_tcr), DESIGN.md section 2 for what each holds'}
+                                       'products on tcgen05 (k_conv_tcr); both hold the 1e-3 A bound in the pretrained regime (DESIGN.md section 2)'}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         cpu_reference_run(args.workload, complexes, sd, cfg, [(0, 0)], 1, threads)
